@@ -1,0 +1,144 @@
+// Host-side planning + launch of one conv_umma_kernel instance: picks the tile configuration, encodes the
+// two TMA descriptors once (buffers are owned by the engine, so addresses are stable) and replays the launch.
+#pragma once
+#include <string>
+
+#include "conv_tcgen05.cuh"
+#include "tmap.cuh"
+
+namespace bp {
+
+struct ConvDesc {
+  // input activation, NHWC fp16 (for matrix mode: N=1, H=1, W=rows, C=K)
+  const __half* x = nullptr;
+  int N = 0, H = 0, W = 0, C = 0, x_pitch = 0;
+  // weights [Cout_pad][R][S][C] fp16 (row pitch w_pitch elements, >= R*S*C, multiple of 8), bias [Cout_pad] fp32
+  const __half* w = nullptr;
+  const float* bias = nullptr;
+  int w_pitch = 0;
+  int Cout = 0, Cout_pad = 0;
+  int R = 1, S = 1, stride = 1, pad = 0;
+  int act = ACT_NONE;
+  const __half* res = nullptr;
+  int res_pitch = 0, res_mode = RES_NONE;
+  void* out = nullptr;
+  int out_pitch = 0, out_coff = 0, out_f32 = 0, store_mode = STORE_PLAIN;
+  int force_block_n = 0;  // 0 = heuristic
+  int force_stages = 0;
+};
+
+struct ConvPlan {
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
+  ConvArgs args;
+  int block_n = 0, block_k = 0, stages = 0, grid = 0;
+  int P = 0, Q = 0;
+  double flops = 0;
+};
+
+template <int BN, int BK, int ST>
+inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, BK, ST>;
+  static bool attr_done = false;  // per-instantiation; set once per process (single device per process)
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  conv_umma_kernel<BN, BK, ST><<<pl.grid, 128, Cfg::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pl.args);
+  return cudaGetLastError();
+}
+
+inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
+#define BP_CASE(BN, BK, ST) \
+  if (pl.block_n == BN && pl.block_k == BK && pl.stages == ST) return launch_cfg<BN, BK, ST>(pl, st);
+  BP_CASE(256, 64, 4)
+  BP_CASE(256, 64, 2)
+  BP_CASE(128, 64, 6)
+  BP_CASE(128, 64, 3)
+  BP_CASE(64, 64, 4)
+  BP_CASE(32, 64, 4)
+  BP_CASE(64, 32, 4)
+  BP_CASE(32, 32, 4)
+#undef BP_CASE
+  return cudaErrorInvalidConfiguration;
+}
+
+inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::string* err) {
+  const int P = (d.H + 2 * d.pad - d.R) / d.stride + 1;
+  const int Q = (d.W + 2 * d.pad - d.S) / d.stride + 1;
+  const int M = d.N * P * Q;
+  const bool matrix = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad == 0);
+  // matrix mode may have a ragged K (explicit im2col of the 3-channel stems): TMA zero-fills the tail
+  const int block_k = matrix ? (d.C >= 64 ? 64 : 32) : ((d.C % 64 == 0) ? 64 : 32);
+  if (!matrix && d.C % 32 != 0) {
+    if (err) *err = "im2col conv needs Cin % 32 == 0";
+    return false;
+  }
+  int bn = d.force_block_n;
+  if (!bn) {
+    bn = 32;
+    while (bn < d.Cout && bn < 256) bn *= 2;
+    if (block_k == 32 && bn > 64) bn = 64;
+    // keep the grid reasonably full on small layers
+    while (bn > 64 && (long)((M + 127) / 128) * ((d.Cout + bn - 1) / bn) < 148) bn /= 2;
+  }
+  if (d.Cout_pad % bn != 0) {
+    if (err) *err = "Cout_pad must be a multiple of BLOCK_N";
+    return false;
+  }
+  int st = d.force_stages;
+  if (!st) st = bn == 256 ? 4 : (bn == 128 ? 3 : 4);
+  const int K = d.R * d.S * d.C;
+  const int num_kb = (K + block_k - 1) / block_k;
+
+  pl->block_n = bn;
+  pl->block_k = block_k;
+  pl->stages = st;
+  pl->P = P;
+  pl->Q = Q;
+  const int n_tiles = d.Cout_pad / bn;
+  // tiles whose channels are all padding are never launched
+  const int n_tiles_live = (d.Cout + bn - 1) / bn;
+  pl->grid = ((M + 127) / 128) * n_tiles_live;
+  (void)n_tiles;
+  pl->flops = 2.0 * M * (double)d.Cout * K;
+
+  ConvArgs& a = pl->args;
+  a.M = M;
+  a.n_tiles = n_tiles_live;
+  a.num_kb = num_kb;
+  a.a_im2col = matrix ? 0 : 1;
+  a.P = P;
+  a.Q = Q;
+  a.stride = d.stride;
+  a.pad = d.pad;
+  a.S = d.S;
+  a.cblocks = d.C / block_k;
+  a.Cout = d.Cout;
+  a.act = d.act;
+  a.res_mode = d.res ? d.res_mode : RES_NONE;
+  a.store_mode = d.store_mode;
+  a.out_f32 = d.out_f32;
+  a.out_pitch = d.out_pitch;
+  a.out_coff = d.out_coff;
+  a.res_pitch = d.res_pitch;
+  a.bias = d.bias;
+  a.res = d.res;
+  a.out = d.out;
+
+  if (matrix) {
+    if (!make_tmap_2d(api, &pl->tmA, d.x, (uint64_t)M, (uint64_t)d.C, (uint64_t)d.x_pitch, 128, block_k, err))
+      return false;
+  } else {
+    if (!make_tmap_im2col(api, &pl->tmA, d.x, d.N, d.H, d.W, d.C, d.x_pitch, d.R, d.S, d.stride, d.pad, block_k,
+                          err))
+      return false;
+  }
+  if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn, block_k, err))
+    return false;
+  return true;
+}
+
+}  // namespace bp

@@ -1,0 +1,371 @@
+// Stand-alone bring-up harness for conv_umma_kernel (no torch, no python): checks the tcgen05/TMA conv against a
+// naive fp32 GPU reference over the shape/epilogue matrix the two networks need, probes the im2col TMA
+// semantics, and times a few production shapes.  Build: see betapose_b200/csrc/Makefile (target conv_harness).
+//   ./conv_harness            -> correctness matrix + timings
+//   ./conv_harness probe      -> im2col probe only
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../betapose_b200/csrc/conv_plan.cuh"
+
+using namespace bp;
+
+#define CK(x)                                                                        \
+  do {                                                                               \
+    cudaError_t e_ = (x);                                                            \
+    if (e_ != cudaSuccess) {                                                         \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                       \
+    }                                                                                \
+  } while (0)
+
+// ------------------------------------------------------------------ naive reference
+__global__ void ref_conv_kernel(const __half* x, int N, int H, int W, int C, int xp, const __half* w, int wp,
+                                const float* bias, int R, int S, int stride, int pad, int P, int Q, int Cout, int act,
+                                const __half* res, int rp, int res_mode, float* out) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)N * P * Q * Cout;
+  if (idx >= total) return;
+  const int co = idx % Cout;
+  const long m = idx / Cout;
+  const int q = m % Q;
+  const int p = (m / Q) % P;
+  const int n = m / ((long)P * Q);
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const int h = p * stride - pad + r;
+    if (h < 0 || h >= H) continue;
+    for (int s = 0; s < S; ++s) {
+      const int ww = q * stride - pad + s;
+      if (ww < 0 || ww >= W) continue;
+      const __half* xr = x + (((long)n * H + h) * W + ww) * xp;
+      const __half* wr = w + (long)co * wp + (r * S + s) * C;
+      for (int c = 0; c < C; ++c) acc += __half2float(xr[c]) * __half2float(wr[c]);
+    }
+  }
+  float v = acc + bias[co];
+  float rv = res ? __half2float(res[m * rp + co]) : 0.f;
+  if (res && res_mode == RES_BEFORE_ACT) v += rv;
+  v = act == ACT_LEAKY ? (v > 0 ? v : 0.1f * v) : act == ACT_RELU ? fmaxf(v, 0.f) : act == ACT_SIGMOID ? 1.f / (1.f + expf(-v)) : v;
+  if (res && res_mode == RES_AFTER_ACT) v += rv;
+  out[idx] = v;
+}
+
+// ------------------------------------------------------------------ im2col probe
+__global__ void probe_kernel(const __grid_constant__ CUtensorMap tm, int c, int w, int h, int n, int offw, int offh,
+                             __half* out, int bytes) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, bytes);
+    tma_load_im2col_4d(&tm, &bar, s, c, w, h, n, (uint16_t)offw, (uint16_t)offh);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < bytes / 2; i += blockDim.x) out[i] = reinterpret_cast<__half*>(s)[i];
+}
+
+struct Rng {  // xorshift32: fast enough to fill the batch-64 tensors
+  uint32_t s;
+  explicit Rng(unsigned seed) : s(seed ? seed : 1u) {}
+  float uni(float a, float b) {
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    return a + (b - a) * ((s >> 8) * (1.0f / 16777216.0f));
+  }
+};
+
+static TmapApi g_api;
+
+struct Case {
+  const char* name;
+  int N, H, W, C, Cout, R, S, stride, pad;
+  int act = ACT_LEAKY, res_mode = RES_NONE, store_mode = STORE_PLAIN, out_f32 = 0;
+  int x_pitch_extra = 0, out_pitch_extra = 0, out_coff = 0;
+  int force_bn = 0, force_st = 0;
+  int iters = 0;  // >0: also time it
+};
+
+static int run_case(const Case& cs) {
+  Rng rng(1234);
+  const int xp = cs.C + cs.x_pitch_extra;
+  const int K = cs.R * cs.S * cs.C;
+  const int wp = (K + 7) / 8 * 8;
+  const int Cout_pad = (cs.Cout + 255) / 256 * 256;
+  const int P = (cs.H + 2 * cs.pad - cs.R) / cs.stride + 1, Q = (cs.W + 2 * cs.pad - cs.S) / cs.stride + 1;
+  const long M = (long)cs.N * P * Q;
+  std::vector<__half> hx((size_t)cs.N * cs.H * cs.W * xp), hw((size_t)Cout_pad * wp, __float2half(0.f));
+  std::vector<float> hb(Cout_pad, 0.f);
+  for (auto& v : hx) v = __float2half(rng.uni(-1.f, 1.f));
+  const float ws = 1.0f / sqrtf((float)K);
+  for (int co = 0; co < cs.Cout; ++co)
+    for (int k = 0; k < K; ++k) hw[(size_t)co * wp + k] = __float2half(rng.uni(-1.f, 1.f) * ws * 1.7f);
+  for (int co = 0; co < cs.Cout; ++co) hb[co] = rng.uni(-0.5f, 0.5f);
+  std::vector<__half> hres;
+  if (cs.res_mode != RES_NONE) {
+    hres.resize((size_t)M * cs.Cout);
+    for (auto& v : hres) v = __float2half(rng.uni(-1.f, 1.f));
+  }
+  // output geometry
+  const int up = cs.store_mode != STORE_PLAIN ? 2 : 1;
+  const int oc = cs.store_mode == STORE_PIXSHUF2 ? cs.Cout / 4 : cs.Cout;
+  const int opitch = oc + cs.out_coff + cs.out_pitch_extra;
+  const size_t out_elems = (size_t)cs.N * P * up * Q * up * opitch;
+  const size_t esz = cs.out_f32 ? 4 : 2;
+
+  __half *dx, *dw, *dres = nullptr;
+  float *db, *dref;
+  void* dout;
+  CK(cudaMalloc(&dx, hx.size() * 2));
+  CK(cudaMalloc(&dw, hw.size() * 2));
+  CK(cudaMalloc(&db, hb.size() * 4));
+  CK(cudaMalloc(&dref, (size_t)M * cs.Cout * 4));
+  CK(cudaMalloc(&dout, out_elems * esz));
+  CK(cudaMemset(dout, 0xFF, out_elems * esz));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+  if (!hres.empty()) {
+    CK(cudaMalloc(&dres, hres.size() * 2));
+    CK(cudaMemcpy(dres, hres.data(), hres.size() * 2, cudaMemcpyHostToDevice));
+  }
+
+  ConvDesc d;
+  d.x = dx; d.N = cs.N; d.H = cs.H; d.W = cs.W; d.C = cs.C; d.x_pitch = xp;
+  d.w = dw; d.bias = db; d.w_pitch = wp; d.Cout = cs.Cout; d.Cout_pad = Cout_pad;
+  d.R = cs.R; d.S = cs.S; d.stride = cs.stride; d.pad = cs.pad; d.act = cs.act;
+  d.res = dres; d.res_pitch = cs.Cout; d.res_mode = cs.res_mode;
+  d.out = dout; d.out_pitch = opitch; d.out_coff = cs.out_coff; d.out_f32 = cs.out_f32; d.store_mode = cs.store_mode;
+  d.force_block_n = cs.force_bn; d.force_stages = cs.force_st;
+  ConvPlan pl;
+  std::string err;
+  if (!conv_plan_build(g_api, &pl, d, &err)) {
+    printf("[%-28s] PLAN FAILED: %s\n", cs.name, err.c_str());
+    return 1;
+  }
+  cudaError_t le = conv_plan_launch(pl, 0);
+  cudaError_t se = cudaDeviceSynchronize();
+  if (le != cudaSuccess || se != cudaSuccess) {
+    printf("[%-28s] LAUNCH/RUN FAILED: %s / %s (bn=%d bk=%d st=%d grid=%d)\n", cs.name, cudaGetErrorString(le),
+           cudaGetErrorString(se), pl.block_n, pl.block_k, pl.stages, pl.grid);
+    exit(3);  // context is likely poisoned
+  }
+  {
+    const long total = M * cs.Cout;
+    ref_conv_kernel<<<(unsigned)((total + 255) / 256), 256>>>(dx, cs.N, cs.H, cs.W, cs.C, xp, dw, wp, db, cs.R, cs.S,
+                                                             cs.stride, cs.pad, P, Q, cs.Cout, cs.act, dres, cs.Cout,
+                                                             cs.res_mode, dref);
+    CK(cudaDeviceSynchronize());
+  }
+  std::vector<float> href((size_t)M * cs.Cout);
+  CK(cudaMemcpy(href.data(), dref, href.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> hout(out_elems * esz);
+  CK(cudaMemcpy(hout.data(), dout, hout.size(), cudaMemcpyDeviceToHost));
+  auto get = [&](size_t i) -> float {
+    return cs.out_f32 ? reinterpret_cast<float*>(hout.data())[i] : __half2float(reinterpret_cast<__half*>(hout.data())[i]);
+  };
+  double max_err = 0, max_ref = 0;
+  long bad = 0, first_bad = -1;
+  for (long m = 0; m < M; ++m) {
+    const int q = m % Q, p = (m / Q) % P, n = m / ((long)P * Q);
+    for (int co = 0; co < cs.Cout; ++co) {
+      const float r = href[(size_t)m * cs.Cout + co];
+      int ndst = 1;
+      size_t dst[4];
+      if (cs.store_mode == STORE_PLAIN) {
+        dst[0] = (size_t)m * opitch + cs.out_coff + co;
+      } else if (cs.store_mode == STORE_UPSAMPLE2) {
+        ndst = 4;
+        for (int k = 0; k < 4; ++k)
+          dst[k] = (((size_t)n * 2 * P + 2 * p + (k >> 1)) * 2 * Q + 2 * q + (k & 1)) * opitch + cs.out_coff + co;
+      } else {
+        // harness weights are NOT permuted: channel index co is already "o' = sub*C4 + c"
+        const int c4 = cs.Cout / 4, sub = co / c4, cc = co % c4;
+        dst[0] = (((size_t)n * 2 * P + 2 * p + (sub >> 1)) * 2 * Q + 2 * q + (sub & 1)) * opitch + cs.out_coff + cc;
+      }
+      for (int k = 0; k < ndst; ++k) {
+        const float g = get(dst[k]);
+        const double e = fabs((double)g - r);
+        const double tol = 2e-2 + 4e-3 * fabs(r);
+        if (!(e <= tol)) {
+          if (first_bad < 0) first_bad = m * cs.Cout + co;
+          ++bad;
+        }
+        if (e > max_err || e != e) max_err = e;
+        if (fabs(r) > max_ref) max_ref = fabs(r);
+      }
+    }
+  }
+  double ms = 0;
+  if (cs.iters > 0 && bad == 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) conv_plan_launch(pl, 0);
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < cs.iters; ++i) conv_plan_launch(pl, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float t;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    ms = t / cs.iters;
+  }
+  printf("[%-28s] bn=%3d bk=%2d st=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", cs.name,
+         pl.block_n, pl.block_k, pl.stages, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
+  if (bad) printf(" first_bad: m=%ld co=%ld", first_bad / cs.Cout, first_bad % cs.Cout);
+  if (ms > 0) printf("  %.3f ms  %.1f TFLOP/s", ms, pl.flops / ms * 1e-9);
+  printf("\n");
+  fflush(stdout);
+  cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dref); cudaFree(dout);
+  if (dres) cudaFree(dres);
+  return bad ? 1 : 0;
+}
+
+// Dump what one im2col TMA load actually fetches, against the expected gather, to pin the coordinate semantics.
+static int run_probe(int N, int H, int W, int C, int R, int S, int stride, int pad, int m0, int fr, int fs) {
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  std::vector<__half> hx((size_t)N * H * W * C);
+  // value encodes (n,h,w) exactly in fp16 range: v = n*512 + h*20 + w  (small dims), channel adds 0
+  for (int n = 0; n < N; ++n)
+    for (int h = 0; h < H; ++h)
+      for (int w = 0; w < W; ++w)
+        for (int c = 0; c < C; ++c) hx[(((size_t)n * H + h) * W + w) * C + c] = __float2half(float(n * 512 + h * 20 + w + 1));
+  __half *dx, *dout;
+  CK(cudaMalloc(&dx, hx.size() * 2));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  const int bk = 64;
+  const int bytes = 128 * bk * 2;
+  CK(cudaMalloc(&dout, bytes));
+  alignas(64) CUtensorMap tm;
+  std::string err;
+  if (!make_tmap_im2col(g_api, &tm, dx, N, H, W, C, C, R, S, stride, pad, bk, &err)) {
+    printf("probe: tmap failed %s\n", err.c_str());
+    return 1;
+  }
+  const int img = m0 / (P * Q), rem = m0 % (P * Q), op = rem / Q, oq = rem % Q;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + 1024));
+  probe_kernel<<<1, 128, bytes + 1024>>>(tm, 0, oq * stride - pad, op * stride - pad, img, fs, fr, dout, bytes);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("probe: kernel failed: %s\n", cudaGetErrorString(e));
+    exit(3);
+  }
+  std::vector<__half> ho(bytes / 2);
+  CK(cudaMemcpy(ho.data(), dout, bytes, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  printf("probe N=%d H=%d W=%d R=%d S=%d stride=%d pad=%d P=%d Q=%d m0=%d tap=(%d,%d)\n", N, H, W, R, S, stride, pad,
+         P, Q, m0, fr, fs);
+  for (int i = 0; i < 128; ++i) {
+    const int m = m0 + i;
+    float expect = 0.f;
+    if (m < N * P * Q) {
+      const int n = m / (P * Q), r2 = m % (P * Q), p = r2 / Q, q = r2 % Q;
+      const int h = p * stride - pad + fr, w = q * stride - pad + fs;
+      if (h >= 0 && h < H && w >= 0 && w < W) expect = float(n * 512 + h * 20 + w + 1);
+    }
+    // 128B swizzle: 16B chunk index XOR (row & 7); read chunk 0 of the logical row
+    const int chunk = 0 ^ (i & 7);
+    const float got = __half2float(ho[(size_t)i * 64 + chunk * 8]);
+    if (got != expect) {
+      if (bad < 24) printf("  row %3d: got %6.0f expect %6.0f\n", i, got, expect);
+      ++bad;
+    }
+  }
+  printf("probe result: %d/128 rows mismatched\n", bad);
+  cudaFree(dx);
+  cudaFree(dout);
+  return bad ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+  std::string err;
+  CK(cudaSetDevice(0));
+  CK(cudaFree(0));
+  if (!g_api.load(&err)) {
+    printf("tmap api: %s\n", err.c_str());
+    return 2;
+  }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s sm_%d%d, %d SMs, driver %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
+         g_api.driver_version);
+  const bool probe_only = argc > 1 && !strcmp(argv[1], "probe");
+  const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+  int fails = 0;
+
+  if (!probe_only) {
+    // 1) plain GEMM path (2-D TMA only) first: isolates descriptor/idesc/TMEM plumbing from im2col
+    std::vector<Case> gemm = {
+        {"gemm 1x1 C64->128 bn128", 1, 1, 1000, 64, 128, 1, 1, 1, 0},
+        {"gemm 1x1 C256->256 bn256", 2, 20, 16, 256, 256, 1, 1, 1, 0},
+        {"gemm 1x1 C512->64", 1, 13, 13, 512, 64, 1, 1, 1, 0},
+        {"gemm 1x1 C1024->18 f32", 2, 13, 13, 1024, 18, 1, 1, 1, 0, ACT_NONE, RES_NONE, STORE_PLAIN, 1, 0, 14},
+        {"gemm K=27 ragged bk32", 1, 1, 3000, 27, 32, 1, 1, 1, 0},
+        {"gemm K=147 ragged bk64", 1, 1, 3000, 147, 64, 1, 1, 1, 0, ACT_RELU},
+        {"gemm 1x1 C32->64 bk32", 1, 16, 16, 32, 64, 1, 1, 1, 0},
+        {"gemm pitch/coff", 1, 26, 26, 128, 256, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 64, 128, 64},
+        {"gemm res after-act", 1, 26, 26, 128, 256, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT},
+        {"gemm res before-act relu", 1, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT},
+        {"gemm sigmoid (SE fc)", 1, 1, 64, 256, 256, 1, 1, 1, 0, ACT_SIGMOID},
+        {"gemm upsample2 store", 2, 13, 13, 512, 256, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_UPSAMPLE2, 0, 0, 512, 0},
+        {"gemm bn256 st2", 2, 20, 16, 256, 512, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 256, 2},
+        {"gemm bn128 st6", 2, 20, 16, 256, 512, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 128, 6},
+    };
+    for (auto& c : gemm) fails += run_case(c);
+  }
+
+  // 2) im2col probes (cheap, very informative if the conv cases below fail)
+  int pf = 0;
+  pf += run_probe(2, 13, 13, 64, 3, 3, 1, 1, 0, 0, 0);
+  pf += run_probe(2, 13, 13, 64, 3, 3, 1, 1, 128, 1, 2);
+  pf += run_probe(2, 13, 13, 64, 3, 3, 1, 1, 256, 2, 2);
+  pf += run_probe(2, 16, 16, 64, 3, 3, 2, 1, 0, 0, 0);
+  pf += run_probe(2, 16, 16, 64, 3, 3, 2, 1, 0, 2, 1);
+  pf += run_probe(3, 15, 11, 64, 1, 1, 2, 0, 0, 0, 0);
+  printf("probe failures: %d\n", pf);
+  if (probe_only) return pf ? 1 : 0;
+
+  std::vector<Case> conv = {
+      {"3x3 s1 C64->128 13x13", 2, 13, 13, 64, 128, 3, 3, 1, 1},
+      {"3x3 s1 C128->256 52x52", 1, 52, 52, 128, 256, 3, 3, 1, 1},
+      {"3x3 s2 C128->256 26x26", 2, 26, 26, 128, 256, 3, 3, 2, 1},
+      {"3x3 s2 C32->64 bk32", 1, 32, 32, 32, 64, 3, 3, 2, 1},
+      {"3x3 s1 C32->64 bk32", 1, 24, 24, 32, 64, 3, 3, 1, 1},
+      {"1x1 s2 C256->512 40x32", 2, 40, 32, 256, 512, 1, 1, 2, 0, ACT_NONE},
+      {"3x3 s2 C128->128 80x64", 1, 80, 64, 128, 128, 3, 3, 2, 1, ACT_RELU},
+      {"3x3 pixshuf C512->1024", 1, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2},
+      {"3x3 C128->50 f32 head", 1, 80, 64, 128, 50, 3, 3, 1, 1, ACT_NONE, RES_NONE, STORE_PLAIN, 1, 0, 14},
+      {"3x3 s1 x_pitch 768", 1, 26, 26, 512, 256, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 256},
+      {"3x3 s1 C512->1024 res", 2, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT},
+  };
+  for (auto& c : conv) fails += run_case(c);
+
+  if (!quick && fails == 0) {
+    printf("---- timing (batch 64 production shapes) ----\n");
+    std::vector<Case> perf = {
+        {"Y 3x3 128->256 @52 B64", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 128->256 @52 bn128", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 3, 10},
+        {"Y 3x3 128->256 @52 bn256s2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 2, 10},
+        {"Y 1x1 256->128 @52 B64", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 256->512 @26 B64", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 512->1024 @13 B64", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 512->1024 @13 bn128", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 6, 10},
+        {"Y 3x3 32->64 s2 @416", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
+        {"K 3x3 256->256 @20x16", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K 1x1 256->1024 @20x16", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_NONE, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K 1x1 1024->256 @20x16", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K 1x1 64->256 @80x64", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_NONE, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+    };
+    for (auto& c : perf) fails += run_case(c);
+  }
+  printf("TOTAL FAILURES: %d\n", fails);
+  return fails ? 1 : 0;
+}
