@@ -308,8 +308,8 @@ int main(int argc, char** argv) {
         {"gemm 1x1 C256->256 bn256", 2, 20, 16, 256, 256, 1, 1, 1, 0},
         {"gemm 1x1 C512->64", 1, 13, 13, 512, 64, 1, 1, 1, 0},
         {"gemm 1x1 C1024->18 f32", 2, 13, 13, 1024, 18, 1, 1, 1, 0, ACT_NONE, RES_NONE, STORE_PLAIN, 1, 0, 14},
-        {"gemm K=27 ragged bk32", 1, 1, 3000, 27, 32, 1, 1, 1, 0},
-        {"gemm K=147 ragged bk64", 1, 1, 3000, 147, 64, 1, 1, 1, 0, ACT_RELU},
+        {"gemm K=27 ragged bk32", 1, 1, 3000, 27, 32, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 5},
+        {"gemm K=147 ragged bk64", 1, 1, 3000, 147, 64, 1, 1, 1, 0, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 5},
         {"gemm 1x1 C32->64 bk32", 1, 16, 16, 32, 64, 1, 1, 1, 0},
         {"gemm pitch/coff", 1, 26, 26, 128, 256, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 64, 128, 64},
         {"gemm res after-act", 1, 26, 26, 128, 256, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT},
