@@ -1,0 +1,474 @@
+// bp_net: ordered list of fused layer ops over NHWC fp16 tensors (C-ABI in include/betapose_b200.h).
+// Build time: BN folding (fp64), weight packing to [Cout_pad][R][S][Cin] fp16, buffer allocation, TMA
+// descriptor encoding for max_batch.  Run time: one kernel launch per op, no host sync, graph-capturable.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "betapose_b200.h"
+#include "conv_plan.cuh"
+#include "engine.h"
+
+using namespace bp;
+
+namespace {
+
+enum OpKind { OP_CONV, OP_IM2COL, OP_MAXPOOL, OP_AVGPOOL, OP_SCALE_ADD_RELU, OP_PIXSHUF, OP_UPSAMPLE, OP_COPYC, OP_ADD };
+
+struct Tensor {
+  void* ptr = nullptr;  // includes the channel offset
+  int H = 0, W = 0, C = 0, pitch = 0, coff = 0;
+  bool f32 = false;
+  int in_kind = -1;  // >= 0 for the network input
+};
+
+struct Op {
+  OpKind kind;
+  ConvPlan plan;  // OP_CONV
+  int pq = 0;     // output pixels per image (conv) for batch scaling
+  int n_tiles = 1;
+  int a = -1, b = -1, c = -1, dst = -1;  // tensor ids for aux ops
+  // im2col
+  int ksize = 0, stride = 0, pad = 0, P = 0, Q = 0, kpitch = 0;
+  __half* col = nullptr;
+  double flops = 0, bytes = 0;  // per image
+  std::string desc;
+};
+
+}  // namespace
+
+struct bp_net {
+  bp_engine* eng = nullptr;
+  bp_net* share = nullptr;
+  int max_batch = 0;
+  int in_kind = 0;
+  std::vector<Tensor> tensors;
+  std::vector<Op> ops;
+  std::vector<void*> owned;       // device allocations owned by this net
+  std::vector<void*> act_buffers; // activation buffers in allocation order (for sharing)
+  std::vector<size_t> act_sizes;
+  size_t act_cursor = 0;
+  double flops = 0;
+};
+
+static void* net_alloc_weights(bp_net* n, size_t bytes) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  n->owned.push_back(p);
+  return p;
+}
+
+// activation buffers: nets with the same topology (one per LineMod object) alias each other's buffers
+static void* net_alloc_act(bp_net* n, size_t bytes) {
+  const size_t i = n->act_cursor++;
+  if (n->share && i < n->share->act_buffers.size() && n->share->act_sizes[i] >= bytes) {
+    n->act_buffers.push_back(n->share->act_buffers[i]);
+    n->act_sizes.push_back(n->share->act_sizes[i]);
+    return n->share->act_buffers[i];
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, bytes);
+  n->owned.push_back(p);
+  n->act_buffers.push_back(p);
+  n->act_sizes.push_back(bytes);
+  return p;
+}
+
+static int new_tensor(bp_net* n, int H, int W, int C, bool f32) {
+  Tensor t;
+  t.H = H; t.W = W; t.C = C; t.f32 = f32;
+  t.pitch = f32 ? (C + 3) / 4 * 4 : (C + 7) / 8 * 8;
+  const size_t bytes = (size_t)n->max_batch * H * W * t.pitch * (f32 ? 4 : 2) + 256;
+  t.ptr = net_alloc_act(n, bytes);
+  if (!t.ptr) return -1;
+  n->tensors.push_back(t);
+  return (int)n->tensors.size() - 1;
+}
+
+static TView view_of(const Tensor& t) { return TView{t.ptr, t.H, t.W, t.C, t.pitch}; }
+
+extern "C" {
+
+int bp_net_create(bp_engine* e, int max_batch, int in_h, int in_w, int in_kind, bp_net* share, bp_net** out) {
+  if (!e || !out || max_batch <= 0) return bp_fail(BP_ERR_INVALID, "bp_net_create: bad arguments");
+  if (in_kind != BP_IN_U8X4 && in_kind != BP_IN_F16X4) return bp_fail(BP_ERR_INVALID, "bp_net_create: in_kind");
+  if (share && share->max_batch < max_batch) return bp_fail(BP_ERR_INVALID, "bp_net_create: shared net is smaller");
+  cudaSetDevice(e->device);
+  bp_net* n = new bp_net();
+  n->eng = e;
+  n->share = share;
+  n->max_batch = max_batch;
+  n->in_kind = in_kind;
+  Tensor t;
+  t.H = in_h; t.W = in_w; t.C = 3; t.pitch = 4; t.in_kind = in_kind;
+  const size_t esz = in_kind == BP_IN_U8X4 ? 1 : 2;
+  t.ptr = net_alloc_act(n, (size_t)max_batch * in_h * in_w * 4 * esz + 256);
+  if (!t.ptr) {
+    delete n;
+    return bp_fail(BP_ERR_CUDA, "bp_net_create: cudaMalloc failed");
+  }
+  n->tensors.push_back(t);
+  *out = n;
+  return BP_OK;
+}
+
+void bp_net_destroy(bp_net* n) {
+  if (!n) return;
+  for (void* p : n->owned) cudaFree(p);
+  delete n;
+}
+
+void* bp_net_input_ptr(bp_net* n) { return n ? n->tensors[0].ptr : nullptr; }
+
+int bp_net_alloc_tensor(bp_net* n, int h, int w, int c) {
+  if (!n) return bp_fail(BP_ERR_INVALID, "null net");
+  const int id = new_tensor(n, h, w, c, false);
+  return id < 0 ? bp_fail(BP_ERR_CUDA, "bp_net_alloc_tensor: cudaMalloc failed") : id;
+}
+
+int bp_net_view(bp_net* n, int tensor, int coff, int c) {
+  if (!n || tensor < 0 || tensor >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_view: tensor id");
+  Tensor t = n->tensors[tensor];
+  if (t.f32 || coff % 8 || c % 8 || coff + c > t.C) return bp_fail(BP_ERR_INVALID, "bp_net_view: window");
+  t.ptr = reinterpret_cast<__half*>(t.ptr) + coff;
+  t.coff += coff;
+  t.C = c;
+  n->tensors.push_back(t);
+  return (int)n->tensors.size() - 1;
+}
+
+int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
+  if (!n || !s || !s->weight) return bp_fail(BP_ERR_INVALID, "bp_net_conv: null argument");
+  if (s->src < 0 || s->src >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_conv: src id");
+  cudaSetDevice(n->eng->device);
+  const Tensor src = n->tensors[s->src];
+  if (src.f32) return bp_fail(BP_ERR_INVALID, "bp_net_conv: fp32 tensors cannot feed a conv");
+  const bool stem = src.in_kind >= 0;
+  const int Cin = src.C, k = s->ksize, Cout = s->cout;
+  const int P = (src.H + 2 * s->pad - k) / s->stride + 1, Q = (src.W + 2 * s->pad - k) / s->stride + 1;
+  if (!stem && Cin % 32 != 0) return bp_fail(BP_ERR_UNSUPPORTED, "bp_net_conv: Cin must be a multiple of 32");
+  if (s->store_mode == BP_STORE_PIXSHUF2 && (Cout % 32 != 0)) return bp_fail(BP_ERR_UNSUPPORTED, "pixel shuffle needs Cout % 32 == 0");
+  if (s->store_mode != BP_STORE_PLAIN && s->out_f32) return bp_fail(BP_ERR_UNSUPPORTED, "fp32 output supports plain stores only");
+  if (s->store_mode != BP_STORE_PLAIN && Cout % 8) return bp_fail(BP_ERR_UNSUPPORTED, "fused stores need Cout % 8 == 0");
+
+  // ---- fold BN (fp64) and pack weights [Cout_pad][R][S][Cin] fp16
+  const int K = k * k * Cin;
+  const int wpitch = (K + 7) / 8 * 8;
+  const int Cout_pad = (Cout + 255) / 256 * 256;
+  std::vector<__half> hw((size_t)Cout_pad * wpitch, __float2half(0.f));
+  std::vector<float> hb(Cout_pad, 0.f);
+  const int c4 = Cout / 4;
+  for (int o = 0; o < Cout; ++o) {
+    double scale = 1.0, shift = s->bias ? (double)s->bias[o] : 0.0;
+    if (s->bn_gamma) {
+      const double inv = (double)s->bn_gamma[o] / std::sqrt((double)s->bn_var[o] + (double)s->bn_eps);
+      scale = inv;
+      shift = (double)s->bn_beta[o] - (double)s->bn_mean[o] * inv + shift * inv;
+    }
+    // PixelShuffle(2) fused store: kernel row o' = sub*(Cout/4) + c holds PyTorch channel o = 4c + sub
+    const int row = s->store_mode == BP_STORE_PIXSHUF2 ? (o % 4) * c4 + o / 4 : o;
+    hb[row] = (float)shift;
+    const float* wsrc = s->weight + (size_t)o * Cin * k * k;
+    __half* wdst = hw.data() + (size_t)row * wpitch;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int r = 0; r < k; ++r)
+        for (int q = 0; q < k; ++q)
+          wdst[(r * k + q) * Cin + ci] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale));
+  }
+  __half* dw = (__half*)net_alloc_weights(n, hw.size() * 2);
+  float* db = (float*)net_alloc_weights(n, hb.size() * 4);
+  if (!dw || !db) return bp_fail(BP_ERR_CUDA, "bp_net_conv: cudaMalloc (weights) failed");
+  if (cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+    return bp_fail(BP_ERR_CUDA, "bp_net_conv: weight upload failed");
+
+  // ---- destination tensor
+  const int up = s->store_mode == BP_STORE_PLAIN ? 1 : 2;
+  const int oc = s->store_mode == BP_STORE_PIXSHUF2 ? Cout / 4 : Cout;
+  int dst = s->dst;
+  int coff = 0;
+  if (dst < 0) {
+    dst = new_tensor(n, P * up, Q * up, oc, s->out_f32 != 0);
+    if (dst < 0) return bp_fail(BP_ERR_CUDA, "bp_net_conv: cudaMalloc (activation) failed");
+  } else {
+    if (dst >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_conv: dst id");
+    const Tensor& d = n->tensors[dst];
+    coff = s->dst_coff;
+    if (d.H != P * up || d.W != Q * up || coff + oc > d.C || coff % 8 || d.f32 != (s->out_f32 != 0))
+      return bp_fail(BP_ERR_INVALID, "bp_net_conv: dst tensor does not fit the output");
+  }
+  const Tensor& dt = n->tensors[dst];
+
+  ConvDesc d;
+  Op col_op;
+  bool have_col = false;
+  if (stem) {
+    // explicit im2col of the 3-channel input, then a plain GEMM over A[M, K]
+    const int kp = (K + 7) / 8 * 8;
+    const size_t bytes = (size_t)n->max_batch * P * Q * kp * 2 + 256;
+    __half* col = (__half*)net_alloc_act(n, bytes);
+    if (!col) return bp_fail(BP_ERR_CUDA, "bp_net_conv: cudaMalloc (im2col) failed");
+    col_op.kind = OP_IM2COL;
+    col_op.a = s->src;
+    col_op.ksize = k; col_op.stride = s->stride; col_op.pad = s->pad; col_op.P = P; col_op.Q = Q; col_op.kpitch = kp;
+    col_op.col = col;
+    col_op.bytes = (double)src.H * src.W * 4 * (src.in_kind == BP_IN_U8X4 ? 1 : 2) + (double)P * Q * kp * 2;
+    char buf[128];
+    snprintf(buf, sizeof buf, "im2col %dx%d/%d 3->K%d @%dx%d", k, k, s->stride, K, P, Q);
+    col_op.desc = buf;
+    have_col = true;
+    d.x = col; d.N = 1; d.H = 1; d.W = n->max_batch * P * Q; d.C = K; d.x_pitch = kp;
+    d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
+  } else {
+    d.x = (const __half*)src.ptr; d.N = n->max_batch; d.H = src.H; d.W = src.W; d.C = Cin; d.x_pitch = src.pitch;
+    d.R = k; d.S = k; d.stride = s->stride; d.pad = s->pad;
+  }
+  d.w = dw; d.bias = db; d.w_pitch = wpitch; d.Cout = Cout; d.Cout_pad = Cout_pad;
+  d.act = s->act;
+  if (s->res >= 0) {
+    if (s->res >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_conv: res id");
+    const Tensor& r = n->tensors[s->res];
+    if (r.f32 || r.H != P || r.W != Q || r.C != Cout || s->store_mode != BP_STORE_PLAIN)
+      return bp_fail(BP_ERR_INVALID, "bp_net_conv: residual tensor shape mismatch");
+    d.res = (const __half*)r.ptr; d.res_pitch = r.pitch; d.res_mode = s->res_mode;
+  }
+  d.out = dt.f32 ? (void*)((float*)dt.ptr) : (void*)((__half*)dt.ptr);
+  d.out_pitch = dt.pitch; d.out_coff = coff; d.out_f32 = s->out_f32; d.store_mode = s->store_mode;
+  if (n->eng->force_block_n) d.force_block_n = n->eng->force_block_n;
+  if (n->eng->force_stages) d.force_stages = n->eng->force_stages;
+
+  Op op;
+  op.kind = OP_CONV;
+  std::string err;
+  if (!conv_plan_build(n->eng->tmap, &op.plan, d, &err)) return bp_fail(BP_ERR_CUDA, ("bp_net_conv: " + err).c_str());
+  if (stem) {
+    // plan was built as a [1,1,M,K] matrix; keep P,Q for the fused-store address math (plain only for stems)
+    op.plan.args.P = P;
+    op.plan.args.Q = Q;
+  }
+  op.pq = P * Q;
+  op.n_tiles = op.plan.args.n_tiles;
+  op.dst = dst;
+  op.flops = 2.0 * P * Q * (double)Cout * K;
+  op.bytes = (stem ? (double)P * Q * ((K + 7) / 8 * 8) * 2 : (double)src.H * src.W * Cin * 2) + (double)K * Cout * 2 / n->max_batch +
+             (double)P * Q * Cout * (s->out_f32 ? 4 : 2) * (s->store_mode == BP_STORE_UPSAMPLE2 ? 4 : 1) +
+             (s->res >= 0 ? (double)P * Q * Cout * 2 : 0.0);
+  char buf[160];
+  snprintf(buf, sizeof buf, "conv %dx%d/%d %d->%d @%dx%d bn%d bk%d st%d%s%s%s", k, k, s->stride, Cin, Cout, P, Q,
+           op.plan.block_n, op.plan.block_k, op.plan.stages, s->res >= 0 ? " +res" : "",
+           s->store_mode == BP_STORE_UPSAMPLE2 ? " up2" : (s->store_mode == BP_STORE_PIXSHUF2 ? " ps2" : ""),
+           s->out_f32 ? " f32" : "");
+  op.desc = buf;
+  if (have_col) n->ops.push_back(col_op);
+  n->ops.push_back(op);
+  n->flops += op.flops;
+  // the tensor id a consumer reads: for dst given by the caller, a view restricted to our channel window
+  if (s->dst >= 0 && (coff != 0 || oc != dt.C)) return bp_net_view(n, dst, coff, oc);
+  return dst;
+}
+
+static int push_aux(bp_net* n, OpKind kind, int a, int b, int c, int dst, double bytes, const char* name) {
+  Op op;
+  op.kind = kind;
+  op.a = a; op.b = b; op.c = c; op.dst = dst;
+  op.bytes = bytes;
+  const Tensor& t = n->tensors[dst];
+  char buf[128];
+  snprintf(buf, sizeof buf, "%s -> %dx%dx%d", name, t.H, t.W, t.C);
+  op.desc = buf;
+  n->ops.push_back(op);
+  return dst;
+}
+
+static bool bad_id(bp_net* n, int id) { return !n || id < 0 || id >= (int)n->tensors.size() || n->tensors[id].f32; }
+
+int bp_net_maxpool3x3s2(bp_net* n, int src) {
+  if (bad_id(n, src) || n->tensors[src].C % 8) return bp_fail(BP_ERR_INVALID, "bp_net_maxpool3x3s2: src");
+  const Tensor s = n->tensors[src];
+  const int dst = new_tensor(n, (s.H + 2 - 3) / 2 + 1, (s.W + 2 - 3) / 2 + 1, s.C, false);
+  if (dst < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
+  const Tensor& d = n->tensors[dst];
+  return push_aux(n, OP_MAXPOOL, src, -1, -1, dst, (double)s.H * s.W * s.C * 2 + (double)d.H * d.W * d.C * 2, "maxpool3x3/2");
+}
+
+int bp_net_global_avgpool(bp_net* n, int src) {
+  if (bad_id(n, src) || n->tensors[src].C % 8) return bp_fail(BP_ERR_INVALID, "bp_net_global_avgpool: src");
+  const Tensor s = n->tensors[src];
+  const int dst = new_tensor(n, 1, 1, s.C, false);
+  if (dst < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
+  return push_aux(n, OP_AVGPOOL, src, -1, -1, dst, (double)s.H * s.W * s.C * 2, "global_avgpool");
+}
+
+int bp_net_scale_add_relu(bp_net* n, int y, int gates, int skip) {
+  if (bad_id(n, y) || bad_id(n, gates) || bad_id(n, skip)) return bp_fail(BP_ERR_INVALID, "bp_net_scale_add_relu: ids");
+  const Tensor ty = n->tensors[y], tg = n->tensors[gates], ts = n->tensors[skip];
+  if (tg.C != ty.C || ts.C != ty.C || ts.H != ty.H || ts.W != ty.W || ty.C % 8)
+    return bp_fail(BP_ERR_INVALID, "bp_net_scale_add_relu: shapes");
+  const int dst = new_tensor(n, ty.H, ty.W, ty.C, false);
+  if (dst < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
+  return push_aux(n, OP_SCALE_ADD_RELU, y, gates, skip, dst, 3.0 * ty.H * ty.W * ty.C * 2, "scale_add_relu");
+}
+
+int bp_net_pixel_shuffle2(bp_net* n, int src) {
+  if (bad_id(n, src) || n->tensors[src].C % 32) return bp_fail(BP_ERR_INVALID, "bp_net_pixel_shuffle2: src");
+  const Tensor s = n->tensors[src];
+  const int dst = new_tensor(n, s.H * 2, s.W * 2, s.C / 4, false);
+  if (dst < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
+  return push_aux(n, OP_PIXSHUF, src, -1, -1, dst, 2.0 * s.H * s.W * s.C * 2, "pixel_shuffle2");
+}
+
+int bp_net_upsample2(bp_net* n, int src, int dst, int dst_coff) {
+  if (bad_id(n, src)) return bp_fail(BP_ERR_INVALID, "bp_net_upsample2: src");
+  const Tensor s = n->tensors[src];
+  int d = dst;
+  if (d < 0) {
+    d = new_tensor(n, s.H * 2, s.W * 2, s.C, false);
+    if (d < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
+  } else {
+    d = bp_net_view(n, dst, dst_coff, s.C);
+    if (d < 0) return d;
+    if (n->tensors[d].H != 2 * s.H || n->tensors[d].W != 2 * s.W) return bp_fail(BP_ERR_INVALID, "bp_net_upsample2: dst");
+  }
+  return push_aux(n, OP_UPSAMPLE, src, -1, -1, d, 5.0 * s.H * s.W * s.C * 2, "upsample2");
+}
+
+int bp_net_copy_channels(bp_net* n, int src, int dst, int dst_coff) {
+  if (bad_id(n, src) || bad_id(n, dst)) return bp_fail(BP_ERR_INVALID, "bp_net_copy_channels: ids");
+  const Tensor s = n->tensors[src];
+  const int d = bp_net_view(n, dst, dst_coff, s.C);
+  if (d < 0) return d;
+  if (n->tensors[d].H != s.H || n->tensors[d].W != s.W) return bp_fail(BP_ERR_INVALID, "bp_net_copy_channels: dst");
+  return push_aux(n, OP_COPYC, src, -1, -1, d, 2.0 * s.H * s.W * s.C * 2, "copy_channels");
+}
+
+int bp_net_add(bp_net* n, int a, int b) {
+  if (bad_id(n, a) || bad_id(n, b)) return bp_fail(BP_ERR_INVALID, "bp_net_add: ids");
+  const Tensor ta = n->tensors[a], tb = n->tensors[b];
+  if (ta.H != tb.H || ta.W != tb.W || ta.C != tb.C || ta.C % 8) return bp_fail(BP_ERR_INVALID, "bp_net_add: shapes");
+  const int dst = new_tensor(n, ta.H, ta.W, ta.C, false);
+  if (dst < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
+  return push_aux(n, OP_ADD, a, b, -1, dst, 3.0 * ta.H * ta.W * ta.C * 2, "add");
+}
+
+int bp_net_tensor_info(bp_net* n, int tensor, int* dims, void** ptr) {
+  if (!n || tensor < 0 || tensor >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_tensor_info: id");
+  const Tensor& t = n->tensors[tensor];
+  if (dims) {
+    dims[0] = t.H; dims[1] = t.W; dims[2] = t.C; dims[3] = t.pitch; dims[4] = t.f32 ? 1 : 0; dims[5] = t.coff;
+  }
+  if (ptr) *ptr = t.ptr;
+  return BP_OK;
+}
+
+int bp_net_num_ops(bp_net* n) { return n ? (int)n->ops.size() : 0; }
+int bp_net_num_launches(bp_net* n) { return n ? (int)n->ops.size() : 0; }
+double bp_net_flops_per_image(bp_net* n) { return n ? n->flops : 0.0; }
+
+int bp_net_op_desc(bp_net* n, int op, char* buf, int buflen, double* flops, double* bytes) {
+  if (!n || op < 0 || op >= (int)n->ops.size()) return bp_fail(BP_ERR_INVALID, "bp_net_op_desc: op");
+  if (buf && buflen > 0) snprintf(buf, buflen, "%s", n->ops[op].desc.c_str());
+  if (flops) *flops = n->ops[op].flops;
+  if (bytes) *bytes = n->ops[op].bytes;
+  return BP_OK;
+}
+
+static inline unsigned blocks_for(long total, int threads) { return (unsigned)((total + threads - 1) / threads); }
+
+int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream_) {
+  if (!n || batch <= 0 || batch > n->max_batch) return bp_fail(BP_ERR_INVALID, "bp_net_forward: batch out of range");
+  if (first < 0 || last > (int)n->ops.size() || first > last) return bp_fail(BP_ERR_INVALID, "bp_net_forward: op range");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  for (int i = first; i < last; ++i) {
+    const Op& op = n->ops[i];
+    cudaError_t e = cudaSuccess;
+    switch (op.kind) {
+      case OP_CONV: {
+        ConvPlan pl = op.plan;
+        pl.args.M = batch * op.pq;
+        pl.grid = ((pl.args.M + 127) / 128) * op.n_tiles;
+        e = conv_plan_launch(pl, st);
+        break;
+      }
+      case OP_IM2COL: {
+        const Tensor& s = n->tensors[op.a];
+        const long M = (long)batch * op.P * op.Q;
+        if (s.in_kind == BP_IN_U8X4)
+          im2col_stem_kernel<uint8_t><<<blocks_for(M, 128), 128, 0, st>>>((const uint8_t*)s.ptr, batch, s.H, s.W, op.ksize,
+                                                                        op.stride, op.pad, op.P, op.Q, 1.0f / 255.0f,
+                                                                        op.col, op.kpitch);
+        else
+          im2col_stem_kernel<__half><<<blocks_for(M, 128), 128, 0, st>>>((const __half*)s.ptr, batch, s.H, s.W, op.ksize,
+                                                                       op.stride, op.pad, op.P, op.Q, 1.0f, op.col,
+                                                                       op.kpitch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_MAXPOOL: {
+        const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
+        const long total = (long)batch * d.H * d.W * (d.C / 8);
+        maxpool3x3s2_kernel<<<blocks_for(total, 256), 256, 0, st>>>(view_of(s), view_of(d), batch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_AVGPOOL: {
+        const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
+        dim3 grid((s.C + 255) / 256, batch);
+        global_avgpool_kernel<<<grid, 256, 0, st>>>(view_of(s), (__half*)d.ptr, d.pitch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_SCALE_ADD_RELU: {
+        const Tensor &y = n->tensors[op.a], &g = n->tensors[op.b], &k = n->tensors[op.c], &d = n->tensors[op.dst];
+        const long total = (long)batch * y.H * y.W * (y.C / 8);
+        scale_add_relu_kernel<<<blocks_for(total, 256), 256, 0, st>>>(view_of(y), (const __half*)g.ptr, g.pitch, view_of(k),
+                                                                     view_of(d), batch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_PIXSHUF: {
+        const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
+        const long total = (long)batch * s.H * s.W * (s.C / 32);
+        pixel_shuffle2_kernel<<<blocks_for(total, 256), 256, 0, st>>>(view_of(s), view_of(d), batch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_UPSAMPLE: {
+        const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
+        const long total = (long)batch * d.H * d.W * (s.C / 8);
+        upsample2_kernel<<<blocks_for(total, 256), 256, 0, st>>>(view_of(s), view_of(d), batch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_COPYC: {
+        const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
+        const long total = (long)batch * s.H * s.W * (s.C / 8);
+        copy_channels_kernel<<<blocks_for(total, 256), 256, 0, st>>>(view_of(s), view_of(d), batch);
+        e = cudaGetLastError();
+        break;
+      }
+      case OP_ADD: {
+        const Tensor &a = n->tensors[op.a], &b = n->tensors[op.b], &d = n->tensors[op.dst];
+        const long total = (long)batch * a.H * a.W * (a.C / 8);
+        add_kernel<<<blocks_for(total, 256), 256, 0, st>>>(view_of(a), view_of(b), view_of(d), batch);
+        e = cudaGetLastError();
+        break;
+      }
+    }
+    if (e != cudaSuccess) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "bp_net_forward: op %d (%s): %s", i, op.desc.c_str(), cudaGetErrorString(e));
+      return bp_fail(BP_ERR_CUDA, buf);
+    }
+  }
+  return BP_OK;
+}
+
+int bp_net_forward(bp_net* n, int batch, void* stream) {
+  return bp_net_forward_range(n, batch, 0, n ? (int)n->ops.size() : 0, stream);
+}
+
+}  // extern "C"

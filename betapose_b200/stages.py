@@ -1,0 +1,162 @@
+"""Tensor-level wrappers of the stage kernels (C ABI: bp_resize_bicubic, bp_yolo_decode_argmax, bp_crop_resize,
+bp_heatmap_decode, bp_pose_pnp, bp_pack_records).  Inputs/outputs are CUDA torch tensors; every call enqueues on
+the current torch stream and returns immediately.  These are what the drop-in seam functions in
+`betapose_b200.compat` and the fused `BetaposeEngine` are built from.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+CAM_K = np.array([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]], np.float64)
+"""LineMod intrinsics hard-coded by the reference (betapose_evaluate.py:59)."""
+
+
+def _eng(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.BetaposeError("expected a CUDA tensor (betapose_b200 has no CPU path)")
+    return _lib.Engine.get(t.device.index)
+
+
+def resize_bicubic(frames_u8: torch.Tensor, out_h: int = 416, out_w: int = 416, want_u8x4: bool = True,
+                   want_f32: bool = False, out_u8x4: torch.Tensor | None = None):
+    """frames uint8 [B,H,W,3] RGB (cuda) -> (u8x4 [B,oh,ow,4] | None, fp32 [B,3,oh,ow] | None); Pillow-exact."""
+    assert frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 and frames_u8.shape[3] == 3 and frames_u8.is_contiguous()
+    e = _eng(frames_u8)
+    B, H, W, _ = frames_u8.shape
+    if want_u8x4 and out_u8x4 is None:
+        out_u8x4 = torch.empty((B, out_h, out_w, 4), dtype=torch.uint8, device=frames_u8.device)
+    f32 = torch.empty((B, 3, out_h, out_w), dtype=torch.float32, device=frames_u8.device) if want_f32 else None
+    _lib.check(_lib.lib().bp_resize_bicubic(e.handle, _lib.ptr(frames_u8), B, H, W, out_h, out_w,
+                                            _lib.ptr(out_u8x4 if want_u8x4 else None), _lib.ptr(f32), _lib.stream_ptr()),
+               "bp_resize_bicubic")
+    return (out_u8x4 if want_u8x4 else None), f32
+
+
+def yolo_decode_argmax(heads, anchors, B: int, reso: int = 416, conf: float = 0.01, frame_w: int = 640, frame_h: int = 480,
+                       n_attr: int = 6, want_decoded: bool = False):
+    """heads: list of fp32 NHWC tensors [>=B, g, g, C] (strided views allowed, channel stride 1);
+    anchors: list (per head) of 3 (w,h) pairs in pixels.
+    -> dict(det [B,8], box [B,4], row int32 [B], valid uint8 [B], decoded [B,R,n_attr] | None)"""
+    h0 = heads[0]
+    e = _eng(h0)
+    nh = len(heads)
+    ptrs = (C.c_void_p * nh)(*[h.data_ptr() for h in heads])
+    grids = (C.c_int * nh)(*[int(h.shape[1]) for h in heads])
+    pitches = (C.c_int * nh)(*[int(h.stride(2)) for h in heads])
+    flat = (C.c_float * (nh * 6))(*[float(v) for hd in anchors for wh in hd for v in wh])
+    dev = h0.device
+    det = torch.empty((B, 8), dtype=torch.float32, device=dev)
+    box = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    row = torch.empty((B,), dtype=torch.int32, device=dev)
+    valid = torch.empty((B,), dtype=torch.uint8, device=dev)
+    total = sum(3 * int(h.shape[1]) ** 2 for h in heads)
+    dec = torch.empty((B, total, n_attr), dtype=torch.float32, device=dev) if want_decoded else None
+    _lib.check(_lib.lib().bp_yolo_decode_argmax(e.handle, ptrs, grids, pitches, nh, flat, n_attr, B, reso, float(conf),
+                                                frame_w, frame_h, _lib.ptr(det), _lib.ptr(box), _lib.ptr(row),
+                                                _lib.ptr(valid), _lib.ptr(dec), _lib.stream_ptr()), "bp_yolo_decode_argmax")
+    return dict(det=det, box=box, row=row, valid=valid, decoded=dec)
+
+
+def crop_resize(frames_u8: torch.Tensor, box: torch.Tensor, img_idx: torch.Tensor, valid: torch.Tensor | None = None,
+                res_h: int = 320, res_w: int = 256, out_f16x4: torch.Tensor | None = None, want_f16: bool = True,
+                want_f32: bool = False):
+    """frames uint8 [F,H,W,3]; box fp32 [n,4]; img_idx int32 [n] -> dict(f16x4 [n,rh,rw,4], f32 [n,3,rh,rw], pt1, pt2)."""
+    e = _eng(frames_u8)
+    n = int(box.shape[0])
+    _, H, W, _ = frames_u8.shape
+    dev = frames_u8.device
+    if want_f16 and out_f16x4 is None:
+        out_f16x4 = torch.empty((n, res_h, res_w, 4), dtype=torch.float16, device=dev)
+    f32 = torch.empty((n, 3, res_h, res_w), dtype=torch.float32, device=dev) if want_f32 else None
+    pt1 = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    pt2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().bp_crop_resize(e.handle, _lib.ptr(frames_u8), H, W, _lib.ptr(box.contiguous()),
+                                         _lib.ptr(img_idx.contiguous()), _lib.ptr(valid), n, res_h, res_w,
+                                         _lib.ptr(out_f16x4 if want_f16 else None), _lib.ptr(f32), _lib.ptr(pt1),
+                                         _lib.ptr(pt2), _lib.stream_ptr()), "bp_crop_resize")
+    return dict(f16x4=out_f16x4 if want_f16 else None, f32=f32, pt1=pt1, pt2=pt2)
+
+
+def heatmap_decode(hm: torch.Tensor, pt1: torch.Tensor, pt2: torch.Tensor, layout: str = "nchw", inp_h: int = 320,
+                   inp_w: int = 256):
+    """hm fp32: layout 'nchw' = [n,K,H,W] (the reference's), 'nhwc' = [n,H,W,K] (possibly channel-padded view).
+    -> dict(preds_hm [n,K,2], preds_img [n,K,2], maxval [n,K,1], idx int32 [n,K])"""
+    e = _eng(hm)
+    assert hm.dtype == torch.float32 and hm.dim() == 4
+    if layout == "nchw":
+        n, K, H, W = hm.shape
+        assert hm.stride(3) == 1 and hm.stride(2) == W
+        strides = (hm.stride(0), hm.stride(1), 1)
+    else:
+        n, H, W, K = hm.shape
+        assert hm.stride(3) == 1 and hm.stride(1) == W * hm.stride(2)
+        strides = (hm.stride(0), 1, hm.stride(2))
+    dev = hm.device
+    ph = torch.empty((n, K, 2), dtype=torch.float32, device=dev)
+    pi = torch.empty((n, K, 2), dtype=torch.float32, device=dev)
+    mv = torch.empty((n, K, 1), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, K), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().bp_heatmap_decode(e.handle, _lib.ptr(hm), strides[0], strides[1], strides[2], n, K, H, W, inp_h,
+                                            inp_w, _lib.ptr(pt1.contiguous()), _lib.ptr(pt2.contiguous()), _lib.ptr(ph),
+                                            _lib.ptr(pi), _lib.ptr(mv), _lib.ptr(idx), _lib.stream_ptr()), "bp_heatmap_decode")
+    return dict(preds_hm=ph, preds_img=pi, maxval=mv, idx=idx)
+
+
+MODE_RANSAC, MODE_ALLPTS = 0, 1
+
+
+def pose_pnp(preds_img: torch.Tensor, maxval: torch.Tensor, det_score: torch.Tensor, kp3d: torch.Tensor,
+             valid: torch.Tensor | None = None, model_idx: torch.Tensor | None = None, cam_K=CAM_K, left_number: int = 50,
+             mode: int = MODE_RANSAC, reproj_thr: float = 12.0, n_hyp: int = 64, seed: int = 0):
+    """Single-proposal pose-NMS + key-point selection + PnP for n detections.
+    kp3d float64 [K,3] or [n_models,K,3] (cuda).  Returns a dict of cuda tensors (see bp_pose_pnp)."""
+    e = _eng(preds_img)
+    n, K = int(preds_img.shape[0]), int(preds_img.shape[1])
+    dev = preds_img.device
+    assert kp3d.dtype == torch.float64 and kp3d.is_cuda
+    cam = torch.tensor([cam_K[0][0], cam_K[1][1], cam_K[0][2], cam_K[1][2]], dtype=torch.float64)
+    cam_arr = (C.c_double * 4)(*cam.tolist())
+    out = dict(
+        keypoints=torch.empty((n, K, 2), dtype=torch.float32, device=dev),
+        kp_score=torch.empty((n, K), dtype=torch.float32, device=dev),
+        proposal=torch.empty((n,), dtype=torch.float32, device=dev),
+        selected=torch.empty((n, K), dtype=torch.uint8, device=dev),
+        R=torch.empty((n, 9), dtype=torch.float64, device=dev),
+        t=torch.empty((n, 3), dtype=torch.float64, device=dev),
+        inlier=torch.empty((n, K), dtype=torch.uint8, device=dev),
+        status=torch.empty((n,), dtype=torch.int32, device=dev),
+    )
+    _lib.check(_lib.lib().bp_pose_pnp(e.handle, _lib.ptr(preds_img.contiguous()), _lib.ptr(maxval.contiguous()),
+                                      _lib.ptr(det_score.contiguous()), _lib.ptr(valid), n, K, _lib.ptr(kp3d.contiguous()),
+                                      _lib.ptr(model_idx), C.cast(cam_arr, C.c_void_p), int(left_number), int(mode),
+                                      float(reproj_thr), int(n_hyp), int(seed) & 0xFFFFFFFF, _lib.ptr(out["keypoints"]),
+                                      _lib.ptr(out["kp_score"]), _lib.ptr(out["proposal"]), _lib.ptr(out["selected"]),
+                                      _lib.ptr(out["R"]), _lib.ptr(out["t"]), _lib.ptr(out["inlier"]),
+                                      _lib.ptr(out["status"]), _lib.stream_ptr()), "bp_pose_pnp")
+    return out
+
+
+def pack_records(image_index0: int, box, det_score, pose: dict) -> torch.Tensor:
+    """-> uint8 [n, RECORD_BYTES] cuda tensor of bp_record structs."""
+    e = _eng(box)
+    n, K = pose["kp_score"].shape
+    out = torch.empty((n, _lib.RECORD_BYTES), dtype=torch.uint8, device=box.device)
+    _lib.check(_lib.lib().bp_pack_records(e.handle, n, K, int(image_index0), _lib.ptr(box.contiguous()),
+                                          _lib.ptr(det_score.contiguous()), _lib.ptr(pose["keypoints"]),
+                                          _lib.ptr(pose["kp_score"]), _lib.ptr(pose["proposal"]), _lib.ptr(pose["R"]),
+                                          _lib.ptr(pose["t"]), _lib.ptr(pose["status"]), _lib.ptr(out), _lib.stream_ptr()),
+               "bp_pack_records")
+    return out
+
+
+def records_to_numpy(rec_u8: torch.Tensor) -> np.ndarray:
+    """host copy of packed records as a numpy structured array."""
+    dt = np.dtype([("image_index", "<i4"), ("status", "<i4"), ("box", "<f4", 4), ("det_score", "<f4"),
+                   ("proposal_score", "<f4"), ("keypoints", "<f4", 150), ("R", "<f8", 9), ("t", "<f8", 3)], align=True)
+    assert dt.itemsize == _lib.RECORD_BYTES, (dt.itemsize, _lib.RECORD_BYTES)
+    return rec_u8.detach().cpu().numpy().view(dt).reshape(-1)

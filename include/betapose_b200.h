@@ -1,0 +1,189 @@
+/*
+ * betapose_b200 -- C ABI of the B200-native engine for Betapose's per-frame evaluate hot path.
+ *
+ * The reference (sjtuytc/betapose) has no plugin / FFI boundary on this path: its seams are Python call
+ * signatures.  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md); each entry point names the reference code it replaces.  Conventions:
+ *   - plain pointers and sizes only; device pointers are raw CUDA addresses owned by the CALLER unless stated;
+ *   - every call enqueues on the given cudaStream_t (passed as void*) and never synchronises, except
+ *     bp_net_conv / bp_net_finalize (load-time: host->device weight upload) and bp_*_create;
+ *   - int return: 0 = OK, negative = error, message via bp_last_error() (thread-local);
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef BETAPOSE_B200_H
+#define BETAPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_OK 0
+#define BP_ERR_INVALID (-1)
+#define BP_ERR_CUDA (-2)
+#define BP_ERR_UNSUPPORTED (-3)
+
+/* activation / residual / store selectors of a fused conv block */
+#define BP_ACT_NONE 0
+#define BP_ACT_LEAKY 1   /* LeakyReLU(0.1): yolo/darknet.py:259 */
+#define BP_ACT_RELU 2    /* SE_Resnet.py:28-30,40 ; DUC.py:21 */
+#define BP_ACT_SIGMOID 3 /* SE_module.py:12 */
+#define BP_RES_NONE 0
+#define BP_RES_AFTER_ACT 1  /* darknet [shortcut]: act(conv) + skip, yolo/darknet.py:338-340 */
+#define BP_RES_BEFORE_ACT 2 /* ResNet bottleneck: relu(conv + skip), SE_Resnet.py:38-40 */
+#define BP_STORE_PLAIN 0
+#define BP_STORE_UPSAMPLE2 1 /* nn.Upsample(2, nearest) fused into the producer, darknet.py:273-276 */
+#define BP_STORE_PIXSHUF2 2  /* nn.PixelShuffle(2) fused into the producer, DUC.py:16,22 */
+
+typedef struct bp_engine bp_engine;
+typedef struct bp_net bp_net;
+
+const char* bp_last_error(void);
+int bp_version(void);
+
+/* ---------------------------------------------------------------------------------------------- engine */
+/* One per device.  Owns the TMA driver entry points, the PIL coefficient tables and scratch space. */
+int bp_engine_create(int device, bp_engine** out);
+void bp_engine_destroy(bp_engine* e);
+
+/* ---------------------------------------------------------------------------------------------- networks
+ * A bp_net is an ordered list of fused layer ops over NHWC fp16 tensors, built once (weights uploaded, BN
+ * folded, TMA descriptors encoded for max_batch) and replayed per batch.  It replaces
+ *   Darknet.build_model / load_weights / forward   (3_6Dpose_estimator/yolo/darknet.py:223-432) and
+ *   FastPose / SEResnet / Bottleneck / SELayer / DUC (KPD/src/models/FastPose.py:13-35, layers/*.py).
+ * Tensors are named by small integer ids returned by the builder calls.
+ */
+#define BP_IN_U8X4 0  /* input tensor is uint8 [N,H,W,4] (RGBX), scaled by 1/255 when read  */
+#define BP_IN_F16X4 1 /* input tensor is fp16  [N,H,W,4] (RGB + pad)                        */
+
+int bp_net_create(bp_engine* e, int max_batch, int in_h, int in_w, int in_kind, bp_net* share_buffers_with,
+                  bp_net** out);
+void bp_net_destroy(bp_net* n);
+/* id of the network input tensor (always 0) and its device address (caller writes the input there) */
+void* bp_net_input_ptr(bp_net* n);
+
+typedef struct bp_conv_spec {
+  int src;      /* input tensor id */
+  int cout;     /* output channels */
+  int ksize;    /* square kernel: 1, 3 or 7 */
+  int stride;   /* 1 or 2 */
+  int pad;      /* symmetric zero padding */
+  int act;      /* BP_ACT_* */
+  int res;      /* residual tensor id, or -1 */
+  int res_mode; /* BP_RES_* */
+  int dst;      /* tensor id to write into (e.g. a concat buffer), or -1 to allocate a fresh tensor */
+  int dst_coff; /* channel offset inside dst */
+  int store_mode; /* BP_STORE_* */
+  int out_f32;  /* 1: fp32 output (network heads) */
+  /* host fp32 parameters, PyTorch layouts; bn_* may be NULL (then `bias` is the conv bias or NULL) */
+  const float* weight; /* [cout, cin, k, k] */
+  const float* bias;   /* [cout] */
+  const float* bn_gamma;
+  const float* bn_beta;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_eps;
+} bp_conv_spec;
+
+/* conv (+folded BN) + bias + activation (+ residual) (+ fused upsample / pixel-shuffle store). Returns the
+ * output tensor id (>= 0) or a negative error. */
+int bp_net_conv(bp_net* n, const bp_conv_spec* spec);
+/* pre-allocate a tensor several producers write into (darknet [route] with two layers = channel concat) */
+int bp_net_alloc_tensor(bp_net* n, int h, int w, int c);
+/* channel window [coff, coff+c) of an existing tensor as a tensor of its own (no copy) */
+int bp_net_view(bp_net* n, int tensor, int coff, int c);
+/* MaxPool2d(3, 2, 1): SE_Resnet.py:59 */
+int bp_net_maxpool3x3s2(bp_net* n, int src);
+/* AdaptiveAvgPool2d(1) -> [N,1,1,C] fp16: SE_module.py:7,16 */
+int bp_net_global_avgpool(bp_net* n, int src);
+/* relu(y * s + skip), s = [N,1,1,C] channel gates: SE_module.py:19 + SE_Resnet.py:38-40 */
+int bp_net_scale_add_relu(bp_net* n, int y, int gates, int skip);
+/* stand-alone PixelShuffle(2): FastPose.py:21,30 */
+int bp_net_pixel_shuffle2(bp_net* n, int src);
+/* generic fall-backs for cfg files whose route/upsample pattern cannot be fused */
+int bp_net_upsample2(bp_net* n, int src, int dst, int dst_coff);
+int bp_net_copy_channels(bp_net* n, int src, int dst, int dst_coff);
+/* element-wise sum (darknet [shortcut] whose producer could not absorb it) */
+int bp_net_add(bp_net* n, int a, int b);
+
+/* query a tensor: dims[0..5] = {H, W, C, pitch (elements per pixel), is_f32, coff}; *ptr = device address */
+int bp_net_tensor_info(bp_net* n, int tensor, int* dims, void** ptr);
+int bp_net_num_launches(bp_net* n);
+double bp_net_flops_per_image(bp_net* n);
+/* run all ops for `batch` images on `stream`; input must already be at bp_net_input_ptr() */
+int bp_net_forward(bp_net* n, int batch, void* stream);
+/* debugging / profiling: run only ops [first, last) */
+int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream);
+int bp_net_num_ops(bp_net* n);
+/* per-op description for profiling tables: writes a short text into buf */
+int bp_net_op_desc(bp_net* n, int op, char* buf, int buflen, double* flops_per_image, double* bytes_per_image);
+
+/* ---------------------------------------------------------------------------------------------- stages */
+/* a1: transforms.Resize((oh,ow), BICUBIC) + ToTensor  (dataloader.py:94-99,162) -- Pillow's two integer
+ * passes, bit-exact.  frames: uint8 [B,H,W,3] RGB.  out_u8x4: uint8 [B,oh,ow,4] (detector input) and/or
+ * out_f32_chw: fp32 [B,3,oh,ow] in 0..1 (what the reference feeds Darknet); either may be NULL. */
+int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int H, int W, int oh, int ow, uint8_t* out_u8x4,
+                      float* out_f32_chw, void* stream);
+
+/* a3+a4+a5: DetectionLayer.forward (yolo/darknet.py:129-169) + write_results (yolo/util.py:118-223, nms off,
+ * arg-max objectness) + box rescale (dataloader.py:350-364), fused; never materialises the 10647x6 tensor
+ * unless `decoded` != NULL.  heads[i]: fp32 NHWC [B,g_i,g_i,pitch_i] raw head i (stride 32,16,8 order),
+ * channel c = a*(5+classes)+attr.  anchors: 2*3 floats per head (pixels).
+ * Outputs per image: det[B,8] = (img, x1,y1,x2,y2 in reso-space, obj, cls_conf, cls_idx), box[B,4] rescaled to
+ * the frame, row[B] winning flat row (anchor-major, lowest index on ties), valid[B] (0: no candidate > conf). */
+int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, const int* grids, const int* pitches,
+                          int n_heads, const float* anchors, int n_attr, int B, int reso, float conf, int frame_w,
+                          int frame_h, float* det, float* box, int32_t* row, uint8_t* valid, float* decoded,
+                          void* stream);
+
+/* a6: im_to_torch + crop_from_dets + cropBox (KPD/src/utils/img.py:13-18,242-262; dataloader.py:794-835).
+ * frames uint8 [F,H,W,3] RGB; box[n,4]; img_idx[n] (frame of each box); valid[n] (may be NULL).
+ * Outputs: out_f16x4 fp16 [n,rh,rw,4] (keypoint-net input) and/or out_f32_chw fp32 [n,3,rh,rw]; pt1/pt2 [n,2]
+ * fp32 un-truncated expanded corners. */
+int bp_crop_resize(bp_engine* e, const uint8_t* frames, int H, int W, const float* box, const int32_t* img_idx,
+                   const uint8_t* valid, int n, int rh, int rw, void* out_f16x4, float* out_f32_chw, float* pt1,
+                   float* pt2, void* stream);
+
+/* a8: getPrediction + transformBoxInvert_batch (KPD/src/utils/eval.py:113-147; img.py:216-239).
+ * hm: fp32 heat-maps addressed as hm[img*img_stride + k*k_stride + pos*pos_stride], pos = y*res_w + x.
+ * Outputs: preds_hm[n,K,2], preds_img[n,K,2], maxval[n,K], idx[n,K] (flat arg-max, lowest index on ties). */
+int bp_heatmap_decode(bp_engine* e, const float* hm, long img_stride, long k_stride, long pos_stride, int n, int K,
+                      int res_h, int res_w, int inp_h, int inp_w, const float* pt1, const float* pt2,
+                      float* preds_hm, float* preds_img, float* maxval, int32_t* idx, void* stream);
+
+/* a9 (n = 1 branch) + a10 + a11: pose_nms for a single proposal (pPose_nms.py:24-122), keypoint selection
+ * (dataloader.py:715-724) and PnP (utils/utils.py:17-41).  mode 0: RANSAC-EPnP (5-point hypotheses, 12 px
+ * consensus, LM refit on the consensus set) mirroring cv2.solvePnPRansac; mode 1: EPnP on all selected points
+ * + LM, mirroring the active cv2.solvePnP call.
+ * In: preds_img[n,K,2], maxval[n,K], det_score[n], valid[n] (NULL = all), kp3d f64 [n_models,K,3] + model_idx[n]
+ * (NULL = model 0), cam f64[4] = (fx,fy,cx,cy).
+ * Out: keypoints[n,K,2] (= preds - 0.3), kp_score[n,K], proposal[n], selected[n,K] (u8 mask of the points
+ * handed to PnP), R f64[n,9] row-major, t f64[n,3], inlier[n,K] u8, status[n]: 1 = pose, 0 = rejected by
+ * pose-NMS (max score < 0.3) or invalid, -1 = PnP failed. */
+int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* maxval, const float* det_score,
+                const uint8_t* valid, int n, int K, const double* kp3d, const int32_t* model_idx, const double* cam,
+                int left_number, int mode, float reproj_thr, int n_hyp, uint32_t seed, float* keypoints,
+                float* kp_score, float* proposal, uint8_t* selected, double* R, double* t, uint8_t* inlier,
+                int32_t* status, void* stream);
+
+/* a12: fixed-size result record per image, the unit the multi-GPU all-gather moves. */
+typedef struct bp_record {
+  int32_t image_index; /* global image index */
+  int32_t status;      /* see bp_pose_pnp */
+  float box[4];
+  float det_score;
+  float proposal_score;
+  float keypoints[50 * 3]; /* x, y, score */
+  double R[9];
+  double t[3];
+} bp_record;
+int bp_pack_records(bp_engine* e, int n, int K, int image_index0, const float* box, const float* det_score,
+                    const float* keypoints, const float* kp_score, const float* proposal, const double* R,
+                    const double* t, const int32_t* status, bp_record* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BETAPOSE_B200_H */
