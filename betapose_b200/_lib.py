@@ -94,7 +94,7 @@ def lib() -> C.CDLL:
     L.bp_net_op_desc.argtypes = [vp, i, C.c_char_p, i, C.POINTER(d), C.POINTER(d)]
     L.bp_resize_bicubic.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]
     L.bp_yolo_decode_argmax.argtypes = [vp, C.POINTER(vp), C.POINTER(i), C.POINTER(i), i, C.POINTER(f), i, i, i, f, i, i,
-                                        vp, vp, vp, vp, vp, vp]
+                                        vp, vp, vp, vp, vp, vp, vp]
     L.bp_crop_resize.argtypes = [vp, vp, i, i, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp]
     L.bp_heatmap_decode.argtypes = [vp, vp, C.c_long, C.c_long, C.c_long, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.bp_pose_pnp.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, i, i, f, i, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, vp]

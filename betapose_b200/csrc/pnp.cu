@@ -45,7 +45,6 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
   __shared__ double s_t[kMaxHyp * 3];
   __shared__ int s_state;  // 1 = run PnP, 0 = rejected
   __shared__ int s_nsel;
-  __shared__ int s_best;
 
   const int i = blockIdx.x;
   const int tid = threadIdx.x;
@@ -102,44 +101,33 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
   const bool run = s_state == 1 && s_nsel >= 4;
   const bool ransac = run && mode == 0 && s_nsel >= 6;
 
-  // ---- stage B: hypotheses
+  // ---- stage B: hypotheses (RANSAC: one 5-point EPnP per thread; all-points mode: thread 0 solves all selected)
   if (tid < kMaxHyp) s_cnt[tid] = -1;
   __syncthreads();
-  if (run) {
+  if (run && (ransac ? tid < n_hyp : tid == 0)) {
     int pool[kMaxK];
+    int m = 0;
+    for (int j = 0; j < K; ++j)
+      if (s_sel[j]) pool[m++] = j;
     if (ransac) {
-      if (tid < n_hyp) {
-        int m = 0;
-        for (int j = 0; j < K; ++j)
-          if (s_sel[j]) pool[m++] = j;
-        bp::pnp::sample_subset(pool, m, tid, seed, 5);
-        double R[9], t[3];
-        if (bp::pnp::epnp(s_pw, s_uv, pool, 5, fx, fy, cx, cy, R, t)) {
-          int cnt;
-          double tot;
-          bp::pnp::score_hypothesis(R, t, s_pw, s_uv, s_sel, K, fx, fy, cx, cy, thr2, &cnt, &tot);
-          s_cnt[tid] = cnt;
-          s_tot[tid] = tot;
-          for (int k = 0; k < 9; ++k) s_R[tid * 9 + k] = R[k];
-          for (int k = 0; k < 3; ++k) s_t[tid * 3 + k] = t[k];
-        }
-      }
-    } else if (tid == 0) {
-      int m = 0;
-      for (int j = 0; j < K; ++j)
-        if (s_sel[j]) pool[m++] = j;
-      double R[9], t[3];
-      if (bp::pnp::epnp(s_pw, s_uv, pool, m, fx, fy, cx, cy, R, t)) {
-        s_cnt[0] = m;
-        s_tot[0] = 0.0;
-        for (int k = 0; k < 9; ++k) s_R[k] = R[k];
-        for (int k = 0; k < 3; ++k) s_t[k] = t[k];
-      }
+      bp::pnp::sample_subset(pool, m, tid, seed, 5);
+      m = 5;
+    }
+    double R[9], t[3];
+    if (bp::pnp::epnp(s_pw, s_uv, pool, m, fx, fy, cx, cy, R, t)) {
+      int cnt = m;
+      double tot = 0.0;
+      if (ransac) bp::pnp::score_hypothesis(R, t, s_pw, s_uv, s_sel, K, fx, fy, cx, cy, thr2, &cnt, &tot);
+      s_cnt[tid] = cnt;
+      s_tot[tid] = tot;
+      for (int k = 0; k < 9; ++k) s_R[tid * 9 + k] = R[k];
+      for (int k = 0; k < 3; ++k) s_t[tid * 3 + k] = t[k];
     }
   }
   __syncthreads();
 
-  // ---- stage C: consensus (warp 0)
+  // ---- stage C + D (warp 0): pick the consensus winner, then alternate {classify points against the current
+  // pose, LM refit on the consensus set} until the set is stable (at most BP_PNP_LO_ROUNDS refits)
   if (tid < 32) {
     int bc = -1, bh = 0x7fffffff;
     double bt = INFINITY;
@@ -164,44 +152,42 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
         bh = oh;
       }
     }
-    if (tid == 0) s_best = (run && bc >= 4) ? bh : -1;
-  }
-  __syncthreads();
-  const int best = s_best;
-  if (best >= 0 && tid < K) {
-    uint8_t in = 0;
-    if (s_sel[tid]) {
-      if (ransac) {
-        double u, v, z;
-        bp::pnp::project(s_R + best * 9, s_t + best * 3, s_pw + 3 * tid, fx, fy, cx, cy, &u, &v, &z);
-        const double e2 = (u - s_uv[2 * tid]) * (u - s_uv[2 * tid]) + (v - s_uv[2 * tid + 1]) * (v - s_uv[2 * tid + 1]);
-        in = (z > 0 && e2 <= thr2) ? 1 : 0;
-      } else {
-        in = 1;
+    bool ok = run && bc >= 4;
+    double R[9], t[3];
+    for (int k = 0; k < 9; ++k) R[k] = ok ? s_R[bh * 9 + k] : 0.0;
+    for (int k = 0; k < 3; ++k) t[k] = ok ? s_t[bh * 3 + k] : 0.0;
+    if (ok) {
+      WarpLanes ln;
+      for (int round = 0; round < BP_PNP_LO_ROUNDS; ++round) {
+        int changed = 0, cnt = 0;
+        for (int j = tid; j < K; j += 32) {
+          const uint8_t in = s_sel[j] && (!ransac || bp::pnp::within_threshold(R, t, s_pw, s_uv, j, fx, fy, cx, cy, thr2)) ? 1 : 0;
+          changed |= in != s_inl[j];
+          s_inl[j] = in;
+          cnt += in;
+        }
+        __syncwarp();
+        changed = __any_sync(0xffffffffu, changed);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (round > 0 && !changed) break;
+        if (cnt < 4) {
+          ok = false;
+          break;
+        }
+        bp::pnp::lm_refine(ln, R, t, s_pw, s_uv, s_inl, K, fx, fy, cx, cy, 50);
+        if (!ransac) break;
       }
     }
-    s_inl[tid] = in;
+    if (tid == 0) {
+      for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = ok ? R[k] : 0.0;
+      for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = ok ? t[k] : 0.0;
+      status[i] = s_state == 0 ? 0 : (ok ? 1 : -1);
+    }
+    if (!ok)
+      for (int j = tid; j < K; j += 32) s_inl[j] = 0;
   }
   __syncthreads();
-
-  // ---- stage D: LM refit on the consensus set (warp 0, lanes over points)
-  if (tid < 32) {
-    double R[9], t[3];
-    if (best >= 0) {
-      for (int k = 0; k < 9; ++k) R[k] = s_R[best * 9 + k];
-      for (int k = 0; k < 3; ++k) t[k] = s_t[best * 3 + k];
-      WarpLanes ln;
-      bp::pnp::lm_refine(ln, R, t, s_pw, s_uv, s_inl, K, fx, fy, cx, cy, 50);
-    } else {
-      for (int k = 0; k < 9; ++k) R[k] = 0.0;
-      for (int k = 0; k < 3; ++k) t[k] = 0.0;
-    }
-    if (tid == 0) {
-      for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = R[k];
-      for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = t[k];
-      status[i] = s_state == 0 ? 0 : (best >= 0 ? 1 : -1);
-    }
-  }
   if (tid < K) inlier[(long)i * K + tid] = s_inl[tid];
 }
 

@@ -10,7 +10,10 @@
 
 #if defined(__CUDACC__)
 #define BP_HD __host__ __device__ __forceinline__
-#define BP_HD_NOINLINE __host__ __device__ __noinline__
+// NOTE: these were __noinline__ at first; cicc 12.9 -O3 then merges the stack slots of the caller's local arrays that
+// are passed by pointer (jacobi_eig's A and V came back aliased: eigenvalues all 1.0 on the device, correct with
+// -G / -Xcicc -O1 and on the host).  Forced inlining avoids the miscompile; each function has one call site.
+#define BP_HD_NOINLINE __host__ __device__ __forceinline__
 #else
 #define BP_HD inline
 #define BP_HD_NOINLINE
@@ -59,7 +62,10 @@ BP_HD_NOINLINE void jacobi_eig(double* A, double* V, double* w) {
       diag += A[p * N + p] * A[p * N + p];
       for (int q = p + 1; q < N; ++q) off += A[p * N + q] * A[p * N + q];
     }
-    if (off <= 1e-34 * diag || off < 1e-300) break;
+    if (off < 1e-300) break;
+    // quadratic convergence: once the off-diagonal mass is below 1e-22 of the diagonal one more sweep reaches the
+    // rounding floor
+    const bool last = off <= 1e-22 * diag;
     for (int p = 0; p < N - 1; ++p) {
       for (int q = p + 1; q < N; ++q) {
         const double apq = A[p * N + q];
@@ -84,6 +90,7 @@ BP_HD_NOINLINE void jacobi_eig(double* A, double* V, double* w) {
         }
       }
     }
+    if (last) break;
   }
   for (int i = 0; i < N; ++i) w[i] = A[i * N + i];
 }
@@ -190,7 +197,11 @@ BP_HD_NOINLINE void horn_rotation(const double S[9], double* R) {
 // pw[n][3] world points, uv[n][2] pixels, ids[0..n) selects the correspondences.  Returns false on a
 // degenerate configuration.  Scratch lives on the caller's stack/local memory (~3.5 KB).
 BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* ids, int n, double fx, double fy, double cx,
-                         double cy, double* R_out, double* t_out) {
+                         double cy, double* R_out, double* t_out
+#ifdef BP_PNP_DEBUG
+                         , double* dbg
+#endif
+) {
   // 1. control points: centroid + principal axes
   double c0[3] = {0, 0, 0};
   for (int i = 0; i < n; ++i)
@@ -268,6 +279,11 @@ BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* 
       order[k] = m;
     }
   }
+#ifdef BP_PNP_DEBUG
+  for (int i = 0; i < 12; ++i) dbg[i] = w12[i];
+  for (int i = 0; i < 4; ++i) dbg[12 + i] = order[i];
+  for (int i = 0; i < 3; ++i) dbg[16 + i] = w3[i];
+#endif
   double v[4][12];
   for (int k = 0; k < 4; ++k)
     for (int i = 0; i < 12; ++i) v[k][i] = V12[i * 12 + order[k]];
@@ -314,6 +330,9 @@ BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* 
       if (x[1] < 0) be[0] = -be[0];
       be[2] = be[0] != 0.0 ? x[3] / be[0] : 0.0;
     }
+#ifdef BP_PNP_DEBUG
+    for (int i = 0; i < 4; ++i) dbg[40 + cand * 4 + i] = be[i];
+#endif
     // Gauss-Newton on the 4 betas (5 iterations)
     for (int it = 0; it < 5; ++it) {
       double A[24], r6[6], x[4];
@@ -365,6 +384,10 @@ BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* 
       const double du = u - uv_all[ids[i] * 2], dv2 = vv - uv_all[ids[i] * 2 + 1];
       err += sqrt(du * du + dv2 * dv2);
     }
+#ifdef BP_PNP_DEBUG
+    dbg[20 + cand * 5 + 4] = err;
+    for (int i = 0; i < 4; ++i) dbg[20 + cand * 5 + i] = be[i];
+#endif
     if (err == err && err < best_err) {  // finite and better
       best_err = err;
       have = true;
@@ -510,6 +533,18 @@ struct SingleLane {  // host / single-thread policy
   BP_HD int count() const { return 1; }
   BP_HD void allreduce(double*, int) const {}
 };
+
+// is point i within the reprojection threshold (and in front of the camera) under (R, t)?
+BP_HD bool within_threshold(const double* R, const double* t, const double* pw, const double* uv, int i, double fx, double fy,
+                            double cx, double cy, double thr2) {
+  double u, v, z;
+  project(R, t, pw + 3 * i, fx, fy, cx, cy, &u, &v, &z);
+  const double e2 = (u - uv[2 * i]) * (u - uv[2 * i]) + (v - uv[2 * i + 1]) * (v - uv[2 * i + 1]);
+  return z > 0 && e2 <= thr2;
+}
+
+// number of consensus re-estimation rounds after the winning hypothesis (classify -> LM refit -> classify ...)
+#define BP_PNP_LO_ROUNDS 4
 
 // score one hypothesis against all candidate points: consensus count and summed squared error of inliers
 BP_HD void score_hypothesis(const double* R, const double* t, const double* pw, const double* uv, const uint8_t* sel,

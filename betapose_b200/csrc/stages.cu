@@ -182,8 +182,9 @@ __device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.f, _
 // one block per image; 256 threads scan all candidate rows (obj logit only), block arg-max with lowest-index
 // tie-break, then thread 0 decodes the winner.  Optionally every row is decoded into `decoded` [B,R,n_attr].
 __global__ void yolo_decode_argmax_kernel(HeadDesc hd, int n_attr, int total_rows, int reso, float conf, float wr, float hr,
-                                          float* __restrict__ det, float* __restrict__ box, int32_t* __restrict__ row_out,
-                                          uint8_t* __restrict__ valid, float* __restrict__ decoded) {
+                                          float* __restrict__ det, float* __restrict__ box, float* __restrict__ score,
+                                          int32_t* __restrict__ row_out, uint8_t* __restrict__ valid,
+                                          float* __restrict__ decoded) {
   const int b = blockIdx.x;
   __shared__ float s_val[256];
   __shared__ int s_idx[256];
@@ -270,6 +271,7 @@ __global__ void yolo_decode_argmax_kernel(HeadDesc hd, int n_attr, int total_row
       bx[3] = __fmul_rn(d[4], hr);
     }
     for (int i = 0; i < 8; ++i) det[b * 8 + i] = d[i];
+    if (score) score[b] = d[5];
     for (int i = 0; i < 4; ++i) box[b * 4 + i] = bx[i];
   }
 }
@@ -278,8 +280,8 @@ __global__ void yolo_decode_argmax_kernel(HeadDesc hd, int n_attr, int total_row
 
 extern "C" int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, const int* grids, const int* pitches,
                                      int n_heads, const float* anchors, int n_attr, int B, int reso, float conf,
-                                     int frame_w, int frame_h, float* det, float* box, int32_t* row, uint8_t* valid,
-                                     float* decoded, void* stream) {
+                                     int frame_w, int frame_h, float* det, float* box, float* score, int32_t* row,
+                                     uint8_t* valid, float* decoded, void* stream) {
   if (!e || !heads || n_heads < 1 || n_heads > 3 || B <= 0 || n_attr < 6) return bp_fail(BP_ERR_INVALID, "bp_yolo_decode_argmax: bad arguments");
   HeadDesc hd;
   int total = 0;
@@ -294,7 +296,7 @@ extern "C" int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, co
   hd.n_heads = n_heads;
   const float wr = (float)frame_w / (float)reso, hr = (float)frame_h / (float)reso;
   yolo_decode_argmax_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(hd, n_attr, total, reso, conf, wr, hr, det,
-                                                                                  box, row, valid, decoded);
+                                                                                  box, score, row, valid, decoded);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }

@@ -1,0 +1,216 @@
+"""BetaposeEngine: the whole per-frame evaluate path as one enqueue-only pipeline.
+
+    frames uint8 [B,480,640,3] RGB
+      -> bp_resize_bicubic      (a1  dataloader.py:94-99,162)          writes the detector input in place
+      -> bp_net_forward (YOLO)  (a2  yolo/darknet.py:319-363)          75 fused tcgen05 conv launches
+      -> bp_yolo_decode_argmax  (a3-a5 darknet.py:129-169, util.py:118-223, dataloader.py:350-364)
+      -> bp_crop_resize         (a6  dataloader.py:794-835, img.py:242-262) writes the keypoint-net input in place
+      -> bp_net_forward (KPD)   (a7  KPD/src/models/FastPose.py:28-35)
+      -> bp_heatmap_decode      (a8  KPD/src/utils/eval.py:113-147)
+      -> bp_pose_pnp            (a9-a11 pPose_nms.py:24-122, dataloader.py:715-726, utils/utils.py:17-41)
+      -> bp_pack_records        (a12 dataloader.py:708-730)
+    -> records uint8 [B, sizeof(bp_record)]
+
+Nothing synchronises with the host; every buffer is allocated once in __init__ so a step can be captured in a
+CUDA graph (`capture=True`).  One detector + one keypoint network per object id ("slot"); slots share activation
+buffers (bp_net_create(share_buffers_with=...)) and a mixed batch is processed slot by slot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, net as _net, stages, yolo_cfg
+
+
+class BetaposeEngine:
+    def __init__(self, max_batch: int, yolo_streams, kpd_state_dicts, kp3d, cfg_blocks=None, frame_h: int = 480,
+                 frame_w: int = 640, reso: int = 416, inp_h: int = 320, inp_w: int = 256, n_kp: int = 50,
+                 left_number: int = 50, conf: float = 0.01, pnp_mode: int = stages.MODE_RANSAC, reproj_thr: float = 12.0,
+                 n_hyp: int = 64, seed: int = 0, cam_K=stages.CAM_K, device=None):
+        """yolo_streams: fp32 darknet weight stream (or list, one per object slot); kpd_state_dicts: FastPose
+        state_dict (or list); kp3d: float64 [K,3] (or [n_slots,K,3]) key-point model in metres."""
+        _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.B = int(max_batch)
+        self.frame_h, self.frame_w, self.reso, self.inp_h, self.inp_w = frame_h, frame_w, reso, inp_h, inp_w
+        self.K, self.left_number, self.conf = int(n_kp), int(left_number), float(conf)
+        self.pnp_mode, self.reproj_thr, self.n_hyp, self.seed = int(pnp_mode), float(reproj_thr), int(n_hyp), int(seed)
+        self.cam_K = np.asarray(cam_K, np.float64)
+        if not isinstance(yolo_streams, (list, tuple)):
+            yolo_streams = [yolo_streams]
+        if not isinstance(kpd_state_dicts, (list, tuple)):
+            kpd_state_dicts = [kpd_state_dicts]
+        assert len(yolo_streams) == len(kpd_state_dicts)
+        self.n_slots = len(yolo_streams)
+        blocks = cfg_blocks if cfg_blocks is not None else yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+        self.blocks = blocks
+
+        self.yolo: list[_net.Net] = []
+        self.kpd: list[_net.Net] = []
+        self.heads: list[list[dict]] = []
+        self.hm_id: list[int] = []
+        with torch.cuda.device(self.device):
+            for s in range(self.n_slots):
+                y = _net.Net(self.B, reso, reso, _lib.IN_U8X4, share=self.yolo[0] if s else None, device=self.device.index)
+                params, used = _net.split_darknet_stream(blocks, np.asarray(yolo_streams[s], np.float32))
+                self.heads.append(_net.build_darknet(y, blocks, params))
+                self.yolo.append(y)
+                k = _net.Net(self.B, inp_h, inp_w, _lib.IN_F16X4, share=self.kpd[0] if s else None, device=self.device.index)
+                self.hm_id.append(_net.build_fastpose(k, kpd_state_dicts[s], self.K))
+                self.kpd.append(k)
+            kp3d = np.asarray(kp3d, np.float64)
+            if kp3d.ndim == 2:
+                kp3d = np.broadcast_to(kp3d[None], (self.n_slots,) + kp3d.shape)
+            assert kp3d.shape == (self.n_slots, self.K, 3), kp3d.shape
+            self.kp3d = torch.from_numpy(np.array(kp3d, np.float64, copy=True)).to(self.device)
+            dev, B, K = self.device, self.B, self.K
+            f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+            self.det = torch.zeros((B, 8), dtype=f32, device=dev)
+            self.box = torch.zeros((B, 4), dtype=f32, device=dev)
+            self.det_score = torch.zeros((B,), dtype=f32, device=dev)
+            self.row = torch.zeros((B,), dtype=i32, device=dev)
+            self.valid = torch.zeros((B,), dtype=u8, device=dev)
+            self.pt1 = torch.zeros((B, 2), dtype=f32, device=dev)
+            self.pt2 = torch.zeros((B, 2), dtype=f32, device=dev)
+            self.preds_hm = torch.zeros((B, K, 2), dtype=f32, device=dev)
+            self.preds_img = torch.zeros((B, K, 2), dtype=f32, device=dev)
+            self.maxval = torch.zeros((B, K), dtype=f32, device=dev)
+            self.hm_idx = torch.zeros((B, K), dtype=i32, device=dev)
+            self.keypoints = torch.zeros((B, K, 2), dtype=f32, device=dev)
+            self.kp_score = torch.zeros((B, K), dtype=f32, device=dev)
+            self.proposal = torch.zeros((B,), dtype=f32, device=dev)
+            self.selected = torch.zeros((B, K), dtype=u8, device=dev)
+            self.R = torch.zeros((B, 9), dtype=torch.float64, device=dev)
+            self.t = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+            self.inlier = torch.zeros((B, K), dtype=u8, device=dev)
+            self.status = torch.zeros((B,), dtype=i32, device=dev)
+            self.records = torch.zeros((B, _lib.RECORD_BYTES), dtype=u8, device=dev)
+            self.img_idx = torch.arange(B, dtype=i32, device=dev)
+            self.model_idx = torch.zeros((B,), dtype=i32, device=dev)
+            self.frames = torch.zeros((B, frame_h, frame_w, 3), dtype=u8, device=dev)
+        self._cam = (C.c_double * 4)(self.cam_K[0, 0], self.cam_K[1, 1], self.cam_K[0, 2], self.cam_K[1, 2])
+        self._head_args = []
+        for s in range(self.n_slots):
+            hs = self.heads[s]
+            infos = [self.yolo[s].tensor_info(h["tensor"]) for h in hs]
+            nh = len(hs)
+            self._head_args.append(dict(
+                ptrs=(C.c_void_p * nh)(*[i["ptr"] for i in infos]),
+                grids=(C.c_int * nh)(*[h["grid"] for h in hs]),
+                pitches=(C.c_int * nh)(*[i["pitch"] for i in infos]),
+                anchors=(C.c_float * (nh * 6))(*[float(v) for h in hs for wh in h["anchors"] for v in wh]),
+                n=nh, n_attr=5 + hs[0]["classes"]))
+        self._graphs: dict = {}
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def flops_per_image(self) -> float:
+        return self.yolo[0].flops_per_image + self.kpd[0].flops_per_image
+
+    def count_launches(self, n_slots_in_batch: int = 1) -> int:
+        """kernel launches one step enqueues: per slot 2 resize passes + detector ops + decode + crop + keypoint-net
+        ops + heat-map decode; then pnp + pack once."""
+        per_slot = 2 + self.yolo[0].num_ops + 1 + 1 + self.kpd[0].num_ops + 1
+        return per_slot * n_slots_in_batch + 2
+
+    def _enqueue_slot(self, slot: int, b0: int, n: int, st) -> None:
+        """Run images [b0, b0+n) of the current batch through slot `slot`'s networks (frames already on device)."""
+        L, e = _lib.lib(), self.yolo[slot].engine.handle
+        yolo, kpd = self.yolo[slot], self.kpd[slot]
+        off = lambda t: C.c_void_p(t.data_ptr() + b0 * t.stride(0) * t.element_size())  # noqa: E731
+        # a1: resize straight into the detector's input buffer
+        _lib.check(L.bp_resize_bicubic(e, off(self.frames), n, self.frame_h, self.frame_w, self.reso, self.reso,
+                                       C.c_void_p(yolo.tensor_info(0)["ptr"]), None, st), "bp_resize_bicubic")
+        _lib.check(L.bp_net_forward(yolo.handle, n, st), "bp_net_forward(yolo)")
+        ha = self._head_args[slot]
+        _lib.check(L.bp_yolo_decode_argmax(e, ha["ptrs"], ha["grids"], ha["pitches"], ha["n"], ha["anchors"], ha["n_attr"], n,
+                                           self.reso, self.conf, self.frame_w, self.frame_h, off(self.det), off(self.box),
+                                           off(self.det_score), off(self.row), off(self.valid), None, st), "bp_yolo_decode_argmax")
+        # a6: crop straight into the keypoint net's input buffer (img_idx is relative to the frame slice)
+        _lib.check(L.bp_crop_resize(e, off(self.frames), self.frame_h, self.frame_w, off(self.box), _lib.ptr(self.img_idx),
+                                    off(self.valid), n, self.inp_h, self.inp_w, C.c_void_p(kpd.tensor_info(0)["ptr"]), None,
+                                    off(self.pt1), off(self.pt2), st), "bp_crop_resize")
+        _lib.check(L.bp_net_forward(kpd.handle, n, st), "bp_net_forward(kpd)")
+        hi = kpd.tensor_info(self.hm_id[slot])
+        _lib.check(L.bp_heatmap_decode(e, C.c_void_p(hi["ptr"]), hi["H"] * hi["W"] * hi["pitch"], 1, hi["pitch"], n, self.K,
+                                       hi["H"], hi["W"], self.inp_h, self.inp_w, off(self.pt1), off(self.pt2),
+                                       off(self.preds_hm), off(self.preds_img), off(self.maxval), off(self.hm_idx), st),
+                   "bp_heatmap_decode")
+
+    def _enqueue_tail(self, n: int, image_index0: int, st) -> None:
+        L, e = _lib.lib(), self.yolo[0].engine.handle
+        _lib.check(L.bp_pose_pnp(e, _lib.ptr(self.preds_img), _lib.ptr(self.maxval), _lib.ptr(self.det_score),
+                                 _lib.ptr(self.valid), n, self.K, _lib.ptr(self.kp3d), _lib.ptr(self.model_idx),
+                                 C.cast(self._cam, C.c_void_p), self.left_number, self.pnp_mode, self.reproj_thr, self.n_hyp,
+                                 self.seed & 0xFFFFFFFF, _lib.ptr(self.keypoints), _lib.ptr(self.kp_score),
+                                 _lib.ptr(self.proposal), _lib.ptr(self.selected), _lib.ptr(self.R), _lib.ptr(self.t),
+                                 _lib.ptr(self.inlier), _lib.ptr(self.status), st), "bp_pose_pnp")
+        _lib.check(L.bp_pack_records(e, n, self.K, int(image_index0), _lib.ptr(self.box), _lib.ptr(self.det_score),
+                                     _lib.ptr(self.keypoints), _lib.ptr(self.kp_score), _lib.ptr(self.proposal),
+                                     _lib.ptr(self.R), _lib.ptr(self.t), _lib.ptr(self.status), _lib.ptr(self.records), st),
+                   "bp_pack_records")
+
+    def _enqueue(self, n: int, groups, image_index0: int) -> None:
+        st = _lib.stream_ptr()
+        for slot, b0, cnt in groups:
+            self._enqueue_slot(slot, b0, cnt, st)
+        self._enqueue_tail(n, image_index0, st)
+
+    # ------------------------------------------------------------------------------------------------
+    def run_device(self, n: int | None = None, groups=None, image_index0: int = 0, graph: bool = False) -> torch.Tensor:
+        """Process the first n frames already resident in `self.frames` (grouped by slot: list of (slot, first, count),
+        frames of one slot contiguous; `self.model_idx` must match).  Returns the records tensor view [n, RECORD_BYTES]
+        (device); nothing has synchronised."""
+        n = self.B if n is None else int(n)
+        groups = [(0, 0, n)] if groups is None else list(groups)
+        with torch.cuda.device(self.device):
+            if not graph:
+                self._enqueue(n, groups, image_index0)
+            else:
+                key = (n, tuple(groups), image_index0)
+                g = self._graphs.get(key)
+                if g is None:
+                    # warm-up outside capture (lazy allocations, func attributes), then capture on a side stream
+                    self._enqueue(n, groups, image_index0)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue(n, groups, image_index0)
+                    self._graphs[key] = g
+                g.replay()
+        self.launches_per_step = self.count_launches(len(groups))
+        return self.records[:n]
+
+    def run(self, frames_u8, obj_slots=None, image_index0: int = 0, graph: bool = False) -> np.ndarray:
+        """Public end-to-end call: frames uint8 [n,H,W,3] RGB (host numpy / pinned torch / cuda tensor), optional
+        per-frame object slot ids.  Returns the host structured array of bp_record (one per frame, input order)."""
+        fr = torch.as_tensor(frames_u8)
+        n = int(fr.shape[0])
+        assert n <= self.B and tuple(fr.shape[1:]) == (self.frame_h, self.frame_w, 3) and fr.dtype == torch.uint8
+        order = None
+        groups = [(0, 0, n)]
+        if obj_slots is not None and self.n_slots > 1:
+            slots = np.asarray(obj_slots, np.int64)
+            order = np.argsort(slots, kind="stable")
+            groups, s0 = [], 0
+            sorted_slots = slots[order]
+            for s in np.unique(sorted_slots):
+                cnt = int((sorted_slots == s).sum())
+                groups.append((int(s), s0, cnt))
+                s0 += cnt
+            idx = torch.from_numpy(order)
+            fr = fr[idx.to(fr.device)] if fr.is_cuda else fr[idx]
+            self.model_idx[:n].copy_(torch.from_numpy(sorted_slots.astype(np.int32)), non_blocking=True)
+        self.frames[:n].copy_(fr, non_blocking=True)
+        rec = self.run_device(n, groups, image_index0, graph=graph)
+        out = stages.records_to_numpy(rec)
+        if order is not None:
+            inv = np.empty_like(order)
+            inv[order] = np.arange(n)
+            out = out[inv]
+            out["image_index"] = image_index0 + np.arange(n)
+        return out

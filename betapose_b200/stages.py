@@ -41,7 +41,7 @@ def yolo_decode_argmax(heads, anchors, B: int, reso: int = 416, conf: float = 0.
                        n_attr: int = 6, want_decoded: bool = False):
     """heads: list of fp32 NHWC tensors [>=B, g, g, C] (strided views allowed, channel stride 1);
     anchors: list (per head) of 3 (w,h) pairs in pixels.
-    -> dict(det [B,8], box [B,4], row int32 [B], valid uint8 [B], decoded [B,R,n_attr] | None)"""
+    -> dict(det [B,8], box [B,4], score [B], row int32 [B], valid uint8 [B], decoded [B,R,n_attr] | None)"""
     h0 = heads[0]
     e = _eng(h0)
     nh = len(heads)
@@ -52,14 +52,16 @@ def yolo_decode_argmax(heads, anchors, B: int, reso: int = 416, conf: float = 0.
     dev = h0.device
     det = torch.empty((B, 8), dtype=torch.float32, device=dev)
     box = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    score = torch.empty((B,), dtype=torch.float32, device=dev)
     row = torch.empty((B,), dtype=torch.int32, device=dev)
     valid = torch.empty((B,), dtype=torch.uint8, device=dev)
     total = sum(3 * int(h.shape[1]) ** 2 for h in heads)
     dec = torch.empty((B, total, n_attr), dtype=torch.float32, device=dev) if want_decoded else None
     _lib.check(_lib.lib().bp_yolo_decode_argmax(e.handle, ptrs, grids, pitches, nh, flat, n_attr, B, reso, float(conf),
-                                                frame_w, frame_h, _lib.ptr(det), _lib.ptr(box), _lib.ptr(row),
+                                                frame_w, frame_h, _lib.ptr(det), _lib.ptr(box), _lib.ptr(score),
+                                                _lib.ptr(row),
                                                 _lib.ptr(valid), _lib.ptr(dec), _lib.stream_ptr()), "bp_yolo_decode_argmax")
-    return dict(det=det, box=box, row=row, valid=valid, decoded=dec)
+    return dict(det=det, box=box, score=score, row=row, valid=valid, decoded=dec)
 
 
 def crop_resize(frames_u8: torch.Tensor, box: torch.Tensor, img_idx: torch.Tensor, valid: torch.Tensor | None = None,

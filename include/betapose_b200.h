@@ -52,7 +52,7 @@ void bp_engine_destroy(bp_engine* e);
  * A bp_net is an ordered list of fused layer ops over NHWC fp16 tensors, built once (weights uploaded, BN
  * folded, TMA descriptors encoded for max_batch) and replayed per batch.  It replaces
  *   Darknet.build_model / load_weights / forward   (3_6Dpose_estimator/yolo/darknet.py:223-432) and
- *   FastPose / SEResnet / Bottleneck / SELayer / DUC (KPD/src/models/FastPose.py:13-35, layers/*.py).
+ *   FastPose / SEResnet / Bottleneck / SELayer / DUC (KPD/src/models/FastPose.py:13-35, layers/{SE_Resnet,SE_module,DUC}.py).
  * Tensors are named by small integer ids returned by the builder calls.
  */
 #define BP_IN_U8X4 0  /* input tensor is uint8 [N,H,W,4] (RGBX), scaled by 1/255 when read  */
@@ -132,11 +132,13 @@ int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int H, int W, 
  * unless `decoded` != NULL.  heads[i]: fp32 NHWC [B,g_i,g_i,pitch_i] raw head i (stride 32,16,8 order),
  * channel c = a*(5+classes)+attr.  anchors: 2*3 floats per head (pixels).
  * Outputs per image: det[B,8] = (img, x1,y1,x2,y2 in reso-space, obj, cls_conf, cls_idx), box[B,4] rescaled to
- * the frame, row[B] winning flat row (anchor-major, lowest index on ties), valid[B] (0: no candidate > conf). */
+ * the frame, score[B] = objectness of the winner (what DetectionLoader hands on as `scores`, dataloader.py:352),
+ * row[B] winning flat row (anchor-major, lowest index on ties), valid[B] (0: no candidate > conf).
+ * score and decoded may be NULL. */
 int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, const int* grids, const int* pitches,
                           int n_heads, const float* anchors, int n_attr, int B, int reso, float conf, int frame_w,
-                          int frame_h, float* det, float* box, int32_t* row, uint8_t* valid, float* decoded,
-                          void* stream);
+                          int frame_h, float* det, float* box, float* score, int32_t* row, uint8_t* valid,
+                          float* decoded, void* stream);
 
 /* a6: im_to_torch + crop_from_dets + cropBox (KPD/src/utils/img.py:13-18,242-262; dataloader.py:794-835).
  * frames uint8 [F,H,W,3] RGB; box[n,4]; img_idx[n] (frame of each box); valid[n] (may be NULL).

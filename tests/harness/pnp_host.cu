@@ -38,23 +38,27 @@ extern "C" int bp_host_pnp(const double* pw, const double* uv, const unsigned ch
       }
     }
     if (bc < 4) { *best_h = -1; return -1; }
-    for (int j = 0; j < K; ++j) {
-      if (!sel[j]) continue;
-      double u, v, z;
-      project(bR, bt, pw + 3 * j, fx, fy, cx, cy, &u, &v, &z);
-      const double e2 = (u - uv[2 * j]) * (u - uv[2 * j]) + (v - uv[2 * j + 1]) * (v - uv[2 * j + 1]);
-      inl[j] = (z > 0 && e2 <= thr * thr) ? 1 : 0;
-    }
   } else {
     int m = 0;
     for (int j = 0; j < K; ++j)
       if (sel[j]) pool[m++] = j;
     if (!epnp(pw, uv, pool, m, fx, fy, cx, cy, bR, bt)) return -1;
-    for (int j = 0; j < K; ++j) inl[j] = sel[j] ? 1 : 0;
     *best_h = 0;
   }
   SingleLane ln;
-  lm_refine(ln, bR, bt, pw, uv, inl, K, fx, fy, cx, cy, 50);
+  for (int round = 0; round < BP_PNP_LO_ROUNDS; ++round) {
+    int changed = 0, cnt = 0;
+    for (int j = 0; j < K; ++j) {
+      const unsigned char in = sel[j] && (!ransac || within_threshold(bR, bt, pw, uv, j, fx, fy, cx, cy, thr * thr)) ? 1 : 0;
+      changed |= in != inl[j];
+      inl[j] = in;
+      cnt += in;
+    }
+    if (round > 0 && !changed) break;
+    if (cnt < 4) { memset(inl, 0, K); return -1; }
+    lm_refine(ln, bR, bt, pw, uv, inl, K, fx, fy, cx, cy, 50);
+    if (!ransac) break;
+  }
   memcpy(R_out, bR, sizeof bR);
   memcpy(t_out, bt, sizeof bt);
   return 0;

@@ -1,0 +1,270 @@
+"""GPU parity of the two networks (tcgen05 conv ops through bp_net) against the torch fp32 CPU oracle (oracle/nets.py).
+fp16 storage / fp32 accumulate vs an fp32 reference: tolerance stated per test, relative to the tensor's scale."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets as onets
+
+pytestmark = pytest.mark.gpu
+
+MINI_CFG = """
+[convolutional]
+batch_normalize=1
+filters=32
+size=3
+stride=1
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=3
+stride=2
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=32
+size=1
+stride=1
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=3
+stride=1
+pad=1
+activation=leaky
+
+[shortcut]
+from=-3
+activation=linear
+
+[convolutional]
+batch_normalize=1
+filters=128
+size=3
+stride=2
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=1
+stride=1
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=128
+size=3
+stride=1
+pad=1
+activation=leaky
+
+[shortcut]
+from=-3
+activation=linear
+
+[convolutional]
+filters=18
+size=1
+stride=1
+pad=1
+activation=linear
+
+[yolo]
+mask = 6,7,8
+anchors = 10,13,  16,30,  33,23,  30,61,  62,45,  59,119,  116,90,  156,198,  373,326
+classes=1
+num=9
+
+[route]
+layers = ROUTE1
+
+[convolutional]
+batch_normalize=1
+filters=32
+size=1
+stride=1
+pad=1
+activation=leaky
+
+[upsample]
+stride=2
+
+[route]
+layers = -1, 4
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=3
+stride=1
+pad=1
+activation=leaky
+
+[convolutional]
+filters=18
+size=1
+stride=1
+pad=1
+activation=linear
+
+[yolo]
+mask = 3,4,5
+anchors = 10,13,  16,30,  33,23,  30,61,  62,45,  59,119,  116,90,  156,198,  373,326
+classes=1
+num=9
+"""
+
+
+def _stream_for(blocks, seed, in_c=3):
+    rng = np.random.default_rng(seed)
+    from betapose_b200 import net as bnet
+
+    info = bnet.infer_darknet_shapes(blocks, 64)
+    chunks = []
+    for i, b in enumerate(blocks):
+        if b["type"] != "convolutional":
+            continue
+        cin = in_c if i == 0 else info[i - 1]["C"]
+        cout, k = int(b["filters"]), int(b["size"])
+        if int(b.get("batch_normalize", 0)):
+            chunks += [rng.normal(0, 0.2, cout), rng.uniform(0.6, 1.4, cout), rng.normal(0, 0.2, cout), rng.uniform(0.5, 1.5, cout)]
+        else:
+            chunks.append(rng.normal(0, 0.5, cout))
+        chunks.append(rng.normal(0, np.sqrt(2.0 / (cin * k * k)), cout * cin * k * k))
+    return np.concatenate(chunks).astype(np.float32)
+
+
+def _run_yolo(blocks, stream, x_u8, reso):
+    """x_u8 [B,reso,reso,3] uint8 -> list of fp32 heads [B,18,g,g] from the engine."""
+    from betapose_b200 import _lib, net as bnet
+
+    B = x_u8.shape[0]
+    n = bnet.Net(B, reso, reso, _lib.IN_U8X4)
+    params, used = bnet.split_darknet_stream(blocks, stream)
+    assert used == stream.size
+    heads = bnet.build_darknet(n, blocks, params)
+    inp = n.input(B)
+    inp[..., :3] = torch.from_numpy(x_u8).cuda()
+    n.forward(B)
+    torch.cuda.synchronize()
+    return n, [n.tensor(h["tensor"], B).permute(0, 3, 1, 2).contiguous().cpu() for h in heads]
+
+
+@pytest.mark.parametrize("route1,fused", [("-3", True), ("-4", False)])
+def test_mini_darknet_all_fusions(route1, fused):
+    """conv+bn+leaky, fused shortcut, fused upsample + concat route, alias route, fp32 heads.  With route1 = -4 the
+    route taps the conv *before* a shortcut, so that shortcut cannot be folded into the conv: exercises bp_net_add."""
+    from betapose_b200 import yolo_cfg
+
+    blocks = yolo_cfg.parse_cfg_text(MINI_CFG.replace("ROUTE1", route1))
+    stream = _stream_for(blocks, 0)
+    rng = np.random.default_rng(1)
+    x = rng.integers(0, 256, (3, 64, 64, 3), dtype=np.uint8)
+    n, got = _run_yolo(blocks, stream, x, 64)
+    params, _ = onets.split_darknet_weights(blocks, stream)
+    ref = onets.darknet_forward(blocks, params, torch.from_numpy(x).permute(0, 3, 1, 2).float() / 255.0)
+    assert len(got) == len(ref) == 2
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape
+        err = (g - r).abs().max().item()
+        assert err <= 2e-2 * r.abs().max().item(), (err, r.abs().max().item())
+    # the route/upsample/shortcut blocks must all have been absorbed into conv launches
+    descs = [n.op_desc(i)[0] for i in range(n.num_ops)]
+    if fused:
+        assert all(d.startswith(("conv", "im2col")) for d in descs), descs
+    else:
+        assert sum(d.startswith("add") for d in descs) == 1, descs
+
+
+def test_yolov3_full_vs_oracle(yolo_blocks, yolo_stream, frames8):
+    from betapose_b200 import stages
+    from oracle import restate as R
+
+    B = 2
+    fr = torch.from_numpy(frames8[:B]).cuda()
+    u8x4, _ = stages.resize_bicubic(fr, 416, 416)
+    x = u8x4[..., :3].cpu().numpy()
+    n, got = _run_yolo(yolo_blocks, yolo_stream, x, 416)
+    assert n.num_ops == 76  # stem im2col + 75 convs: every shortcut / route / upsample fused away
+    assert abs(n.flops_per_image - 65.29e9) < 0.05e9
+    params, used = onets.split_darknet_weights(yolo_blocks, yolo_stream)
+    assert used == yolo_stream.size
+    with torch.no_grad():
+        ref = onets.darknet_forward(yolo_blocks, params, torch.from_numpy(x).permute(0, 3, 1, 2).float() / 255.0)
+    for g, r in zip(got, ref):
+        scale = r.abs().max().item()
+        err = (g - r).abs()
+        assert err.max().item() <= 3e-2 * scale, (err.max().item(), scale)
+        assert err.mean().item() <= 3e-3 * scale
+    # decisions downstream of the fp16 network: the winning row is the oracle's, or within fp16 noise of it
+    pred_g = R.yolo_decode([g.numpy() for g in got])
+    pred_r = R.yolo_decode([r.numpy() for r in ref])
+    _, rows_g = R.write_results(pred_g)
+    _, rows_r = R.write_results(pred_r)
+    for b in range(B):
+        if rows_g[b] != rows_r[b]:
+            assert abs(pred_r[b, rows_g[b], 4] - pred_r[b, rows_r[b], 4]) < 5e-3
+
+
+def test_fastpose_full_vs_oracle(kpd_sd, frames8):
+    from betapose_b200 import _lib, net as bnet, stages
+    from oracle import restate as R
+
+    B = 2
+    fr = torch.from_numpy(frames8[:B]).cuda()
+    box = torch.tensor([[200.0, 100.0, 420.0, 380.0], [50.0, 60.0, 300.0, 400.0]], device="cuda")
+    crop = stages.crop_resize(fr, box, torch.arange(B, dtype=torch.int32, device="cuda"), want_f32=True)
+    n = bnet.Net(B, 320, 256, _lib.IN_F16X4)
+    hm_id = bnet.build_fastpose(n, kpd_sd, 50)
+    n.input(B).copy_(crop["f16x4"])
+    n.forward(B)
+    torch.cuda.synchronize()
+    got = n.tensor(hm_id, B).permute(0, 3, 1, 2).contiguous().cpu()
+    assert abs(n.flops_per_image - (32.097e9 + 0.022e9)) < 0.05e9
+    with torch.no_grad():
+        ref = onets.fastpose_forward(kpd_sd, crop["f32"].cpu())
+    assert got.shape == ref.shape == (B, 50, 80, 64)
+    scale = ref.abs().max().item()
+    err = (got - ref).abs()
+    assert err.max().item() <= 3e-2 * scale, (err.max().item(), scale)
+    assert err.mean().item() <= 3e-3 * scale
+    # arg-max agreement: identical unless the oracle's top two values are within fp16 noise
+    ig = got.reshape(B, 50, -1).argmax(2)
+    ir = ref.reshape(B, 50, -1).argmax(2)
+    agree = (ig == ir).float().mean().item()
+    assert agree >= 0.9, agree
+
+
+def test_net_batch_smaller_than_max(yolo_blocks):
+    """bp_net built for max_batch = 4 and run at batch 1, 3: rows of the unused images must not be touched."""
+    from betapose_b200 import _lib, net as bnet, yolo_cfg
+
+    blocks = yolo_cfg.parse_cfg_text(MINI_CFG.replace("ROUTE1", "-3"))
+    stream = _stream_for(blocks, 3)
+    params, _ = bnet.split_darknet_stream(blocks, stream)
+    n = bnet.Net(4, 64, 64, _lib.IN_U8X4)
+    heads = bnet.build_darknet(n, blocks, params)
+    x = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (4, 64, 64, 4), dtype=np.uint8)).cuda()
+    n.input(4).copy_(x)
+    n.forward(4)
+    torch.cuda.synchronize()
+    full = [n.tensor(h["tensor"], 4).clone() for h in heads]
+    for h in heads:
+        n.tensor(h["tensor"], 4).zero_()
+    n.forward(3)
+    torch.cuda.synchronize()
+    for h, f in zip(heads, full):
+        t = n.tensor(h["tensor"], 4)
+        assert torch.equal(t[:3], f[:3])
+        assert float(t[3].abs().max()) == 0.0
