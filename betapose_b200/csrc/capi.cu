@@ -35,6 +35,7 @@ int bp_engine_create(int device, bp_engine** out) {
   cudaFree(0);
   bp_engine* e = new bp_engine();
   e->device = device;
+  e->num_sms = prop.multiProcessorCount;
   std::string err;
   if (!e->tmap.load(&err)) {
     delete e;

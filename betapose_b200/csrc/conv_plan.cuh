@@ -1,6 +1,7 @@
 // Host-side planning + launch of one conv_umma_kernel instance: picks the tile configuration, encodes the
 // two TMA descriptors once (buffers are owned by the engine, so addresses are stable) and replays the launch.
 #pragma once
+#include <algorithm>
 #include <string>
 
 #include "conv_tcgen05.cuh"
@@ -24,12 +25,15 @@ struct ConvDesc {
   void* out = nullptr;
   int out_pitch = 0, out_coff = 0, out_f32 = 0, store_mode = STORE_PLAIN;
   int force_block_n = 0;  // 0 = heuristic
-  int force_stages = 0;
+  int force_stages = 0;   // kept for the harness; the stage count now follows from the tile configuration
+  int num_sms = 148;
 };
 
 struct ConvPlan {
   alignas(64) CUtensorMap tmA;
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmOut;  // valid when args.tma_store
+  alignas(64) CUtensorMap tmRes;  // valid when args.tma_store && residual
   ConvArgs args;
   int block_n = 0, block_k = 0, stages = 0, grid = 0;
   int P = 0, Q = 0;
@@ -46,21 +50,19 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  conv_umma_kernel<BN, BK, ST><<<pl.grid, 128, Cfg::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pl.args);
+  conv_umma_kernel<BN, BK, ST><<<pl.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
   return cudaGetLastError();
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
 #define BP_CASE(BN, BK, ST) \
   if (pl.block_n == BN && pl.block_k == BK && pl.stages == ST) return launch_cfg<BN, BK, ST>(pl, st);
-  BP_CASE(256, 64, 4)
-  BP_CASE(256, 64, 2)
-  BP_CASE(128, 64, 6)
-  BP_CASE(128, 64, 3)
-  BP_CASE(64, 64, 4)
-  BP_CASE(32, 64, 4)
-  BP_CASE(64, 32, 4)
-  BP_CASE(32, 32, 4)
+  BP_CASE(256, 64, 3)
+  BP_CASE(128, 64, 4)
+  BP_CASE(64, 64, 6)
+  BP_CASE(32, 64, 6)
+  BP_CASE(64, 32, 8)
+  BP_CASE(32, 32, 8)
 #undef BP_CASE
   return cudaErrorInvalidConfiguration;
 }
@@ -88,8 +90,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
     if (err) *err = "Cout_pad must be a multiple of BLOCK_N";
     return false;
   }
-  int st = d.force_stages;
-  if (!st) st = bn == 256 ? 4 : (bn == 128 ? 3 : 4);
+  const int st = bn == 256 ? 3 : (bn == 128 ? 4 : (block_k == 64 ? 6 : 8));
   const int K = d.R * d.S * d.C;
   const int num_kb = (K + block_k - 1) / block_k;
 
@@ -101,13 +102,15 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   const int n_tiles = d.Cout_pad / bn;
   // tiles whose channels are all padding are never launched
   const int n_tiles_live = (d.Cout + bn - 1) / bn;
-  pl->grid = ((M + 127) / 128) * n_tiles_live;
+  const int m_tiles = (M + 127) / 128;
+  pl->grid = std::min(m_tiles * n_tiles_live, d.num_sms);  // persistent: one CTA per SM
   (void)n_tiles;
   pl->flops = 2.0 * M * (double)d.Cout * K;
 
   ConvArgs& a = pl->args;
   a.M = M;
   a.n_tiles = n_tiles_live;
+  a.m_tiles = m_tiles;
   a.num_kb = num_kb;
   a.a_im2col = matrix ? 0 : 1;
   a.P = P;
@@ -121,6 +124,10 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.res_mode = d.res ? d.res_mode : RES_NONE;
   a.store_mode = d.store_mode;
   a.out_f32 = d.out_f32;
+  a.tma_store = (!d.out_f32 && d.store_mode == STORE_PLAIN && d.Cout % 8 == 0 && d.out_pitch % 8 == 0 && d.out_coff % 8 == 0 &&
+                 (!d.res || d.res_pitch % 8 == 0))
+                    ? 1
+                    : 0;
   a.out_pitch = d.out_pitch;
   a.out_coff = d.out_coff;
   a.res_pitch = d.res_pitch;
@@ -138,6 +145,16 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   }
   if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn, block_k, err))
     return false;
+  pl->tmOut = pl->tmB;  // placeholders keep the kernel parameters well-formed when the TMA epilogue is off
+  pl->tmRes = pl->tmB;
+  if (a.tma_store) {
+    // dense [M pixels, Cout channels] fp16 boxes of 128 x CHUNK; rows >= M and channels >= Cout are clipped by TMA
+    const int chunk = bn >= 64 ? 64 : 32;
+    const __half* obase = reinterpret_cast<const __half*>(d.out) + d.out_coff;
+    if (!make_tmap_2d(api, &pl->tmOut, obase, (uint64_t)M, (uint64_t)d.Cout, (uint64_t)d.out_pitch, 128, chunk, err)) return false;
+    if (d.res && !make_tmap_2d(api, &pl->tmRes, d.res, (uint64_t)M, (uint64_t)d.Cout, (uint64_t)d.res_pitch, 128, chunk, err))
+      return false;
+  }
   return true;
 }
 

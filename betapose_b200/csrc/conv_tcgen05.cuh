@@ -1,12 +1,19 @@
 // Implicit-GEMM convolution for sm_100a: D[M = B*P*Q pixels, N = Cout] = im2col(X)[M, K] * W[N, K]^T
 //   A (activations, NHWC fp16)  : TMA im2col loads (3x3 / strided) or TMA 2-D tiles (1x1 s1, explicit matrices)
 //   B (weights, [Cout][R][S][Cin] fp16, BN folded) : TMA 2-D tiles
-//   both land in 128B- (or 64B-) swizzled shared memory, K-major, and feed tcgen05.mma (M=128, N=BLOCK_N, K=16)
-//   accumulators live in TMEM; the epilogue reads them back with tcgen05.ld and fuses
-//   bias + activation + residual add + {plain | nearest-x2 | pixel-shuffle} store.
-// One CTA = one 128 x BLOCK_N output tile, 4 warps: warp0 = TMA producer, warp1 = MMA issuer (+TMEM owner),
-// all four warps drain TMEM (warp w owns lanes 32w..32w+31). Several CTAs co-reside per SM so one CTA's
-// epilogue overlaps another's main loop.
+//   both land in 128B- (or 64B-) swizzled shared memory, K-major, and feed tcgen05.mma (M=128, N=BLOCK_N, K=16);
+//   accumulators live in TMEM, double buffered (2 x BLOCK_N columns).
+//
+// Persistent, warp-specialised: one CTA per SM loops over output tiles (n-tile fastest, so the CTAs running at the
+// same time share A rows in L2 and all share the weights).
+//   warp 0    : TMA producer (A + B per k-block, STAGES-deep mbarrier ring)
+//   warp 1    : MMA issuer (one elected lane) + TMEM owner
+//   warps 2-5 : epilogue.  tcgen05.ld -> bias + activation (+ residual) -> fp16 -> swizzled smem staging ->
+//               TMA store (cp.async.bulk.tensor), 64 output channels at a time; the residual tile arrives by TMA
+//               too (prefetched while the main loop of the same tile is still running).  The epilogue of tile i
+//               overlaps the main loop of tile i+1 through the second TMEM accumulator.
+//   Stores that are not a dense [pixels, channels] box (fp32 heads, fused nearest-x2 upsample, fused PixelShuffle)
+//   go out as per-thread 16-byte stores instead.
 //
 // Replaces, for the reference, every nn.Conv2d+BatchNorm2d+activation (+shortcut) block of
 // 3_6Dpose_estimator/yolo/darknet.py:252-259,333-340 and KPD/src/models/layers/SE_Resnet.py:11-40, DUC.py:12-22.
@@ -21,7 +28,8 @@ enum : int { STORE_PLAIN = 0, STORE_UPSAMPLE2 = 1, STORE_PIXSHUF2 = 2 };
 
 struct ConvArgs {
   int M;         // output pixels (B*P*Q)
-  int n_tiles;   // Cout_pad / BLOCK_N
+  int n_tiles;   // live N tiles (ceil(Cout / BLOCK_N))
+  int m_tiles;   // ceil(M / 128)
   int num_kb;    // K / BLOCK_K
   int a_im2col;  // 1: A through the im2col tensor map over NHWC; 0: A is a row-major [M, K] matrix
   int P, Q;      // output height / width
@@ -33,6 +41,7 @@ struct ConvArgs {
   int res_mode;
   int store_mode;
   int out_f32;
+  int tma_store;  // 1: dense fp16 box -> staged TMA store (+ TMA residual); 0: per-thread stores
   int out_pitch;  // elements between consecutive output pixels
   int out_coff;   // channel offset inside the output pixel
   int res_pitch;
@@ -57,219 +66,409 @@ struct ConvCfg {
   static constexpr int A_BYTES = BLOCK_M * SWZ;
   static constexpr int B_BYTES = BLOCK_N * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for 1024B alignment
+  static constexpr int CHUNK = BLOCK_N >= 64 ? 64 : 32;  // output channels per epilogue chunk / TMA store box
+  static constexpr int OUT_SWZ = CHUNK * 2;
+  static constexpr int CHUNK_BYTES = BLOCK_M * OUT_SWZ;
+  static constexpr int N_CHUNKS = BLOCK_N / CHUNK;
+  static constexpr int NBUF = 4;                       // ring of chunk buffers: residual lands in it, result leaves from it
+  static constexpr int EPI_BYTES = NBUF * CHUNK_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;  // + slack for 1024B alignment
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, each takes half of a chunk's columns
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
 };
 
+// byte offset of 16-byte unit j of row r inside a swizzled [128][ROW_BYTES] tile (TMA SWIZZLE_128B / SWIZZLE_64B)
+template <int ROW_BYTES>
+__device__ __forceinline__ uint32_t swz_off(int r, int j) {
+  if constexpr (ROW_BYTES == 128) return uint32_t(r * 128 + ((j ^ (r & 7)) << 4));
+  else return uint32_t(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+}
+
+// Epilogue math for one thread's NV consecutive channels of one output pixel: fp32 accumulator + fp32 bias, then
+// packed fp16: activation, residual.  `buf` points at this thread's first 16-byte unit slot; units are addressed
+// through swz_off so the same code reads the TMA-loaded residual and writes the TMA-stored result in place.
+template <int ACT, int RESMODE, int ROW_BYTES, int NV>
+__device__ __forceinline__ void epi_math_store(const uint32_t* a, const float* bias, uint8_t* tile, int row_l, int unit0) {
+#pragma unroll
+  for (int j = 0; j < NV / 8; ++j) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 8 + 4);
+    float v[8];
+    v[0] = __uint_as_float(a[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(a[j * 8 + 1]) + b0.y;
+    v[2] = __uint_as_float(a[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(a[j * 8 + 3]) + b0.w;
+    v[4] = __uint_as_float(a[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(a[j * 8 + 5]) + b1.y;
+    v[6] = __uint_as_float(a[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(a[j * 8 + 7]) + b1.w;
+    uint8_t* slot = tile + swz_off<ROW_BYTES>(row_l, unit0 + j);
+    uint4 pk;
+    __half2* h = reinterpret_cast<__half2*>(&pk);
+    if constexpr (ACT == ACT_SIGMOID) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        h[e] = __floats2half2_rn(1.f / (1.f + __expf(-v[2 * e])), 1.f / (1.f + __expf(-v[2 * e + 1])));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+    }
+    uint4 rv = make_uint4(0, 0, 0, 0);
+    if constexpr (RESMODE != RES_NONE) rv = *reinterpret_cast<const uint4*>(slot);
+    const __half2* r = reinterpret_cast<const __half2*>(&rv);
+    const __half2 zero = __float2half2_rn(0.f), slope = __float2half2_rn(0.1f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __half2 x = h[e];
+      if constexpr (RESMODE == RES_BEFORE_ACT) x = __hadd2(x, r[e]);
+      if constexpr (ACT == ACT_LEAKY) x = __hmax2(x, __hmul2(x, slope));  // slope < 1: max(x, 0.1 x)
+      if constexpr (ACT == ACT_RELU) x = __hmax2(x, zero);
+      if constexpr (RESMODE == RES_AFTER_ACT) x = __hadd2(x, r[e]);
+      h[e] = x;
+    }
+    *reinterpret_cast<uint4*>(slot) = pk;
+  }
+}
+
+template <int ROW_BYTES, int NV>
+__device__ __forceinline__ void epi_dispatch(int act, int res_mode, const uint32_t* a, const float* bias, uint8_t* tile,
+                                             int row_l, int unit0) {
+#define BP_EPI(A, R) epi_math_store<A, R, ROW_BYTES, NV>(a, bias, tile, row_l, unit0)
+  if (res_mode == RES_NONE) {
+    if (act == ACT_LEAKY) BP_EPI(ACT_LEAKY, RES_NONE);
+    else if (act == ACT_RELU) BP_EPI(ACT_RELU, RES_NONE);
+    else if (act == ACT_SIGMOID) BP_EPI(ACT_SIGMOID, RES_NONE);
+    else BP_EPI(ACT_NONE, RES_NONE);
+  } else if (res_mode == RES_AFTER_ACT) {
+    if (act == ACT_LEAKY) BP_EPI(ACT_LEAKY, RES_AFTER_ACT);
+    else if (act == ACT_RELU) BP_EPI(ACT_RELU, RES_AFTER_ACT);
+    else BP_EPI(ACT_NONE, RES_AFTER_ACT);
+  } else {
+    if (act == ACT_RELU) BP_EPI(ACT_RELU, RES_BEFORE_ACT);
+    else if (act == ACT_LEAKY) BP_EPI(ACT_LEAKY, RES_BEFORE_ACT);
+    else BP_EPI(ACT_NONE, RES_BEFORE_ACT);
+  }
+#undef BP_EPI
+}
+
 template <int BLOCK_N, int BLOCK_K, int STAGES>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES>;
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
+  constexpr int CHUNK = Cfg::CHUNK;
+  constexpr int N_CHUNKS = Cfg::N_CHUNKS;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t res_full_bar[Cfg::NBUF];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[BLOCK_N];
+  __shared__ __align__(16) float s_bias[2][BLOCK_N];
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;  // NBUF x CHUNK_BYTES
 
-  const int tile = blockIdx.x;
-  const int n_tile = tile % p.n_tiles;
-  const int m_tile = tile / p.n_tiles;
-  const int m0 = m_tile * Cfg::BLOCK_M;
-  const int n0 = n_tile * BLOCK_N;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) {
+      tma_prefetch_desc(&tmOut);
+      if (p.res_mode != RES_NONE) tma_prefetch_desc(&tmRes);
+    }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], Cfg::EPI_WARPS);  // one arrive per epilogue warp
+    }
+#pragma unroll
+    for (int s = 0; s < Cfg::NBUF; ++s) mbar_init(&res_full_bar[s], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<BLOCK_N>(&tmem_base_slot);
-  for (int i = threadIdx.x; i < BLOCK_N; i += 128) s_bias[i] = p.bias[n0 + i];
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    int w0 = 0, h0 = 0, img = 0;
-    if (p.a_im2col) {
-      const int pq = p.P * p.Q;
-      img = m0 / pq;
-      const int rem = m0 - img * pq;
-      const int op = rem / p.Q;
-      const int oq = rem - op * p.Q;
-      w0 = oq * p.stride - p.pad;
-      h0 = op * p.stride - p.pad;
-    }
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      if (lane == 0) {
-        uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        if (p.a_im2col) {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          const int fr = tap / p.S;
-          const int fs = tap - fr * p.S;
-          tma_load_im2col_4d(&tmA, &full_bar[s], sa, cb * BLOCK_K, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
-        } else {
-          tma_load_2d(&tmA, &full_bar[s], sa, kb * BLOCK_K, m0);
-        }
-        tma_load_2d(&tmB, &full_bar[s], sb, kb * BLOCK_K, n0);
+    int kc = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m0 = (tile / p.n_tiles) * Cfg::BLOCK_M;
+      const int n0 = n_tile * BLOCK_N;
+      int w0 = 0, h0 = 0, img = 0;
+      if (p.a_im2col) {
+        const int pq = p.P * p.Q;
+        img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int op = rem / p.Q;
+        const int oq = rem - op * p.Q;
+        w0 = oq * p.stride - p.pad;
+        h0 = op * p.stride - p.pad;
       }
-      __syncwarp();
+      int tap = 0, cb = 0, fr = 0, fs = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          if (p.a_im2col) {
+            tma_load_im2col_4d(&tmA, &full_bar[s], sa, cb * BLOCK_K, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
+          } else {
+            tma_load_2d(&tmA, &full_bar[s], sa, kb * BLOCK_K, m0);
+          }
+          tma_load_2d(&tmB, &full_bar[s], sb, kb * BLOCK_K, n0);
+        }
+        // advance (tap, channel block) without divisions
+        if (++cb == p.cblocks) {
+          cb = 0;
+          ++tap;
+          if (++fs == p.S) {
+            fs = 0;
+            ++fr;
+          }
+        }
+        __syncwarp();
+      }
+      (void)tap;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
+    int kc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t sb = sa + Cfg::A_BYTES;
-        const uint64_t da = umma_smem_desc<Cfg::SWZ>(sa);
-        const uint64_t db = umma_smem_desc<Cfg::SWZ>(sb);
+      const uint32_t tmem_acc = tmem_base + uint32_t(acc * BLOCK_N);
+      for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t da = umma_smem_desc<Cfg::SWZ>(sa);
+          const uint64_t db = umma_smem_desc<Cfg::SWZ>(sb);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
-          umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
+            umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
-        if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9 = 256 threads)
+    constexpr int HALF = CHUNK / 2;          // channels of a chunk handled by one thread
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may read
+    const int hsel = (warp - 2) >> 2;        // which half of each chunk's columns
+    const int row_l = q4 * 32 + lane;        // row inside the tile
+    const bool leader = threadIdx.x == 64;   // issues TMA stores / residual loads (bulk groups are per thread)
+    const int et = threadIdx.x - 64;         // 0..255
+    const bool use_res = p.res_mode != RES_NONE;
+    int it = 0;
+    uint32_t chunk_ctr = 0;                  // running chunk index: ring buffer = chunk_ctr % NBUF
+    float bias_next = (blockIdx.x < total_tiles && et < BLOCK_N) ? __ldg(p.bias + (blockIdx.x % p.n_tiles) * BLOCK_N + et) : 0.f;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles;
+      const int m0 = (tile / p.n_tiles) * Cfg::BLOCK_M;
+      const int n0 = n_tile * BLOCK_N;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int live = min(N_CHUNKS, (p.Cout - n0 + CHUNK - 1) / CHUNK);  // chunks holding real channels
 
-  // ---------------------------------------------------------------- epilogue (all 4 warps)
-  mbar_wait(&tmem_full_bar, 0);
-  tc_fence_after();
+      float* bias_s = s_bias[it & 1];
+      if (et < BLOCK_N) bias_s[et] = bias_next;
+      {  // bias of the next tile: in flight during this tile's epilogue
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles && et < BLOCK_N) bias_next = __ldg(p.bias + (nt % p.n_tiles) * BLOCK_N + et);
+      }
+      if (p.tma_store && use_res && leader) {
+        // residual tile -> ring buffers (one TMA load per chunk); the stores that last used them must have read them
+        bulk_wait_group_read<Cfg::NBUF - N_CHUNKS>();
+        for (int c = 0; c < live; ++c) {
+          const uint32_t rb = (chunk_ctr + c) % Cfg::NBUF;
+          mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
+          tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, n0 + c * CHUNK, m0);
+        }
+      }
+      bar_sync_named(1, Cfg::EPI_THREADS);  // bias visible
 
-  const int row = m0 + warp * 32 + lane;
-  const bool row_ok = row < p.M;
-  int img = 0, op = 0, oq = 0;
-  if (p.store_mode != STORE_PLAIN) {
-    const int pq = p.P * p.Q;
-    img = row / pq;
-    const int rem = row - img * pq;
-    op = rem / p.Q;
-    oq = rem - op * p.Q;
-  }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + uint32_t(acc * BLOCK_N) + ((uint32_t(q4) * 32u) << 16);
 
+      if (p.tma_store) {
+        for (int c = 0; c < live; ++c, ++chunk_ctr) {
+          const uint32_t bsel = chunk_ctr % Cfg::NBUF;
+          uint32_t a[32];
+          if constexpr (HALF == 32) {
+            tmem_ld_32x32(tmem_acc + uint32_t(c * CHUNK + hsel * 32), a);
+          } else {
+            tmem_ld_32x16(tmem_acc + uint32_t(c * CHUNK + hsel * 16), a);
+          }
+          tmem_ld_wait();
+          if (c == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          uint8_t* buf = ring + bsel * Cfg::CHUNK_BYTES;
+          if (use_res) {
+            mbar_wait(&res_full_bar[bsel], (chunk_ctr / Cfg::NBUF) & 1);
+          } else {
+            if (leader) bulk_wait_group_read<Cfg::NBUF - 1>();  // the store that used this buffer NBUF chunks ago has read it
+            bar_sync_named(1, Cfg::EPI_THREADS);
+          }
+          epi_dispatch<Cfg::OUT_SWZ, HALF>(p.act, p.res_mode, a, bias_s + c * CHUNK + hsel * HALF, buf, row_l, hsel * (HALF / 8));
+          fence_proxy_async_smem();
+          bar_sync_named(1, Cfg::EPI_THREADS);
+          if (leader) {
+            tma_store_2d(&tmOut, buf, n0 + c * CHUNK, m0);
+            bulk_commit_group();
+          }
+        }
+      } else {
+        // -------- per-thread stores: fp32 heads, fused nearest-x2 upsample, fused PixelShuffle(2)
+        const int row = m0 + row_l;
+        const bool row_ok = row < p.M;
+        int img = 0, op = 0, oq = 0;
+        if (p.store_mode != STORE_PLAIN) {
+          const int pq = p.P * p.Q;
+          img = row / pq;
+          const int rem = row - img * pq;
+          op = rem / p.Q;
+          oq = rem - op * p.Q;
+        }
+        const int live32 = min(BLOCK_N / 32, (p.Cout - n0 + 31) / 32);
+        if (hsel >= live32) {  // nothing to read for this warp in this tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
 #pragma unroll 1
-  for (int c = 0; c < BLOCK_N / 32; ++c) {
-    const int ch0 = n0 + c * 32;
-    if (ch0 >= p.Cout) break;  // warp-uniform
-    uint32_t acc[32];
-    tmem_ld_32x32(tmem_acc + ((warp * 32u) << 16) + uint32_t(c * 32), acc);
-    tmem_ld_wait();
-    if (!row_ok) continue;
+        for (int c = hsel; c < live32; c += 2) {
+          const int ch0 = n0 + c * 32;
+          uint32_t a[32];
+          tmem_ld_32x32(tmem_acc + uint32_t(c * 32), a);
+          tmem_ld_wait();
+          if (c + 2 >= live32) {  // this warp's last chunk of the tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          if (!row_ok) continue;
 
-    float v[32];
+          float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + s_bias[c * 32 + j];
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + bias_s[c * 32 + j];
 
-    if (p.res_mode != RES_NONE) {
-      const __half* rp = p.res + (size_t)row * p.res_pitch + ch0;
+          if (use_res) {
+            const __half* rp = p.res + (size_t)row * p.res_pitch + ch0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (ch0 + g * 8 + 8 <= p.Cout) {
-          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + g * 8));
-          const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+            for (int g = 0; g < 4; ++g) {
+              if (ch0 + g * 8 + 8 <= p.Cout) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + g * 8));
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(rh[j]);
-            if (p.res_mode == RES_BEFORE_ACT) {
-              v[g * 8 + 2 * j] = apply_act(v[g * 8 + 2 * j] + f.x, p.act);
-              v[g * 8 + 2 * j + 1] = apply_act(v[g * 8 + 2 * j + 1] + f.y, p.act);
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __half22float2(rh[j]);
+                  if (p.res_mode == RES_BEFORE_ACT) {
+                    v[g * 8 + 2 * j] = apply_act(v[g * 8 + 2 * j] + f.x, p.act);
+                    v[g * 8 + 2 * j + 1] = apply_act(v[g * 8 + 2 * j + 1] + f.y, p.act);
+                  } else {
+                    v[g * 8 + 2 * j] = apply_act(v[g * 8 + 2 * j], p.act) + f.x;
+                    v[g * 8 + 2 * j + 1] = apply_act(v[g * 8 + 2 * j + 1], p.act) + f.y;
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+
+          if (p.out_f32) {
+            float* op32 = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_pitch + p.out_coff + ch0;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (ch0 + g * 4 + 4 <= p.Cout) {
+                *reinterpret_cast<float4*>(op32 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (ch0 + g * 4 + j < p.Cout) op32[g * 4 + j] = v[g * 4 + j];
+              }
+            }
+            continue;
+          }
+
+          __half* o16 = reinterpret_cast<__half*>(p.out);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ch = ch0 + g * 8;
+            if (ch >= p.Cout) break;
+            uint4 pk;
+            __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ph2[j] = __floats2half2_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            if (p.store_mode == STORE_PLAIN) {
+              __half* dst = o16 + (size_t)row * p.out_pitch + p.out_coff + ch;
+              if (ch + 8 <= p.Cout) {
+                *reinterpret_cast<uint4*>(dst) = pk;
+              } else {
+                const __half* ph1 = reinterpret_cast<const __half*>(&pk);
+                for (int j = 0; j < 8 && ch + j < p.Cout; ++j) dst[j] = ph1[j];
+              }
+            } else if (p.store_mode == STORE_UPSAMPLE2) {
+              // nearest x2: this pixel lands on a 2x2 block of the [N, 2P, 2Q, *] destination
+              const size_t base = ((size_t)img * (2 * p.P) + 2 * op) * (2 * p.Q) + 2 * oq;
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+                  *reinterpret_cast<uint4*>(o16 + (base + (size_t)dy * (2 * p.Q) + dx) * p.out_pitch + p.out_coff + ch) = pk;
             } else {
-              v[g * 8 + 2 * j] = apply_act(v[g * 8 + 2 * j], p.act) + f.x;
-              v[g * 8 + 2 * j + 1] = apply_act(v[g * 8 + 2 * j + 1], p.act) + f.y;
+              // PixelShuffle(2): weight rows were pre-permuted to o' = sub*(Cout/4) + c, sub = 2*i + j
+              const int c4 = p.Cout >> 2;
+              const int sub = ch / c4;
+              const int cc = ch - sub * c4;
+              const size_t pix = ((size_t)img * (2 * p.P) + 2 * op + (sub >> 1)) * (2 * p.Q) + 2 * oq + (sub & 1);
+              *reinterpret_cast<uint4*>(o16 + pix * p.out_pitch + p.out_coff + cc) = pk;
             }
           }
         }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
     }
-
-    if (p.out_f32) {
-      // network heads: fp32, plain store only
-      float* op32 = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_pitch + p.out_coff + ch0;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (ch0 + g * 4 + 4 <= p.Cout) {
-          *reinterpret_cast<float4*>(op32 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (ch0 + g * 4 + j < p.Cout) op32[g * 4 + j] = v[g * 4 + j];
-        }
-      }
-      continue;
-    }
-
-    __half* o16 = reinterpret_cast<__half*>(p.out);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int ch = ch0 + g * 8;
-      if (ch >= p.Cout) break;
-      uint4 pk;
-      __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ph2[j] = __floats2half2_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-      if (p.store_mode == STORE_PLAIN) {
-        __half* dst = o16 + (size_t)row * p.out_pitch + p.out_coff + ch;
-        if (ch + 8 <= p.Cout) {
-          *reinterpret_cast<uint4*>(dst) = pk;
-        } else {
-          const __half* ph1 = reinterpret_cast<const __half*>(&pk);
-          for (int j = 0; j < 8 && ch + j < p.Cout; ++j) dst[j] = ph1[j];
-        }
-      } else if (p.store_mode == STORE_UPSAMPLE2) {
-        // nearest x2: this pixel lands on a 2x2 block of the [N, 2P, 2Q, *] destination
-        const size_t base = ((size_t)img * (2 * p.P) + 2 * op) * (2 * p.Q) + 2 * oq;
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 2; ++dx)
-            *reinterpret_cast<uint4*>(o16 + (base + (size_t)dy * (2 * p.Q) + dx) * p.out_pitch + p.out_coff + ch) =
-                pk;
-      } else {
-        // PixelShuffle(2): weight rows were pre-permuted to o' = sub*(Cout/4) + c, sub = 2*i + j
-        const int c4 = p.Cout >> 2;
-        const int sub = ch / c4;
-        const int cc = ch - sub * c4;
-        const size_t pix = ((size_t)img * (2 * p.P) + 2 * op + (sub >> 1)) * (2 * p.Q) + 2 * oq + (sub & 1);
-        *reinterpret_cast<uint4*>(o16 + pix * p.out_pitch + p.out_coff + cc) = pk;
-      }
-    }
+    if (leader) bulk_wait_group_read<0>();  // smem must stay valid until the last TMA store has read it
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BLOCK_N>(tmem_acc);
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 }  // namespace bp

@@ -18,6 +18,7 @@ struct ResizeTables {  // Pillow bicubic coefficient tables for one (in, out) si
 struct bp_engine {
   int device = 0;
   bp::TmapApi tmap;
+  int num_sms = 148;
   int force_block_n = 0;  // tuning overrides (env BP_FORCE_BLOCK_N / BP_FORCE_STAGES)
   int force_stages = 0;
   std::map<std::pair<int, int>, ResizeTables> resize_tables;

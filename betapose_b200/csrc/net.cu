@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -27,9 +28,11 @@ struct Tensor {
 
 struct Op {
   OpKind kind;
-  ConvPlan plan;  // OP_CONV
+  // OP_CONV: the launch plan (tile configuration + TMA descriptors) depends on the batch; built lazily per batch
+  ConvDesc cdesc;
+  bool stem = false;
+  std::map<int, ConvPlan> plans;
   int pq = 0;     // output pixels per image (conv) for batch scaling
-  int n_tiles = 1;
   int a = -1, b = -1, c = -1, dst = -1;  // tensor ids for aux ops
   // im2col
   int ksize = 0, stride = 0, pad = 0, P = 0, Q = 0, kpitch = 0;
@@ -241,17 +244,15 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (n->eng->force_block_n) d.force_block_n = n->eng->force_block_n;
   if (n->eng->force_stages) d.force_stages = n->eng->force_stages;
 
+  d.num_sms = n->eng->num_sms;
   Op op;
   op.kind = OP_CONV;
-  std::string err;
-  if (!conv_plan_build(n->eng->tmap, &op.plan, d, &err)) return bp_fail(BP_ERR_CUDA, ("bp_net_conv: " + err).c_str());
-  if (stem) {
-    // plan was built as a [1,1,M,K] matrix; keep P,Q for the fused-store address math (plain only for stems)
-    op.plan.args.P = P;
-    op.plan.args.Q = Q;
-  }
+  op.cdesc = d;
+  op.stem = stem;
   op.pq = P * Q;
-  op.n_tiles = op.plan.args.n_tiles;
+  std::string err;
+  ConvPlan& plan0 = op.plans[n->max_batch];
+  if (!conv_plan_build(n->eng->tmap, &plan0, d, &err)) return bp_fail(BP_ERR_CUDA, ("bp_net_conv: " + err).c_str());
   op.dst = dst;
   op.flops = 2.0 * P * Q * (double)Cout * K;
   op.bytes = (stem ? (double)P * Q * ((K + 7) / 8 * 8) * 2 : (double)src.H * src.W * Cin * 2) + (double)K * Cout * 2 / n->max_batch +
@@ -259,7 +260,7 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
              (s->res >= 0 ? (double)P * Q * Cout * 2 : 0.0);
   char buf[160];
   snprintf(buf, sizeof buf, "conv %dx%d/%d %d->%d @%dx%d bn%d bk%d st%d%s%s%s", k, k, s->stride, Cin, Cout, P, Q,
-           op.plan.block_n, op.plan.block_k, op.plan.stages, s->res >= 0 ? " +res" : "",
+           plan0.block_n, plan0.block_k, plan0.stages, s->res >= 0 ? " +res" : "",
            s->store_mode == BP_STORE_UPSAMPLE2 ? " up2" : (s->store_mode == BP_STORE_PIXSHUF2 ? " ps2" : ""),
            s->out_f32 ? " f32" : "");
   op.desc = buf;
@@ -387,10 +388,21 @@ int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream
     cudaError_t e = cudaSuccess;
     switch (op.kind) {
       case OP_CONV: {
-        ConvPlan pl = op.plan;
-        pl.args.M = batch * op.pq;
-        pl.grid = ((pl.args.M + 127) / 128) * op.n_tiles;
-        e = conv_plan_launch(pl, st);
+        Op& mop = n->ops[i];
+        auto it = mop.plans.find(batch);
+        if (it == mop.plans.end()) {
+          // first use of this batch size: tile configuration + TMA descriptors for exactly `batch` images
+          ConvDesc d = mop.cdesc;
+          if (mop.stem) d.W = batch * mop.pq; else d.N = batch;
+          std::string err;
+          ConvPlan& np = mop.plans[batch];
+          if (!conv_plan_build(n->eng->tmap, &np, d, &err)) {
+            mop.plans.erase(batch);
+            return bp_fail(BP_ERR_CUDA, ("bp_net_forward: " + err).c_str());
+          }
+          it = mop.plans.find(batch);
+        }
+        e = conv_plan_launch(it->second, st);
         break;
       }
       case OP_IM2COL: {

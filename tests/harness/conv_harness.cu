@@ -318,6 +318,11 @@ int main(int argc, char** argv) {
         {"gemm upsample2 store", 2, 13, 13, 512, 256, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_UPSAMPLE2, 0, 0, 512, 0},
         {"gemm bn256 st2", 2, 20, 16, 256, 512, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 256, 2},
         {"gemm bn128 st6", 2, 20, 16, 256, 512, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 128, 6},
+        {"gemm Cout32 chunk32 res", 3, 31, 29, 64, 32, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT},
+        {"gemm Cout96 ragged N res", 3, 31, 29, 64, 96, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT},
+        {"gemm many tiles persistent", 40, 33, 31, 64, 256, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 64},
+        {"gemm many tiles bn256", 40, 33, 31, 128, 512, 1, 1, 1, 0, ACT_LEAKY, RES_BEFORE_ACT},
+        {"gemm coff+res pitch", 2, 26, 26, 128, 256, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 64, 128, 64},
     };
     for (auto& c : gemm) fails += run_case(c);
   }
@@ -363,6 +368,12 @@ int main(int argc, char** argv) {
         {"K 1x1 256->1024 @20x16", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_NONE, 0, 0, 0, 0, 0, 0, 0, 0, 10},
         {"K 1x1 1024->256 @20x16", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
         {"K 1x1 64->256 @80x64", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_NONE, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K 1x1 64->256 @80x64 +res", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 128->256 @52 +res", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 64->128 @104 +res", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 5},
+        {"Y 1x1 64->32 @208", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
+        {"K 1x1 256->1024 +res", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K 3x3 512->1024 ps2", 64, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 0, 0, 10},
     };
     for (auto& c : perf) fails += run_case(c);
   }
