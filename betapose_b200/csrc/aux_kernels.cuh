@@ -196,59 +196,4 @@ __global__ void add_kernel(TView a, TView b, TView out, int N) {
   stg16(reinterpret_cast<__half*>(out.ptr) + pix * out.pitch + cg * 8, o);
 }
 
-// Explicit im2col for the two 3-channel stem convolutions (YOLO 3x3/1 on the 416^2 detector input, FastPose
-// 7x7/2 on the 320x256 crop): writes the fp16 GEMM operand A[M, kpitch], K ordered (r, s, c), zero padded.
-// Input pixels are 4-wide (RGBX): uint8 scaled by `scale` (= 1/255, ToTensor) or fp16 as is.
-template <typename TIn>
-__global__ void im2col_stem_kernel(const TIn* __restrict__ in, int N, int H, int W, int ksize, int stride, int pad,
-                                   int P, int Q, float scale, __half* __restrict__ out, int kpitch) {
-  const long m = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long M = (long)N * P * Q;
-  if (m >= M) return;
-  const int q = m % Q;
-  const int p = (m / Q) % P;
-  const int n = m / ((long)P * Q);
-  __half* orow = out + m * kpitch;
-  const int K = ksize * ksize * 3;
-  uint4 pk;
-  __half* ph = reinterpret_cast<__half*>(&pk);
-  int fill = 0, kbase = 0;
-  for (int r = 0; r < ksize; ++r) {
-    const int h = p * stride - pad + r;
-    for (int s = 0; s < ksize; ++s) {
-      const int w = q * stride - pad + s;
-      float v[3] = {0.f, 0.f, 0.f};
-      if (h >= 0 && h < H && w >= 0 && w < W) {
-        const long off = (((long)n * H + h) * W + w) * 4;
-        if constexpr (sizeof(TIn) == 1) {
-          const uchar4 px = *reinterpret_cast<const uchar4*>(in + off);
-          v[0] = px.x * scale; v[1] = px.y * scale; v[2] = px.z * scale;
-        } else {
-          const uint2 raw = *reinterpret_cast<const uint2*>(in + off);
-          const __half2* hh = reinterpret_cast<const __half2*>(&raw);
-          const float2 a = __half22float2(hh[0]), b = __half22float2(hh[1]);
-          v[0] = a.x; v[1] = a.y; v[2] = b.x;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        ph[fill++] = __float2half_rn(v[c]);
-        if (fill == 8) {
-          *reinterpret_cast<uint4*>(orow + kbase) = pk;
-          kbase += 8;
-          fill = 0;
-        }
-      }
-    }
-  }
-  // tail: zero pad up to kpitch
-  while (kbase < kpitch) {
-    for (; fill < 8; ++fill) ph[fill] = __float2half_rn(0.f);
-    *reinterpret_cast<uint4*>(orow + kbase) = pk;
-    kbase += 8;
-    fill = 0;
-  }
-  (void)K;
-}
-
 }  // namespace bp

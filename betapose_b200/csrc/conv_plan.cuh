@@ -27,6 +27,8 @@ struct ConvDesc {
   int force_block_n = 0;  // 0 = heuristic
   int force_stages = 0;   // kept for the harness; the stage count now follows from the tile configuration
   int num_sms = 148;
+  // gather mode (stem): x is [N, H, W, 4] uint8 or fp16, C = 4, weights packed [Cout_pad][taps_pad16 * 4]
+  int gather = 0, gather_u8 = 0;
 };
 
 struct ConvPlan {
@@ -40,21 +42,27 @@ struct ConvPlan {
   double flops = 0;
 };
 
-template <int BN, int BK, int ST>
+template <int BN, int BK, int ST, bool GATHER = false>
 inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   using Cfg = ConvCfg<BN, BK, ST>;
   static bool attr_done = false;  // per-instantiation; set once per process (single device per process)
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  conv_umma_kernel<BN, BK, ST><<<pl.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+  conv_umma_kernel<BN, BK, ST, GATHER><<<pl.grid, Cfg::THREADS + (GATHER ? 128 : 0), Cfg::SMEM_BYTES, st>>>(
+      pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
   return cudaGetLastError();
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
+  if (pl.args.a_im2col == 2) {
+    if (pl.block_n == 32) return launch_cfg<32, 64, 6, true>(pl, st);
+    if (pl.block_n == 64) return launch_cfg<64, 64, 6, true>(pl, st);
+    return cudaErrorInvalidConfiguration;
+  }
 #define BP_CASE(BN, BK, ST) \
   if (pl.block_n == BN && pl.block_k == BK && pl.stages == ST) return launch_cfg<BN, BK, ST>(pl, st);
   BP_CASE(256, 64, 3)
@@ -71,10 +79,10 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   const int P = (d.H + 2 * d.pad - d.R) / d.stride + 1;
   const int Q = (d.W + 2 * d.pad - d.S) / d.stride + 1;
   const int M = d.N * P * Q;
-  const bool matrix = (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad == 0);
+  const bool matrix = !d.gather && (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad == 0);
   // matrix mode may have a ragged K (explicit im2col of the 3-channel stems): TMA zero-fills the tail
-  const int block_k = matrix ? (d.C >= 64 ? 64 : 32) : ((d.C % 64 == 0) ? 64 : 32);
-  if (!matrix && d.C % 32 != 0) {
+  const int block_k = d.gather ? 64 : (matrix ? (d.C >= 64 ? 64 : 32) : ((d.C % 64 == 0) ? 64 : 32));
+  if (!matrix && !d.gather && d.C % 32 != 0) {
     if (err) *err = "im2col conv needs Cin % 32 == 0";
     return false;
   }
@@ -91,7 +99,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
     return false;
   }
   const int st = bn == 256 ? 3 : (bn == 128 ? 4 : (block_k == 64 ? 6 : 8));
-  const int K = d.R * d.S * d.C;
+  const int K = d.gather ? (d.R * d.S + 15) / 16 * 64 : d.R * d.S * d.C;  // gather: 16 taps x 4 channels per k-block
   const int num_kb = (K + block_k - 1) / block_k;
 
   pl->block_n = bn;
@@ -105,14 +113,19 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   const int m_tiles = (M + 127) / 128;
   pl->grid = std::min(m_tiles * n_tiles_live, d.num_sms);  // persistent: one CTA per SM
   (void)n_tiles;
-  pl->flops = 2.0 * M * (double)d.Cout * K;
+  pl->flops = 2.0 * M * (double)d.Cout * (d.gather ? d.R * d.S * 3 : K);
 
   ConvArgs& a = pl->args;
   a.M = M;
   a.n_tiles = n_tiles_live;
   a.m_tiles = m_tiles;
   a.num_kb = num_kb;
-  a.a_im2col = matrix ? 0 : 1;
+  a.a_im2col = d.gather ? 2 : (matrix ? 0 : 1);
+  a.gx = d.x;
+  a.gH = d.H;
+  a.gW = d.W;
+  a.g_u8 = d.gather_u8;
+  a.R = d.R;
   a.P = P;
   a.Q = Q;
   a.stride = d.stride;
@@ -135,7 +148,12 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.res = d.res;
   a.out = d.out;
 
-  if (matrix) {
+  if (d.gather) {
+    if (bn > 64) {
+      if (err) *err = "gather (stem) convolutions support Cout <= 64";
+      return false;
+    }
+  } else if (matrix) {
     if (!make_tmap_2d(api, &pl->tmA, d.x, (uint64_t)M, (uint64_t)d.C, (uint64_t)d.x_pitch, 128, block_k, err))
       return false;
   } else {
@@ -145,6 +163,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   }
   if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn, block_k, err))
     return false;
+  if (d.gather) pl->tmA = pl->tmB;
   pl->tmOut = pl->tmB;  // placeholders keep the kernel parameters well-formed when the TMA epilogue is off
   pl->tmRes = pl->tmB;
   if (a.tma_store) {

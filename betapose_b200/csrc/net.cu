@@ -17,7 +17,7 @@ using namespace bp;
 
 namespace {
 
-enum OpKind { OP_CONV, OP_IM2COL, OP_MAXPOOL, OP_AVGPOOL, OP_SCALE_ADD_RELU, OP_PIXSHUF, OP_UPSAMPLE, OP_COPYC, OP_ADD };
+enum OpKind { OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_SCALE_ADD_RELU, OP_PIXSHUF, OP_UPSAMPLE, OP_COPYC, OP_ADD };
 
 struct Tensor {
   void* ptr = nullptr;  // includes the channel offset
@@ -34,9 +34,6 @@ struct Op {
   std::map<int, ConvPlan> plans;
   int pq = 0;     // output pixels per image (conv) for batch scaling
   int a = -1, b = -1, c = -1, dst = -1;  // tensor ids for aux ops
-  // im2col
-  int ksize = 0, stride = 0, pad = 0, P = 0, Q = 0, kpitch = 0;
-  __half* col = nullptr;
   double flops = 0, bytes = 0;  // per image
   std::string desc;
 };
@@ -159,12 +156,17 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (s->store_mode != BP_STORE_PLAIN && Cout % 8) return bp_fail(BP_ERR_UNSUPPORTED, "fused stores need Cout % 8 == 0");
 
   // ---- fold BN (fp64) and pack weights [Cout_pad][R][S][Cin] fp16
-  const int K = k * k * Cin;
+  // stem (3-channel network input): K is laid out (tap, 4 channels) with 16 taps per 64-wide k-block, the 4th
+  // channel and the taps beyond k*k are zero; uint8 inputs are fed as raw 0..255 and ToTensor's 1/255
+  // (dataloader.py:94-99) is folded into the weights
+  const int K = stem ? (k * k + 15) / 16 * 64 : k * k * Cin;
   const int wpitch = (K + 7) / 8 * 8;
   const int Cout_pad = (Cout + 255) / 256 * 256;
+  if (stem && Cout > 64) return bp_fail(BP_ERR_UNSUPPORTED, "bp_net_conv: a stem convolution supports at most 64 output channels");
   std::vector<__half> hw((size_t)Cout_pad * wpitch, __float2half(0.f));
   std::vector<float> hb(Cout_pad, 0.f);
   const int c4 = Cout / 4;
+  const double in_scale = (stem && src.in_kind == BP_IN_U8X4) ? 1.0 / 255.0 : 1.0;
   for (int o = 0; o < Cout; ++o) {
     double scale = 1.0, shift = s->bias ? (double)s->bias[o] : 0.0;
     if (s->bn_gamma) {
@@ -177,10 +179,11 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
     hb[row] = (float)shift;
     const float* wsrc = s->weight + (size_t)o * Cin * k * k;
     __half* wdst = hw.data() + (size_t)row * wpitch;
+    const int cstride = stem ? 4 : Cin;
     for (int ci = 0; ci < Cin; ++ci)
       for (int r = 0; r < k; ++r)
         for (int q = 0; q < k; ++q)
-          wdst[(r * k + q) * Cin + ci] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale));
+          wdst[(r * k + q) * cstride + ci] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale * in_scale));
   }
   __half* dw = (__half*)net_alloc_weights(n, hw.size() * 2);
   float* db = (float*)net_alloc_weights(n, hb.size() * 4);
@@ -207,25 +210,11 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   const Tensor& dt = n->tensors[dst];
 
   ConvDesc d;
-  Op col_op;
-  bool have_col = false;
   if (stem) {
-    // explicit im2col of the 3-channel input, then a plain GEMM over A[M, K]
-    const int kp = (K + 7) / 8 * 8;
-    const size_t bytes = (size_t)n->max_batch * P * Q * kp * 2 + 256;
-    __half* col = (__half*)net_alloc_act(n, bytes);
-    if (!col) return bp_fail(BP_ERR_CUDA, "bp_net_conv: cudaMalloc (im2col) failed");
-    col_op.kind = OP_IM2COL;
-    col_op.a = s->src;
-    col_op.ksize = k; col_op.stride = s->stride; col_op.pad = s->pad; col_op.P = P; col_op.Q = Q; col_op.kpitch = kp;
-    col_op.col = col;
-    col_op.bytes = (double)src.H * src.W * 4 * (src.in_kind == BP_IN_U8X4 ? 1 : 2) + (double)P * Q * kp * 2;
-    char buf[128];
-    snprintf(buf, sizeof buf, "im2col %dx%d/%d 3->K%d @%dx%d", k, k, s->stride, K, P, Q);
-    col_op.desc = buf;
-    have_col = true;
-    d.x = col; d.N = 1; d.H = 1; d.W = n->max_batch * P * Q; d.C = K; d.x_pitch = kp;
-    d.R = 1; d.S = 1; d.stride = 1; d.pad = 0;
+    d.x = (const __half*)src.ptr; d.N = n->max_batch; d.H = src.H; d.W = src.W; d.C = 4; d.x_pitch = 4;
+    d.R = k; d.S = k; d.stride = s->stride; d.pad = s->pad;
+    d.gather = 1;
+    d.gather_u8 = src.in_kind == BP_IN_U8X4 ? 1 : 0;
   } else {
     d.x = (const __half*)src.ptr; d.N = n->max_batch; d.H = src.H; d.W = src.W; d.C = Cin; d.x_pitch = src.pitch;
     d.R = k; d.S = k; d.stride = s->stride; d.pad = s->pad;
@@ -254,8 +243,9 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   ConvPlan& plan0 = op.plans[n->max_batch];
   if (!conv_plan_build(n->eng->tmap, &plan0, d, &err)) return bp_fail(BP_ERR_CUDA, ("bp_net_conv: " + err).c_str());
   op.dst = dst;
-  op.flops = 2.0 * P * Q * (double)Cout * K;
-  op.bytes = (stem ? (double)P * Q * ((K + 7) / 8 * 8) * 2 : (double)src.H * src.W * Cin * 2) + (double)K * Cout * 2 / n->max_batch +
+  op.flops = 2.0 * P * Q * (double)Cout * (k * k * Cin);
+  op.bytes = (stem ? (double)src.H * src.W * 4 * (src.in_kind == BP_IN_U8X4 ? 1 : 2) : (double)src.H * src.W * Cin * 2) +
+             (double)K * Cout * 2 / n->max_batch +
              (double)P * Q * Cout * (s->out_f32 ? 4 : 2) * (s->store_mode == BP_STORE_UPSAMPLE2 ? 4 : 1) +
              (s->res >= 0 ? (double)P * Q * Cout * 2 : 0.0);
   char buf[160];
@@ -264,7 +254,6 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
            s->store_mode == BP_STORE_UPSAMPLE2 ? " up2" : (s->store_mode == BP_STORE_PIXSHUF2 ? " ps2" : ""),
            s->out_f32 ? " f32" : "");
   op.desc = buf;
-  if (have_col) n->ops.push_back(col_op);
   n->ops.push_back(op);
   n->flops += op.flops;
   // the tensor id a consumer reads: for dst given by the caller, a view restricted to our channel window
@@ -393,7 +382,7 @@ int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream
         if (it == mop.plans.end()) {
           // first use of this batch size: tile configuration + TMA descriptors for exactly `batch` images
           ConvDesc d = mop.cdesc;
-          if (mop.stem) d.W = batch * mop.pq; else d.N = batch;
+          d.N = batch;
           std::string err;
           ConvPlan& np = mop.plans[batch];
           if (!conv_plan_build(n->eng->tmap, &np, d, &err)) {
@@ -403,20 +392,6 @@ int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream
           it = mop.plans.find(batch);
         }
         e = conv_plan_launch(it->second, st);
-        break;
-      }
-      case OP_IM2COL: {
-        const Tensor& s = n->tensors[op.a];
-        const long M = (long)batch * op.P * op.Q;
-        if (s.in_kind == BP_IN_U8X4)
-          im2col_stem_kernel<uint8_t><<<blocks_for(M, 128), 128, 0, st>>>((const uint8_t*)s.ptr, batch, s.H, s.W, op.ksize,
-                                                                        op.stride, op.pad, op.P, op.Q, 1.0f / 255.0f,
-                                                                        op.col, op.kpitch);
-        else
-          im2col_stem_kernel<__half><<<blocks_for(M, 128), 128, 0, st>>>((const __half*)s.ptr, batch, s.H, s.W, op.ksize,
-                                                                       op.stride, op.pad, op.P, op.Q, 1.0f, op.col,
-                                                                       op.kpitch);
-        e = cudaGetLastError();
         break;
       }
       case OP_MAXPOOL: {

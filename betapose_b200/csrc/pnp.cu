@@ -30,7 +30,7 @@ struct WarpLanes {
 __global__ void __launch_bounds__(kMaxHyp)
 pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
                 const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d, const int32_t* __restrict__ model_idx,
-                double fx, double fy, double cx, double cy, int left_number, int mode, double thr2, int n_hyp, uint32_t seed,
+                double fx, double fy, double cx, double cy, int left_number, int mode, int flags, double thr2, int n_hyp, uint32_t seed,
                 float* __restrict__ keypoints, float* __restrict__ kp_score, float* __restrict__ proposal,
                 uint8_t* __restrict__ selected, double* __restrict__ R_out, double* __restrict__ t_out,
                 uint8_t* __restrict__ inlier, int32_t* __restrict__ status) {
@@ -52,15 +52,17 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
 
   // ---- stage A: pose-NMS (n = 1) and selection
   if (tid < K) {
-    float sc = ok_in ? maxval[(long)i * K + tid] : 0.f;
+    const bool raw = flags & BP_PNP_RAW_POINTS;  // inputs are final key-points: no pose-NMS arithmetic
+    float sc = ok_in ? (raw ? 1.f : maxval[(long)i * K + tid]) : 0.f;
     if (sc == 0.f) sc = 1e-5f;
     s_sc[tid] = sc;
     const double* mp = kp3d + ((long)(model_idx ? model_idx[i] : 0) * K + tid) * 3;
     s_pw[3 * tid] = mp[0];
     s_pw[3 * tid + 1] = mp[1];
     s_pw[3 * tid + 2] = mp[2];
-    const float kx = ok_in ? __fsub_rn(preds_img[((long)i * K + tid) * 2], 0.3f) : 0.f;
-    const float ky = ok_in ? __fsub_rn(preds_img[((long)i * K + tid) * 2 + 1], 0.3f) : 0.f;
+    const float shift = raw ? 0.f : 0.3f;
+    const float kx = ok_in ? __fsub_rn(preds_img[((long)i * K + tid) * 2], shift) : 0.f;
+    const float ky = ok_in ? __fsub_rn(preds_img[((long)i * K + tid) * 2 + 1], shift) : 0.f;
     s_uv[2 * tid] = (double)kx;
     s_uv[2 * tid + 1] = (double)ky;
     keypoints[((long)i * K + tid) * 2] = kx;
@@ -82,9 +84,9 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
       mx = fmaxf(mx, s_sc[j]);
       sum = __fadd_rn(sum, s_sc[j]);
     }
-    const bool pass = ok_in && !(mx < 0.3f);
+    const bool pass = ok_in && ((flags & BP_PNP_RAW_POINTS) || !(mx < 0.3f));
     s_state = pass ? 1 : 0;
-    proposal[i] = pass ? __fadd_rn(__fadd_rn(__fdiv_rn(sum, (float)K), det_score[i]), __fmul_rn(1.25f, mx)) : 0.f;
+    proposal[i] = pass ? __fadd_rn(__fadd_rn(__fdiv_rn(sum, (float)K), det_score ? det_score[i] : 0.f), __fmul_rn(1.25f, mx)) : 0.f;
   }
   __syncthreads();
   if (tid == 0) {
@@ -98,7 +100,7 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
   }
   __syncthreads();
 
-  const bool run = s_state == 1 && s_nsel >= 4;
+  const bool run = s_state == 1 && s_nsel >= 4 && !(flags & BP_PNP_NMS_ONLY);
   const bool ransac = run && mode == 0 && s_nsel >= 6;
 
   // ---- stage B: hypotheses (RANSAC: one 5-point EPnP per thread; all-points mode: thread 0 solves all selected)
@@ -182,7 +184,7 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
     if (tid == 0) {
       for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = ok ? R[k] : 0.0;
       for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = ok ? t[k] : 0.0;
-      status[i] = s_state == 0 ? 0 : (ok ? 1 : -1);
+      status[i] = s_state == 0 ? 0 : ((ok || (flags & BP_PNP_NMS_ONLY)) ? 1 : -1);
     }
     if (!ok)
       for (int j = tid; j < K; j += 32) s_inl[j] = 0;
@@ -195,15 +197,15 @@ pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ m
 
 extern "C" int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* maxval, const float* det_score,
                            const uint8_t* valid, int n, int K, const double* kp3d, const int32_t* model_idx,
-                           const double* cam, int left_number, int mode, float reproj_thr, int n_hyp, uint32_t seed,
-                           float* keypoints, float* kp_score, float* proposal, uint8_t* selected, double* R, double* t,
+                           const double* cam, int left_number, int mode, int flags, float reproj_thr, int n_hyp,
+                           uint32_t seed, float* keypoints, float* kp_score, float* proposal, uint8_t* selected, double* R, double* t,
                            uint8_t* inlier, int32_t* status, void* stream) {
-  if (!e || !preds_img || !maxval || !det_score || !kp3d || !cam || n <= 0) return bp_fail(BP_ERR_INVALID, "bp_pose_pnp: bad arguments");
+  if (!e || !preds_img || !kp3d || !cam || n <= 0 || (!(flags & BP_PNP_RAW_POINTS) && (!maxval || !det_score))) return bp_fail(BP_ERR_INVALID, "bp_pose_pnp: bad arguments");
   if (K < 1 || K > kMaxK) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pose_pnp: K must be in [1, 64]");
   if (n_hyp < 1 || n_hyp > kMaxHyp) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pose_pnp: n_hyp must be in [1, 128]");
   if (mode != 0 && mode != 1) return bp_fail(BP_ERR_INVALID, "bp_pose_pnp: mode");
   pose_pnp_kernel<<<n, kMaxHyp, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode,
+      preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode, flags,
       (double)reproj_thr * (double)reproj_thr, n_hyp, seed, keypoints, kp_score, proposal, selected, R, t, inlier, status);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));

@@ -301,6 +301,67 @@ extern "C" int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, co
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }
 
+namespace {
+// one block per image over decoded rows (cx, cy, w, h, obj, cls...): arg-max objectness above `conf`, lowest row on ties
+__global__ void write_results_kernel(const float* __restrict__ pred, int R, int n_attr, float conf, float* __restrict__ det,
+                                     int32_t* __restrict__ row_out, uint8_t* __restrict__ valid) {
+  const int b = blockIdx.x;
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  const float* p = pred + (long)b * R * n_attr;
+  float best = -1.f;
+  int best_row = 0x7fffffff;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    const float obj = p[(long)r * n_attr + 4];
+    bool cand = obj > conf;
+    if (cand && n_attr > 6) {
+      int am = 0;
+      float mv = p[(long)r * n_attr + 5];
+      for (int c = 1; c < n_attr - 5; ++c)
+        if (p[(long)r * n_attr + 5 + c] > mv) { mv = p[(long)r * n_attr + 5 + c]; am = c; }
+      cand = am == 0;
+    }
+    if (cand && (obj > best || (obj == best && r < best_row))) { best = obj; best_row = r; }
+  }
+  s_val[threadIdx.x] = best;
+  s_idx[threadIdx.x] = best_row;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float ov = s_val[threadIdx.x + s];
+      const int oi = s_idx[threadIdx.x + s];
+      if (ov > s_val[threadIdx.x] || (ov == s_val[threadIdx.x] && oi < s_idx[threadIdx.x])) { s_val[threadIdx.x] = ov; s_idx[threadIdx.x] = oi; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int r = s_idx[0];
+    const bool ok = s_val[0] >= 0.f && r != 0x7fffffff;
+    valid[b] = ok ? 1 : 0;
+    row_out[b] = ok ? r : -1;
+    float d[8] = {(float)b, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) {
+      const float* q = p + (long)r * n_attr;
+      d[1] = __fsub_rn(q[0], __fdiv_rn(q[2], 2.f));
+      d[2] = __fsub_rn(q[1], __fdiv_rn(q[3], 2.f));
+      d[3] = __fadd_rn(q[0], __fdiv_rn(q[2], 2.f));
+      d[4] = __fadd_rn(q[1], __fdiv_rn(q[3], 2.f));
+      d[5] = q[4];
+      d[6] = q[5];
+    }
+    for (int i = 0; i < 8; ++i) det[b * 8 + i] = d[i];
+  }
+}
+}  // namespace
+
+extern "C" int bp_write_results(bp_engine* e, const float* pred, int B, int R, int n_attr, float conf, float* det, int32_t* row,
+                                uint8_t* valid, void* stream) {
+  if (!e || !pred || B <= 0 || R <= 0 || n_attr < 6 || !det || !row || !valid) return bp_fail(BP_ERR_INVALID, "bp_write_results: bad arguments");
+  write_results_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, R, n_attr, conf, det, row, valid);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
+}
+
 // ===================================================================================================
 // a6  crop_from_dets + cropBox (dataloader.py:794-835, KPD/src/utils/img.py:242-262)
 // ===================================================================================================

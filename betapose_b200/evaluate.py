@@ -1,0 +1,95 @@
+"""Command-line driver of the evaluate path, flag-compatible with the reference's
+`python3 betapose_evaluate.py --nClasses 50 --indir <dir> --outdir <dir> --sp [--profile]` (README.md:75-85) and
+`occlusion_betapose_evaluate.py` (`--left_keypoints`, `--obj_id`).  Frames -> BetaposeEngine -> Betapose-results.json.
+
+    python -m betapose_b200.evaluate --indir frames/ --outdir out/ --yolo_weights 01.weights --kpd_weights seq1_model.pkl \\
+           --kp_model obj_01.ply
+    torchrun --nproc-per-node 8 -m betapose_b200.evaluate ...        # frames sharded over ranks, one all-gather of records
+    python -m betapose_b200.evaluate --synthetic 256 --outdir out/   # synthetic frames + synthetic weights (no assets needed)
+
+Scoring against LineMod ground truth (ADD / 2-D reprojection / IoU) is the stage after this path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import compat, dist as bdist, model3d, stages, synth
+from .engine import BetaposeEngine
+from .opt import parse_args
+
+
+def _load_frames(paths):
+    from PIL import Image  # frame decode is outside the hot path
+
+    out = np.empty((len(paths), 480, 640, 3), np.uint8)
+    for i, p in enumerate(paths):
+        im = np.asarray(Image.open(p).convert("RGB"))
+        assert im.shape == (480, 640, 3), f"{p}: expected a 640x480 frame, got {im.shape}"
+        out[i] = im
+    return out
+
+
+def main(argv=None):
+    o = parse_args(argv)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group(o.backend, device_id=torch.device("cuda", local))
+
+    occlusion = o.mode == "occlusion"
+    left = o.left_keypoints if occlusion else o.nClasses  # DataWriter(cam_K, 50, ...) vs (cam_K, args.left_keypoints, ...)
+    if o.synthetic:
+        names = [f"synthetic_{i:06d}.png" for i in range(o.synthetic)]
+        yolo_stream, kpd_sd, kp3d = synth.cached_yolo_weights(1000), synth.cached_kpd_state_dict(2000), synth.synth_kp_model(1, o.nClasses)
+    else:
+        if o.inputlist:
+            names = [ln.strip() for ln in open(o.inputlist) if ln.strip()]
+        else:
+            names = sorted(f for f in os.listdir(o.inputpath) if f.lower().endswith((".png", ".jpg", ".jpeg")))
+        names = [os.path.join(o.inputpath, n) for n in names]
+        if not names:
+            raise SystemExit("no frames found")
+        with open(o.yolo_weights, "rb") as f:
+            f.read(16)
+            yolo_stream = np.fromfile(f, dtype=np.float32)
+        kpd_sd = torch.load(o.kpd_weights, map_location="cpu")
+        kp3d = model3d.load_kp_model(o.kp_model, o.nClasses)
+
+    n_total = len(names)
+    lo, hi = bdist.shard_range(n_total, rank, world)
+    B = min(o.batch, max(1, hi - lo))
+    mode = stages.MODE_RANSAC if o.pnp_mode == "ransac" else stages.MODE_ALLPTS
+    eng = BetaposeEngine(B, yolo_stream, kpd_sd, kp3d, reso=int(o.inp_dim), inp_h=o.inputResH, inp_w=o.inputResW, n_kp=o.nClasses,
+                         left_number=left, conf=o.confidence, pnp_mode=mode)
+    recs = []
+    t0 = time.time()
+    for b0 in range(lo, hi, B):
+        b1 = min(hi, b0 + B)
+        frames = synth.synth_frames(b1 - b0, seed=b0) if o.synthetic else _load_frames(names[b0:b1])
+        recs.append(eng.run(frames, image_index0=b0).copy())
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    mine = np.concatenate(recs) if recs else np.zeros(0, stages.RECORD_DTYPE)
+    local_bytes = torch.from_numpy(mine.view(np.uint8).reshape(len(mine), -1).copy()).cuda()
+    allrec = stages.records_to_numpy(bdist.gather_records(local_bytes, n_total))
+    if rank == 0:
+        results = [compat.result_from_record(allrec[i], names[int(allrec[i]["image_index"])], o.nClasses) for i in range(n_total)]
+        out = compat.write_json(results, o.outputpath)
+        print(f"{n_total} frames, {len(out)} poses -> {os.path.join(o.outputpath, 'Betapose-results.json')}")
+        if o.profile:
+            print(f"rank 0: {hi - lo} frames in {dt:.3f} s ({(hi - lo) / dt:.1f} frames/s incl. host frame generation/decoding)")
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

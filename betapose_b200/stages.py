@@ -64,6 +64,19 @@ def yolo_decode_argmax(heads, anchors, B: int, reso: int = 416, conf: float = 0.
     return dict(det=det, box=box, score=score, row=row, valid=valid, decoded=dec)
 
 
+def write_results(pred: torch.Tensor, conf: float = 0.01):
+    """pred fp32 [B,R,n_attr] decoded rows (cuda) -> dict(det [B,8], row int32 [B], valid uint8 [B])."""
+    e = _eng(pred)
+    pred = pred.contiguous()
+    B, R, A = pred.shape
+    det = torch.empty((B, 8), dtype=torch.float32, device=pred.device)
+    row = torch.empty((B,), dtype=torch.int32, device=pred.device)
+    valid = torch.empty((B,), dtype=torch.uint8, device=pred.device)
+    _lib.check(_lib.lib().bp_write_results(e.handle, _lib.ptr(pred), B, R, A, float(conf), _lib.ptr(det), _lib.ptr(row),
+                                           _lib.ptr(valid), _lib.stream_ptr()), "bp_write_results")
+    return dict(det=det, row=row, valid=valid)
+
+
 def crop_resize(frames_u8: torch.Tensor, box: torch.Tensor, img_idx: torch.Tensor, valid: torch.Tensor | None = None,
                 res_h: int = 320, res_w: int = 256, out_f16x4: torch.Tensor | None = None, want_f16: bool = True,
                 want_f32: bool = False):
@@ -110,11 +123,12 @@ def heatmap_decode(hm: torch.Tensor, pt1: torch.Tensor, pt2: torch.Tensor, layou
 
 
 MODE_RANSAC, MODE_ALLPTS = 0, 1
+PNP_RAW_POINTS, PNP_NMS_ONLY = 1, 2
 
 
 def pose_pnp(preds_img: torch.Tensor, maxval: torch.Tensor, det_score: torch.Tensor, kp3d: torch.Tensor,
              valid: torch.Tensor | None = None, model_idx: torch.Tensor | None = None, cam_K=CAM_K, left_number: int = 50,
-             mode: int = MODE_RANSAC, reproj_thr: float = 12.0, n_hyp: int = 64, seed: int = 0):
+             mode: int = MODE_RANSAC, reproj_thr: float = 12.0, n_hyp: int = 64, seed: int = 0, flags: int = 0):
     """Single-proposal pose-NMS + key-point selection + PnP for n detections.
     kp3d float64 [K,3] or [n_models,K,3] (cuda).  Returns a dict of cuda tensors (see bp_pose_pnp)."""
     e = _eng(preds_img)
@@ -133,9 +147,10 @@ def pose_pnp(preds_img: torch.Tensor, maxval: torch.Tensor, det_score: torch.Ten
         inlier=torch.empty((n, K), dtype=torch.uint8, device=dev),
         status=torch.empty((n,), dtype=torch.int32, device=dev),
     )
-    _lib.check(_lib.lib().bp_pose_pnp(e.handle, _lib.ptr(preds_img.contiguous()), _lib.ptr(maxval.contiguous()),
-                                      _lib.ptr(det_score.contiguous()), _lib.ptr(valid), n, K, _lib.ptr(kp3d.contiguous()),
-                                      _lib.ptr(model_idx), C.cast(cam_arr, C.c_void_p), int(left_number), int(mode),
+    _lib.check(_lib.lib().bp_pose_pnp(e.handle, _lib.ptr(preds_img.contiguous()),
+                                      _lib.ptr(None if maxval is None else maxval.contiguous()),
+                                      _lib.ptr(None if det_score is None else det_score.contiguous()), _lib.ptr(valid), n, K, _lib.ptr(kp3d.contiguous()),
+                                      _lib.ptr(model_idx), C.cast(cam_arr, C.c_void_p), int(left_number), int(mode), int(flags),
                                       float(reproj_thr), int(n_hyp), int(seed) & 0xFFFFFFFF, _lib.ptr(out["keypoints"]),
                                       _lib.ptr(out["kp_score"]), _lib.ptr(out["proposal"]), _lib.ptr(out["selected"]),
                                       _lib.ptr(out["R"]), _lib.ptr(out["t"]), _lib.ptr(out["inlier"]),
@@ -156,9 +171,11 @@ def pack_records(image_index0: int, box, det_score, pose: dict) -> torch.Tensor:
     return out
 
 
+RECORD_DTYPE = np.dtype([("image_index", "<i4"), ("status", "<i4"), ("box", "<f4", 4), ("det_score", "<f4"),
+                         ("proposal_score", "<f4"), ("keypoints", "<f4", 150), ("R", "<f8", 9), ("t", "<f8", 3)], align=True)
+assert RECORD_DTYPE.itemsize == _lib.RECORD_BYTES, (RECORD_DTYPE.itemsize, _lib.RECORD_BYTES)
+
+
 def records_to_numpy(rec_u8: torch.Tensor) -> np.ndarray:
     """host copy of packed records as a numpy structured array."""
-    dt = np.dtype([("image_index", "<i4"), ("status", "<i4"), ("box", "<f4", 4), ("det_score", "<f4"),
-                   ("proposal_score", "<f4"), ("keypoints", "<f4", 150), ("R", "<f8", 9), ("t", "<f8", 3)], align=True)
-    assert dt.itemsize == _lib.RECORD_BYTES, (dt.itemsize, _lib.RECORD_BYTES)
-    return rec_u8.detach().cpu().numpy().view(dt).reshape(-1)
+    return rec_u8.detach().cpu().numpy().view(RECORD_DTYPE).reshape(-1)

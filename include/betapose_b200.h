@@ -140,6 +140,11 @@ int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, const int* gr
                           int frame_h, float* det, float* box, float* score, int32_t* row, uint8_t* valid,
                           float* decoded, void* stream);
 
+/* a4 alone (the `dynamic_write_results(prediction, confidence, ...)` seam, yolo/util.py:104-223, nms off): arg-max
+ * objectness per image over an already decoded prediction tensor pred[B,R,n_attr].  det[B,8] as above; valid[B]. */
+int bp_write_results(bp_engine* e, const float* pred, int B, int R, int n_attr, float conf, float* det, int32_t* row,
+                     uint8_t* valid, void* stream);
+
 /* a6: im_to_torch + crop_from_dets + cropBox (KPD/src/utils/img.py:13-18,242-262; dataloader.py:794-835).
  * frames uint8 [F,H,W,3] RGB; box[n,4]; img_idx[n] (frame of each box); valid[n] (may be NULL).
  * Outputs: out_f16x4 fp16 [n,rh,rw,4] (keypoint-net input) and/or out_f32_chw fp32 [n,3,rh,rw]; pt1/pt2 [n,2]
@@ -164,9 +169,12 @@ int bp_heatmap_decode(bp_engine* e, const float* hm, long img_stride, long k_str
  * Out: keypoints[n,K,2] (= preds - 0.3), kp_score[n,K], proposal[n], selected[n,K] (u8 mask of the points
  * handed to PnP), R f64[n,9] row-major, t f64[n,3], inlier[n,K] u8, status[n]: 1 = pose, 0 = rejected by
  * pose-NMS (max score < 0.3) or invalid, -1 = PnP failed. */
+#define BP_PNP_RAW_POINTS 1 /* preds_img are final key-points (the bare `pnp(points_3D, points_2D, K)` seam): no score
+                               floor / threshold, no -0.3 shift; maxval and det_score may be NULL */
+#define BP_PNP_NMS_ONLY 2   /* stop after pose-NMS + selection (the bare `pose_nms` seam); R, t are left zero */
 int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* maxval, const float* det_score,
                 const uint8_t* valid, int n, int K, const double* kp3d, const int32_t* model_idx, const double* cam,
-                int left_number, int mode, float reproj_thr, int n_hyp, uint32_t seed, float* keypoints,
+                int left_number, int mode, int flags, float reproj_thr, int n_hyp, uint32_t seed, float* keypoints,
                 float* kp_score, float* proposal, uint8_t* selected, double* R, double* t, uint8_t* inlier,
                 int32_t* status, void* stream);
 

@@ -137,9 +137,10 @@ def yolo_decode_head(x: np.ndarray, reso: int = 416, anchors=None) -> np.ndarray
     return det.reshape(B, -1, nattr)
 
 
-def yolo_decode(heads, reso: int = 416) -> np.ndarray:
-    """heads: list of raw [B,18,g,g] in network order (stride 32, 16, 8) -> [B,10647,6]."""
-    return np.concatenate([yolo_decode_head(h, reso) for h in heads], axis=1)
+def yolo_decode(heads, reso: int = 416, anchors=None) -> np.ndarray:
+    """heads: list of raw [B,18,g,g] in network order (stride 32, 16, 8) -> [B,10647,6].
+    anchors: optional per-head anchor lists (default: the yolov3-single.cfg masks by stride)."""
+    return np.concatenate([yolo_decode_head(h, reso, None if anchors is None else anchors[i]) for i, h in enumerate(heads)], axis=1)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -92,13 +92,14 @@ struct Case {
   int x_pitch_extra = 0, out_pitch_extra = 0, out_coff = 0;
   int force_bn = 0, force_st = 0;
   int iters = 0;  // >0: also time it
+  int gather = 0;  // stem mode: C must be 4, K laid out (tap, 4)
 };
 
 static int run_case(const Case& cs) {
   Rng rng(1234);
   const int xp = cs.C + cs.x_pitch_extra;
   const int K = cs.R * cs.S * cs.C;
-  const int wp = (K + 7) / 8 * 8;
+  const int wp = cs.gather ? (cs.R * cs.S + 15) / 16 * 64 : (K + 7) / 8 * 8;
   const int Cout_pad = (cs.Cout + 255) / 256 * 256;
   const int P = (cs.H + 2 * cs.pad - cs.R) / cs.stride + 1, Q = (cs.W + 2 * cs.pad - cs.S) / cs.stride + 1;
   const long M = (long)cs.N * P * Q;
@@ -145,6 +146,7 @@ static int run_case(const Case& cs) {
   d.res = dres; d.res_pitch = cs.Cout; d.res_mode = cs.res_mode;
   d.out = dout; d.out_pitch = opitch; d.out_coff = cs.out_coff; d.out_f32 = cs.out_f32; d.store_mode = cs.store_mode;
   d.force_block_n = cs.force_bn; d.force_stages = cs.force_st;
+  d.gather = cs.gather;
   ConvPlan pl;
   std::string err;
   if (!conv_plan_build(g_api, &pl, d, &err)) {
@@ -337,6 +339,15 @@ int main(int argc, char** argv) {
   pf += run_probe(3, 15, 11, 64, 1, 1, 2, 0, 0, 0, 0);
   printf("probe failures: %d\n", pf);
   if (probe_only) return pf ? 1 : 0;
+
+  std::vector<Case> stem = {
+      {"stem 3x3 s1 4->32 40x36", 3, 40, 36, 4, 32, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 1},
+      {"stem 7x7 s2 4->64 64x48", 3, 64, 48, 4, 64, 7, 7, 2, 3, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 1},
+      {"stem 3x3 s1 4->32 @416 B64", 64, 416, 416, 4, 32, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 5, 1},
+      {"stem 7x7 s2 4->64 @320x256 B64", 64, 320, 256, 4, 64, 7, 7, 2, 3, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 5, 1},
+  };
+  if (!probe_only)
+    for (auto& c : stem) fails += run_case(c);
 
   std::vector<Case> conv = {
       {"3x3 s1 C64->128 13x13", 2, 13, 13, 64, 128, 3, 3, 1, 1},

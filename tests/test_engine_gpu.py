@@ -146,3 +146,18 @@ def test_planted_pose_tail(kp_model, frames8):
         # planted pose recovered: key-points are quantised to quarter cells of a ~(lenH/80) px grid
         assert sol["inliers"].sum() >= 45
         assert np.abs(Rg - poses[i][0]).max() < 0.08 and np.abs(tg - poses[i][1]).max() < 0.05
+
+
+def test_evaluate_cli_synthetic(tmp_path):
+    """The command-line path with synthetic frames + weights: Betapose-results.json in the reference's format."""
+    import json
+
+    from betapose_b200 import evaluate
+
+    assert evaluate.main(["--synthetic", "6", "--batch", "4", "--outdir", str(tmp_path), "--nClasses", "50", "--sp"]) == 0
+    res = json.load(open(tmp_path / "Betapose-results.json"))
+    assert isinstance(res, list) and len(res) <= 6
+    for e in res:
+        assert set(e) == {"image_id", "cam_R", "cam_t", "keypoints", "score"}
+        assert len(e["cam_R"]) == 9 and len(e["cam_t"]) == 3 and len(e["keypoints"]) == 150
+        assert e["image_id"].startswith("synthetic_")

@@ -1,0 +1,146 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from betapose_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "betapose_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.bp_version() == 100
+    # struct layouts shared across the boundary
+    assert C.sizeof(_lib.Record) == 4 + 4 + 16 + 4 + 4 + 600 + 72 + 24
+    assert C.sizeof(_lib.ConvSpec) == 12 * 4 + 6 * 8 + 8
+
+
+def test_engine_create_fails_loudly_without_gpu():
+    from betapose_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = _lib.lib().bp_engine_create(0, C.byref(h))
+    assert rc < 0 and b"no CUDA device" in _lib.lib().bp_last_error()
+    with pytest.raises(_lib.BetaposeError):
+        _lib.Engine.get(0)
+    from betapose_b200 import compat
+
+    with pytest.raises(_lib.BetaposeError):
+        compat.getPrediction(torch.zeros(1, 50, 80, 64), torch.zeros(1, 2), torch.ones(1, 2), 320, 256, 80, 64)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "betapose_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace("oracle/pnp.py", "").replace("oracle/restate.py", ""), f
+
+
+def test_darknet_cfg_shapes_and_weight_split():
+    from betapose_b200 import net as bnet, yolo_cfg
+
+    blocks = yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+    kinds = [b["type"] for b in blocks]
+    assert (kinds.count("convolutional"), kinds.count("shortcut"), kinds.count("route"), kinds.count("upsample"), kinds.count("yolo")) == (75, 23, 4, 2, 3)
+    info = bnet.infer_darknet_shapes(blocks, 416)
+    assert [(info[i]["H"], info[i]["C"]) for i in (81, 93, 105)] == [(13, 18), (26, 18), (52, 18)]
+    assert info[86]["C"] == 768 and info[98]["C"] == 384
+    n_floats = 0
+    for i, b in enumerate(blocks):
+        if b["type"] == "convolutional":
+            cin = 3 if i == 0 else info[i - 1]["C"]
+            co, k = int(b["filters"]), int(b["size"])
+            n_floats += co * cin * k * k + (4 * co if int(b.get("batch_normalize", 0)) else co)
+    assert n_floats == 61_576_342  # 61,523,734 parameters + 52,608 BN running statistics
+    stream = np.arange(n_floats, dtype=np.float32)
+    params, used = bnet.split_darknet_stream(blocks, stream)
+    assert used == n_floats
+    assert params[0]["bn_bias"][0] == 0 and params[0]["bn_weight"][0] == 32 and params[0]["weight"].shape == (32, 3, 3, 3)
+    with pytest.raises(Exception):
+        bnet.split_darknet_stream(blocks, stream[:-5])
+
+
+def test_opt_surface_matches_reference_defaults():
+    from betapose_b200 import opt as O
+
+    o = O.parse_args([])
+    assert (o.nClasses, o.inputResH, o.inputResW, o.outputResH, o.outputResW) == (50, 320, 256, 80, 64)
+    assert (o.inp_dim, o.confidence, o.nms_thesh, o.detbatch, o.posebatch, o.left_keypoints, o.obj_id) == ("416", 0.01, 0.6, 1, 80, 10, 5)
+    assert o.num_classes == 80 and o.outputpath == "examples/res/"
+    o = O.parse_args(["--nClasses", "50", "--indir", "a", "--outdir", "b", "--sp", "--profile", "--unknown-training-flag", "3"])
+    assert o.inputpath == "a" and o.outputpath == "b" and o.sp and o.profile
+
+
+def test_write_json_format(tmp_path):
+    from betapose_b200 import compat
+
+    rec_dt = np.dtype([("image_index", "<i4"), ("status", "<i4"), ("box", "<f4", 4), ("det_score", "<f4"), ("proposal_score", "<f4"),
+                       ("keypoints", "<f4", 150), ("R", "<f8", 9), ("t", "<f8", 3)], align=True)
+    rec = np.zeros(3, rec_dt)
+    rec["status"] = [1, 0, -1]
+    rec["keypoints"][0] = np.arange(150)
+    rec["R"][0] = np.arange(9)
+    rec["t"][0] = [0.1, 0.2, 0.9]
+    rec["proposal_score"][0] = 2.5
+    res = [compat.result_from_record(rec[i], f"/data/rgb/{i:04d}.png") for i in range(3)]
+    out = compat.write_json(res, str(tmp_path))
+    on_disk = json.load(open(tmp_path / "Betapose-results.json"))
+    assert on_disk == out and len(out) == 1  # rejected / failed frames emit no entry (pPose_nms.py:296)
+    e = out[0]
+    assert e["image_id"] == "0000.png" and e["cam_R"] == list(map(float, range(9))) and e["cam_t"] == [0.1, 0.2, 0.9]
+    assert e["keypoints"][:6] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and len(e["keypoints"]) == 150 and e["score"] == 2.5
+    out = compat.write_json(res, str(tmp_path), for_eval=True)
+    assert out[0]["image_id"] == 0
+
+
+def test_shard_ranges_cover_everything():
+    from betapose_b200 import dist as D
+
+    for n in (0, 1, 7, 64, 128, 256, 1000):
+        for w in (1, 2, 3, 4, 8):
+            r = [D.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+    assert D.shard_sizes(256, 8) == [32] * 8 and D.shard_sizes(128, 8) == [16] * 8  # BASELINE.json configs 4 and 5
+
+
+def test_model3d_ply_roundtrip(tmp_path):
+    from betapose_b200 import model3d
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "kp_models.npz"))
+    v = g["obj_1"]
+    p = tmp_path / "obj_01.ply"
+    with open(p, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nend_header\n" % len(v))
+        for row in v * 1000.0:
+            f.write("%.9g %.9g %.9g\n" % tuple(row))
+    out = model3d.load_kp_model(str(p), 50)
+    np.testing.assert_allclose(out, v, rtol=1e-7)
+    assert model3d.refine(v, 40).shape == (40, 3)
+    from oracle import restate as R
+
+    assert np.array_equal(model3d.refine(v, 44), R.refine_vertices(v, 44))
+    q = tmp_path / "obj_10.ply"
+    with open(q, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 17\nproperty float x\nproperty float y\nproperty float z\nend_header\n")
+        for row in g["obj_10"] * 1000.0:
+            f.write("%.9g %.9g %.9g\n" % tuple(row))
+    with pytest.raises(ValueError):
+        model3d.load_kp_model(str(q), 50)   # the shipped obj-10 model has 17 points
+    assert np.array_equal(model3d.CAM_K, R.CAM_K)

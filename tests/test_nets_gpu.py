@@ -196,7 +196,7 @@ def test_yolov3_full_vs_oracle(yolo_blocks, yolo_stream, frames8):
     u8x4, _ = stages.resize_bicubic(fr, 416, 416)
     x = u8x4[..., :3].cpu().numpy()
     n, got = _run_yolo(yolo_blocks, yolo_stream, x, 416)
-    assert n.num_ops == 76  # stem im2col + 75 convs: every shortcut / route / upsample fused away
+    assert n.num_ops == 75  # 75 convs: every shortcut / route / upsample fused away, the stem gathers its own operand
     assert abs(n.flops_per_image - 65.29e9) < 0.05e9
     params, used = onets.split_darknet_weights(yolo_blocks, yolo_stream)
     assert used == yolo_stream.size

@@ -1,0 +1,190 @@
+"""CPU: the oracle (oracle/restate.py, oracle/nets.py, oracle/pnp.py) against golden vectors produced by the
+unmodified reference + Pillow + OpenCV (tests/golden/make_golden.py, versions recorded inside each file).
+This is what pins the oracle where /root/reference does not exist (e.g. the GPU box)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets as onets
+from oracle import pnp as opnp
+from oracle import restate as R
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+# ------------------------------------------------------------------------------------------------ a1
+def test_resize_bit_exact_vs_pillow():
+    g = load("resize_golden.npz")
+    assert np.array_equal(R.pil_resize_bicubic(g["small"], 31, 29), g["small_out"])      # down-scale (anti-aliased support)
+    assert np.array_equal(R.pil_resize_bicubic(g["up"], 40, 48), g["up_out"])            # up-scale
+    frame = np.random.default_rng(int(g["frame_seed"])).integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    big = R.pil_resize_bicubic(frame, 416, 416)
+    assert np.array_equal(big[::52], g["big_rows"])
+    assert hashlib.sha256(big.tobytes()).hexdigest() == str(g["big_sha256"])
+    x = R.yolo_input_from_frame(frame)
+    assert x.shape == (3, 416, 416) and x.dtype == np.float32 and np.array_equal(x[1], big[:, :, 1].astype(np.float32) / np.float32(255))
+
+
+# ------------------------------------------------------------------------------------------------ a2-a5
+def test_darknet_mini_vs_reference():
+    from betapose_b200 import yolo_cfg
+
+    g = load("darknet_mini_golden.npz")
+    blocks = yolo_cfg.parse_cfg_text(str(g["cfg"]))
+    params, used = onets.split_darknet_weights(blocks, g["stream"])
+    assert used == g["stream"].size
+    with torch.no_grad():
+        heads = onets.darknet_forward(blocks, params, torch.from_numpy(g["x"]))
+    pred = R.yolo_decode([h.numpy() for h in heads], reso=64, anchors=[R.YOLO_ANCHORS[32], R.YOLO_ANCHORS[16]])
+    assert pred.shape == g["pred"].shape
+    np.testing.assert_allclose(pred, g["pred"], rtol=2e-5, atol=2e-5)
+    dets, rows = R.write_results(pred, 0.01)
+    gd = g["dets"]
+    assert dets.shape == gd.shape
+    np.testing.assert_allclose(dets, gd, rtol=3e-5, atol=2e-4)
+    # the winning row is exactly the reference's: re-derive it from the golden prediction tensor
+    _, rows_g = R.write_results(g["pred"], 0.01)
+    assert np.array_equal(rows, rows_g)
+    assert R.write_results(pred * 0, 0.6) == (0, None)  # "no detection in the whole batch" sentinel (util.py:122-125)
+
+
+def test_yolo_cfg_matches_reference_file():
+    from betapose_b200 import yolo_cfg
+
+    g = load("yolo_cfg_golden.npz")
+    blocks = yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+    assert len(blocks) == int(g["n_blocks"]) == 107
+    ours = [repr(sorted(b.items())) for b in blocks]
+    assert ours == [str(x) for x in g["blocks"]]
+
+
+# ------------------------------------------------------------------------------------------------ a6
+def test_crop_vs_reference():
+    g = load("crop_golden.npz")
+    fr = g["frame"]
+    full = []
+    for i, box in enumerate(g["boxes"]):
+        pt1, pt2 = R.expand_box(box, 640, 480)
+        assert np.array_equal(pt1, g["pt1"][i]) and np.array_equal(pt2, g["pt2"][i])
+        full.append(R.crop_box(fr, pt1, pt2))
+    full = np.stack(full)
+    np.testing.assert_allclose(full[:, :, ::7, ::5], g["inps_sub"], rtol=0, atol=2.4e-7)
+    np.testing.assert_allclose(full.mean(axis=(2, 3)), g["inps_mean"], atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ a8
+def test_get_prediction_vs_reference():
+    g = load("getpred_golden.npz")
+    hm = g["hm"].astype(np.float32)  # stored as fp16: exactly representable inputs for both sides
+    ph, pi, mv, idx, sign = R.get_prediction(hm, g["pt1"], g["pt2"])
+    # golden was produced from the fp32 originals; fp16 storage only changes values, not the planted structure
+    assert ph.shape == g["preds_hm"].shape
+    agree = np.all(ph == g["preds_hm"], axis=2).mean()
+    assert agree > 0.97  # fp16 storage can flip a near-tie arg-max / gradient sign in a random map
+    same = np.all(ph == g["preds_hm"], axis=2)
+    np.testing.assert_allclose(pi[same], g["preds_img"][same], rtol=0, atol=1e-4)
+    # the planted cases must agree exactly
+    for (i, k) in ((0, 0), (0, 1), (1, 2), (1, 3), (2, 4), (3, 5)):
+        assert np.array_equal(ph[i, k], g["preds_hm"][i, k]), (i, k)
+        np.testing.assert_allclose(pi[i, k], g["preds_img"][i, k], atol=1e-4)
+    assert np.array_equal(ph[0, 0], np.float32([0.2, 0.2])) and np.array_equal(ph[1, 2], np.float32([0.2, 0.2]))
+    assert np.array_equal(ph[2, 4], np.float32([30.2 + 0.25, 40.2 + 0.25]))  # tie -> lowest index, gradient towards the twin
+
+
+# ------------------------------------------------------------------------------------------------ a9
+def test_pose_nms_vs_reference():
+    g = load("pose_nms_golden.npz")
+    for i in range(int(g["n_cases"])):
+        res = R.pose_nms(g[f"c{i}_bb"], g[f"c{i}_bs"], g[f"c{i}_pp"], g[f"c{i}_ps"])
+        assert len(res) == int(g[f"c{i}_n"]), i
+        for j, r in enumerate(res):
+            np.testing.assert_allclose(r["keypoints"], g[f"c{i}_r{j}_kp"], rtol=1e-6, atol=1e-4)
+            np.testing.assert_allclose(r["kp_score"].reshape(-1), g[f"c{i}_r{j}_sc"].reshape(-1), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(np.asarray(r["proposal_score"]).reshape(-1), g[f"c{i}_r{j}_prop"].reshape(-1), rtol=1e-5)
+            np.testing.assert_allclose(r["bbox"], g[f"c{i}_r{j}_bbox"])
+        if g[f"c{i}_bb"].shape[0] == 1 and len(res) == 1:
+            # n = 1 closed form used by the CUDA kernel
+            one = R.pose_nms_single(float(g[f"c{i}_bs"][0, 0]), g[f"c{i}_pp"][0], g[f"c{i}_ps"][0])
+            assert np.array_equal(one[0], g[f"c{i}_r0_kp"])
+            np.testing.assert_allclose(one[2], g[f"c{i}_r0_prop"].reshape(-1)[0], rtol=1e-6)
+    # the rejected case
+    last = int(g["n_cases"]) - 1
+    assert int(g[f"c{last}_n"]) == 0
+    assert R.pose_nms_single(float(g[f"c{last}_bs"][0, 0]), g[f"c{last}_pp"][0], g[f"c{last}_ps"][0]) is None
+
+
+def test_select_keypoints():
+    sc = np.float32([0.5, 0.1, 0.9, 0.1, 0.3, 0.7])
+    assert R.select_keypoints(sc, 6).tolist() == [0, 1, 2, 3, 4, 5]
+    assert R.select_keypoints(sc, 4).tolist() == [0, 2, 4, 5]       # both 0.1s go, first one first
+    assert R.select_keypoints(sc, 5).tolist() == [0, 2, 3, 4, 5]
+
+
+# ------------------------------------------------------------------------------------------------ a11
+def test_pnp_vs_opencv_golden():
+    """solve_pnp(MODE_RANSAC) against cv2.solvePnPRansac(reprojectionError=12) and, at <= 0.1 px noise, against the
+    active cv2.solvePnP call (utils/utils.py:25-29).  Tolerance of record: 1e-3 on R and t (BASELINE.json)."""
+    g = load("pnp_golden.npz")
+    kp = g["kp3d"]
+    n_same = n_tot = 0
+    for i in range(len(g["uv"])):
+        sol = opnp.solve_pnp(kp, g["uv"][i], R.CAM_K, mode=opnp.MODE_RANSAC, thr=12.0, n_hyp=64, seed=i)
+        assert sol["ok"]
+        same = np.array_equal(sol["inliers"], g["inliers"][i])
+        n_tot += 1
+        n_same += int(same)
+        if same:
+            # tolerance of record is 1e-3; with equal consensus sets the two LM refits agree to ~1e-8
+            np.testing.assert_allclose(sol["R"], g["R_ransac"][i], atol=1e-6)
+            np.testing.assert_allclose(sol["t"], g["t_ransac"][i], atol=1e-6)
+        else:
+            # consensus sets differ by borderline points judged against different 5-point models (SURVEY D5 iii):
+            # both are refits on slightly different inlier sets of the same pose
+            assert np.abs(sol["inliers"].astype(int) - g["inliers"][i].astype(int)).sum() <= 3
+            # (seen once in the 30 KATs: sigma = 2 px + 10 outliers, 40 vs 41 inliers, ours closer to the planted pose)
+            np.testing.assert_allclose(sol["R"], g["R_ransac"][i], atol=6e-2)
+            np.testing.assert_allclose(sol["t"], g["t_ransac"][i], atol=6e-2)
+            assert np.abs(sol["R"] - g["R_true"][i]).max() <= np.abs(g["R_ransac"][i] - g["R_true"][i]).max() + 1e-2
+        if g["sigma"][i] <= 0.1:
+            np.testing.assert_allclose(sol["R"], g["R_true"][i], atol=5e-3)  # 0.1 px noise on a 10 cm object
+            a = opnp.solve_pnp(kp, g["uv"][i], R.CAM_K, mode=opnp.MODE_ALLPTS)
+            np.testing.assert_allclose(a["R"], g["R_ransac"][i], atol=1e-3)
+            if np.abs(g["R_iter"][i] - g["R_true"][i]).max() < 1e-2:  # where ITERATIVE itself converged (SURVEY D5 ii)
+                np.testing.assert_allclose(a["R"], g["R_iter"][i], atol=1e-3)
+                np.testing.assert_allclose(a["t"], g["t_iter"][i], atol=1e-3)
+    assert n_same >= 0.9 * n_tot, (n_same, n_tot)
+
+
+def test_kp_models_shipped():
+    g = load("kp_models.npz")
+    assert sorted(g.files) == sorted(f"obj_{i}" for i in (1, 2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15))
+    for k in g.files:
+        assert g[k].shape == ((17, 3) if k == "obj_10" else (50, 3))  # the shipped obj-10 PLY has 17 vertices
+        assert np.abs(g[k]).max() < 0.2  # metres
+    v = g["obj_1"]
+    assert np.array_equal(R.refine_vertices(v, 50), v)
+    assert R.refine_vertices(v, 45).shape == (45, 3)
+
+
+# ------------------------------------------------------------------------------------------------ a7
+def test_fastpose_vs_reference():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(G, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = load("fastpose_golden.npz")
+    sd = mg.fastpose_det_weights(int(g["seed"]))
+    with torch.no_grad():
+        hm = onets.fastpose_forward(sd, torch.from_numpy(g["x"])).numpy()
+    assert hm.shape == (1, 50, 80, 64)
+    scale = float(g["hm_absmax"])
+    np.testing.assert_allclose(hm[:, :, ::4, ::4], g["hm_sub"], rtol=0, atol=2e-4 * scale)
+    assert (hm.reshape(1, 50, -1).argmax(2) == g["hm_argmax"]).mean() >= 0.98
