@@ -56,18 +56,25 @@ __global__ void maxpool3x3s2_kernel(TView in, TView out, int N) {
 }
 
 // AdaptiveAvgPool2d(1): mean over H*W per (n, c), fp32 accumulate, fp16 result [N, C]  -- SE_module.py:7,16
-// grid (C/256, N), block 256 = 32 channel-groups x 8 pixel lanes.
-__global__ void global_avgpool_kernel(TView in, __half* out, int out_pitch) {
+// grid (C/256, N, S), block 256 = 32 channel-groups x 8 pixel lanes.  The H*W pixels of an image are cut into S
+// slices so that even a 64-image batch fills the machine; every block leaves its partial sums in `scratch`
+// ([N][S][C] fp32) and the last block to finish an (image, channel-block) adds the S partials in a fixed order
+// (bit-reproducible: no floating-point atomics) and writes the fp16 mean.
+__global__ void global_avgpool_kernel(TView in, __half* out, int out_pitch, float* scratch, unsigned* counters, int S) {
   __shared__ float red[8][32][8];
+  __shared__ bool s_last;
   const int n = blockIdx.y;
+  const int sl = blockIdx.z;
   const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
   const int pl = threadIdx.x >> 5;
   const int HW = in.H * in.W;
+  const int chunk = (HW + S - 1) / S;
+  const int px0 = sl * chunk, px1 = min(HW, px0 + chunk);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const bool live = cg * 8 < in.C;
   if (live) {
     const __half* ip = reinterpret_cast<const __half*>(in.ptr) + (long)n * HW * in.pitch + cg * 8;
-    for (int px = pl; px < HW; px += 8) {
+    for (int px = px0 + pl; px < px1; px += 8) {
       const uint4 v = ldg16(ip + (long)px * in.pitch);
       const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -81,17 +88,49 @@ __global__ void global_avgpool_kernel(TView in, __half* out, int out_pitch) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[pl][threadIdx.x & 31][i] = acc[i];
   __syncthreads();
+  float* part = scratch + ((long)n * S) * in.C + cg * 8;
   if (pl == 0 && live) {
+    float4 lo, hi;
+    float* f = &lo.x;
+    float* g = &hi.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        a += red[l][threadIdx.x & 31][i];
+        b += red[l][threadIdx.x & 31][4 + i];
+      }
+      f[i] = a;
+      g[i] = b;
+    }
+    float* dst = part + (long)sl * in.C;
+    *reinterpret_cast<float4*>(dst) = lo;
+    *reinterpret_cast<float4*>(dst + 4) = hi;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ctr = counters + (long)n * gridDim.x + blockIdx.x;
+    const unsigned old = atomicAdd(ctr, 1u);
+    s_last = old == (unsigned)S - 1u;
+    if (s_last) *ctr = 0u;  // ready for the next launch
+  }
+  __syncthreads();
+  if (s_last && pl == 0 && live) {
+    __threadfence();
+    float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < S; ++k) {
+      const float4 lo = __ldcg(reinterpret_cast<const float4*>(part + (long)k * in.C));
+      const float4 hi = __ldcg(reinterpret_cast<const float4*>(part + (long)k * in.C + 4));
+      sum[0] += lo.x; sum[1] += lo.y; sum[2] += lo.z; sum[3] += lo.w;
+      sum[4] += hi.x; sum[5] += hi.y; sum[6] += hi.z; sum[7] += hi.w;
+    }
     uint4 o;
     __half* oh = reinterpret_cast<__half*>(&o);
     const float inv = 1.f / (float)HW;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float s = 0.f;
-#pragma unroll
-      for (int l = 0; l < 8; ++l) s += red[l][threadIdx.x & 31][i];
-      oh[i] = __float2half_rn(s * inv);
-    }
+    for (int i = 0; i < 8; ++i) oh[i] = __float2half_rn(sum[i] * inv);
     stg16(out + (long)n * out_pitch + cg * 8, o);
   }
 }

@@ -25,6 +25,7 @@ struct ConvDesc {
   void* out = nullptr;
   int out_pitch = 0, out_coff = 0, out_f32 = 0, store_mode = STORE_PLAIN;
   int force_block_n = 0;  // 0 = heuristic
+  int force_cg = 0;       // 0 = heuristic, 1 = single CTA, 2 = CTA pairs (cta_group::2)
   int force_stages = 0;   // kept for the harness; the stage count now follows from the tile configuration
   int num_sms = 148;
   // gather mode (stem): x is [N, H, W, 4] uint8 or fp16, C = 4, weights packed [Cout_pad][taps_pad16 * 4]
@@ -37,30 +38,51 @@ struct ConvPlan {
   alignas(64) CUtensorMap tmOut;  // valid when args.tma_store
   alignas(64) CUtensorMap tmRes;  // valid when args.tma_store && residual
   ConvArgs args;
-  int block_n = 0, block_k = 0, stages = 0, grid = 0;
+  int block_n = 0, block_k = 0, stages = 0, grid = 0, cg = 1;
   int P = 0, Q = 0;
   double flops = 0;
 };
 
-template <int BN, int BK, int ST, bool GATHER = false>
+template <int BN, int BK, int ST, bool GATHER = false, int CG = 1, int NB = 4>
 inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, BK, ST>;
+  using Cfg = ConvCfg<BN, BK, ST, CG, NB>;
   static bool attr_done = false;  // per-instantiation; set once per process (single device per process)
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, GATHER, CG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  conv_umma_kernel<BN, BK, ST, GATHER><<<pl.grid, Cfg::THREADS + (GATHER ? 128 : 0), Cfg::SMEM_BYTES, st>>>(
-      pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
-  return cudaGetLastError();
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, GATHER, CG, NB>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+  } else {
+    conv_umma_kernel<BN, BK, ST, GATHER, CG, NB><<<pl.grid, Cfg::THREADS + (GATHER ? 128 : 0), Cfg::SMEM_BYTES, st>>>(
+        pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+    return cudaGetLastError();
+  }
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
   if (pl.args.a_im2col == 2) {
     if (pl.block_n == 32) return launch_cfg<32, 64, 6, true>(pl, st);
     if (pl.block_n == 64) return launch_cfg<64, 64, 6, true>(pl, st);
+    return cudaErrorInvalidConfiguration;
+  }
+  if (pl.cg == 2) {
+    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 4, false, 2>(pl, st);
+    if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, false, 2>(pl, st);
     return cudaErrorInvalidConfiguration;
   }
 #define BP_CASE(BN, BK, ST) \
@@ -86,19 +108,52 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
     if (err) *err = "im2col conv needs Cin % 32 == 0";
     return false;
   }
-  int bn = d.force_block_n;
-  if (!bn) {
-    bn = 32;
-    while (bn < d.Cout && bn < 256) bn *= 2;
-    if (block_k == 32 && bn > 64) bn = 64;
-    // keep the grid reasonably full on small layers
-    while (bn > 64 && (long)((M + 127) / 128) * ((d.Cout + bn - 1) / bn) < 148) bn /= 2;
+  // Tile configuration by a small cost model fitted to B200 measurements (tests/harness/conv_harness.cu, batch 64):
+  // a persistent grid walks the tiles round-robin, so a launch takes ceil(tiles / CTAs) rounds of one tile each, and a
+  // k-block costs ~500 + (BLOCK_K / 16) * bn / 2 cycles (bn = 64 / 128 / 256: 628 / 758 / 1000-1040 measured; the
+  // second term is the tensor-pipe time, the first does not shrink with the tile).  Wider tiles therefore win unless
+  // they leave most of the machine idle.  CTA pairs (cta_group::2, M = 256) measured within +-5 % of single CTAs on
+  // every production shape, so they are only used when forced (d.force_cg = 2).
+  int bn = d.force_block_n, cg = d.force_cg;
+  {
+    int cap = 32;
+    while (cap < d.Cout && cap < 256) cap *= 2;
+    if (block_k == 32 || d.gather) cap = std::min(cap, 64);
+    const long m_tiles_ = (M + 127) / 128;
+    const int K_ = d.gather ? (d.R * d.S + 15) / 16 * 64 : d.R * d.S * d.C;
+    const long nkb = (K_ + block_k - 1) / block_k;
+    double best = 0;
+    int best_bn = 0, best_cg = 0;
+    for (int c = cap; c >= 32; c /= 2) {
+      if (d.force_block_n && c != d.force_block_n) continue;
+      if (d.Cout_pad % c) continue;
+      for (int g = 1; g <= 2; ++g) {
+        if (g != (d.force_cg ? d.force_cg : 1)) continue;
+        if (g == 2 && (block_k != 64 || c < 128 || d.gather || d.num_sms < 2)) continue;
+        const long tiles = ((m_tiles_ + g - 1) / g) * ((d.Cout + c - 1) / c);
+        const long units = g == 2 ? d.num_sms / 2 : d.num_sms;
+        const long rounds = (tiles + units - 1) / units;
+        const double per_kb = 500.0 + (block_k / 16) * (c / 2.0);
+        const double cost = rounds * (nkb * per_kb + 400.0 + 200.0 * ((c + 63) / 64));
+        if (!best_bn || cost < 0.97 * best) {  // later candidates (narrower / paired) must win by 3 %
+          best_bn = c;
+          best_cg = g;
+          best = cost;
+        }
+      }
+    }
+    if (!best_bn) {
+      if (err) *err = "no tile configuration fits (forced block_n / cg?)";
+      return false;
+    }
+    bn = best_bn;
+    cg = best_cg;
   }
   if (d.Cout_pad % bn != 0) {
     if (err) *err = "Cout_pad must be a multiple of BLOCK_N";
     return false;
   }
-  const int st = bn == 256 ? 3 : (bn == 128 ? 4 : (block_k == 64 ? 6 : 8));
+  const int st = cg == 2 ? (bn == 256 ? 4 : 6) : (bn == 256 ? 3 : (bn == 128 ? 4 : (block_k == 64 ? 6 : 8)));
   const int K = d.gather ? (d.R * d.S + 15) / 16 * 64 : d.R * d.S * d.C;  // gather: 16 taps x 4 channels per k-block
   const int num_kb = (K + block_k - 1) / block_k;
 
@@ -111,7 +166,9 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   // tiles whose channels are all padding are never launched
   const int n_tiles_live = (d.Cout + bn - 1) / bn;
   const int m_tiles = (M + 127) / 128;
-  pl->grid = std::min(m_tiles * n_tiles_live, d.num_sms);  // persistent: one CTA per SM
+  pl->cg = cg;
+  // persistent: one CTA per SM (pairs: one cluster of 2 per TPC)
+  pl->grid = cg == 2 ? 2 * std::min(((m_tiles + 1) / 2) * n_tiles_live, d.num_sms / 2) : std::min(m_tiles * n_tiles_live, d.num_sms);
   (void)n_tiles;
   pl->flops = 2.0 * M * (double)d.Cout * (d.gather ? d.R * d.S * 3 : K);
 
@@ -130,6 +187,8 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.Q = Q;
   a.stride = d.stride;
   a.pad = d.pad;
+  a.pad_w = d.pad;
+  a.C = d.C;
   a.S = d.S;
   a.cblocks = d.C / block_k;
   a.Cout = d.Cout;
@@ -161,7 +220,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
                           err))
       return false;
   }
-  if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn, block_k, err))
+  if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn / cg, block_k, err))
     return false;
   if (d.gather) pl->tmA = pl->tmB;
   pl->tmOut = pl->tmB;  // placeholders keep the kernel parameters well-formed when the TMA epilogue is off

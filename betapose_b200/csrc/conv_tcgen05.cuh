@@ -33,7 +33,9 @@ struct ConvArgs {
   int num_kb;    // K / BLOCK_K
   int a_im2col;  // 1: A through the im2col tensor map over NHWC; 0: A is a row-major [M, K] matrix; 2: gathered (stem)
   int P, Q;      // output height / width
-  int stride, pad;
+  int stride, pad;  // pad = vertical padding
+  int pad_w;        // horizontal padding (== pad except for the packed stem convolutions)
+  int C;            // input channels per filter tap as seen by the im2col map (multiple of BLOCK_K)
   int S;         // filter width
   int cblocks;   // Cin / BLOCK_K
   int Cout;      // real output channels
@@ -63,18 +65,23 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES>
+// CG = 2: the kernel runs as CTA pairs (cluster of 2, tcgen05 cta_group::2).  A pair computes a 256 x BLOCK_N tile:
+// each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues M = 256 MMAs that read both CTAs'
+// shared memory, and each CTA's TMEM receives its own 128 x BLOCK_N accumulator (so the epilogue is unchanged).
+// Per CTA and k-block that is 128*SWZ + BLOCK_N/2*SWZ bytes from L2 instead of 128*SWZ + BLOCK_N*SWZ: the L2->SM
+// fabric (~43 B/clk/SM on B200) is what bounds the single-CTA kernel on every compute-heavy layer.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4>
 struct ConvCfg {
   static constexpr int BLOCK_M = 128;
   static constexpr int SWZ = BLOCK_K * 2;  // bytes per smem row == swizzle span
   static constexpr int A_BYTES = BLOCK_M * SWZ;
-  static constexpr int B_BYTES = BLOCK_N * SWZ;
+  static constexpr int B_BYTES = (BLOCK_N / CG) * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CHUNK = BLOCK_N >= 64 ? 64 : 32;  // output channels per epilogue chunk / TMA store box
   static constexpr int OUT_SWZ = CHUNK * 2;
   static constexpr int CHUNK_BYTES = BLOCK_M * OUT_SWZ;
   static constexpr int N_CHUNKS = BLOCK_N / CHUNK;
-  static constexpr int NBUF = 4;                       // ring of chunk buffers: residual lands in it, result leaves from it
+  static constexpr int NBUF = NB;                      // ring of chunk buffers: residual lands in it, result leaves from it
   static constexpr int EPI_BYTES = NBUF * CHUNK_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;  // + slack for 1024B alignment
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -153,12 +160,13 @@ __device__ __forceinline__ void epi_dispatch(int act, int res_mode, const uint32
 #undef BP_EPI
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, bool GATHER = false>
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool GATHER = false, int CG = 1, int NB = 4>
 __global__ void __launch_bounds__(GATHER ? 448 : 320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB>;
+  static_assert(CG == 1 || (CG == 2 && !GATHER && BLOCK_N >= 64), "pairs: plain convolutions with BLOCK_N >= 64");
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
   constexpr int CHUNK = Cfg::CHUNK;
@@ -178,7 +186,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;  // NBUF x CHUNK_BYTES
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // tile walk: cluster c of the grid takes (pair-)tiles c, c + num_clusters, ...; inside a pair CTA `rank` owns the
+  // rows of m-tile 2 * pair_m_tile + rank
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cl_id = CG == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int cl_num = CG == 2 ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int total_tiles = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -195,95 +208,124 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], Cfg::EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[s], Cfg::EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
 #pragma unroll
     for (int s = 0; s < Cfg::NBUF; ++s) mbar_init(&res_full_bar[s], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_slot);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(&tmem_base_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    int kc = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m0 = (tile / p.n_tiles) * Cfg::BLOCK_M;
-      const int n0 = n_tile * BLOCK_N;
-      int w0 = 0, h0 = 0, img = 0;
-      if (p.a_im2col) {
-        const int pq = p.P * p.Q;
-        img = m0 / pq;
-        const int rem = m0 - img * pq;
-        const int op = rem / p.Q;
-        const int oq = rem - op * p.Q;
-        w0 = oq * p.stride - p.pad;
-        h0 = op * p.stride - p.pad;
-      }
-      int tap = 0, cb = 0, fr = 0, fs = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (lane == 0) {
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[s], GATHER ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
-          if constexpr (!GATHER) {
-            if (p.a_im2col) {
-              tma_load_im2col_4d(&tmA, &full_bar[s], sa, cb * BLOCK_K, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
+    // ------------------------------------------------------------ TMA producer (one thread: the loop is pure issue
+    // overhead, so it is kept to a handful of instructions per k-block; the other 31 lanes idle at the final barrier)
+    if (lane == 0) {
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t s = 0, ph = 0;
+      for (int tile = cl_id; tile < total_tiles; tile += cl_num) {
+        const int pm_tile = tile / p.n_tiles;
+        const int n0 = (tile - pm_tile * p.n_tiles) * BLOCK_N + int(rank) * (BLOCK_N / CG);  // this CTA's share of B
+        const int m0 = (pm_tile * CG + int(rank)) * Cfg::BLOCK_M;
+        int w0 = 0, h0 = 0, img = 0;
+        if (p.a_im2col == 1) {
+          const int pq = p.P * p.Q;
+          img = m0 / pq;
+          const int rem = m0 - img * pq;
+          const int op = rem / p.Q;
+          const int oq = rem - op * p.Q;
+          w0 = oq * p.stride - p.pad_w;
+          h0 = op * p.stride - p.pad;
+        }
+        int cb = 0, fr = 0, fs = 0, kcol = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
+          const uint32_t sa = smem_base + s * uint32_t(Cfg::STAGE_BYTES);
+          const uint32_t fb = CG == 2 ? leader_addr(full0 + 8u * s) : full0 + 8u * s;
+          if constexpr (CG == 2) {
+            // the leader's barrier collects the bytes of both CTAs
+            if (rank == 0) mbar_expect_tx_a(fb, 2 * Cfg::STAGE_BYTES);
+            if (p.a_im2col == 1) {
+              tma_load_im2col_4d_cg2(&tmA, fb, sa, cb, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
             } else {
-              tma_load_2d(&tmA, &full_bar[s], sa, kb * BLOCK_K, m0);
+              tma_load_2d_cg2(&tmA, fb, sa, kcol, m0);
+            }
+            tma_load_2d_cg2(&tmB, fb, sa + uint32_t(Cfg::A_BYTES), kcol, n0);
+          } else {
+            mbar_expect_tx_a(fb, GATHER ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
+            if constexpr (!GATHER) {
+              if (p.a_im2col == 1) {
+                tma_load_im2col_4d_a(&tmA, fb, sa, cb, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
+              } else {
+                tma_load_2d_a(&tmA, fb, sa, kcol, m0);
+              }
+            }
+            tma_load_2d_a(&tmB, fb, sa + uint32_t(Cfg::A_BYTES), kcol, n0);
+          }
+          kcol += BLOCK_K;
+          // advance (tap, channel block) without divisions
+          cb += BLOCK_K;
+          if (cb == p.C) {
+            cb = 0;
+            if (++fs == p.S) {
+              fs = 0;
+              ++fr;
             }
           }
-          tma_load_2d(&tmB, &full_bar[s], sb, kb * BLOCK_K, n0);
-        }
-        // advance (tap, channel block) without divisions
-        if (++cb == p.cblocks) {
-          cb = 0;
-          ++tap;
-          if (++fs == p.S) {
-            fs = 0;
-            ++fr;
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1u;
           }
         }
-        __syncwarp();
       }
-      (void)tap;
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
-    int kc = 0, it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_ph = (it >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + uint32_t(acc * BLOCK_N);
-      for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
-        const int s = kc % STAGES;
-        const uint32_t ph = (kc / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+    // ------------------------------------------------------------ MMA issuer (one thread; pairs: the leader CTA's)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N, 128 * CG);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+      // descriptors differ between stages only in the 14-bit start-address field (smem < 256 KB: no carry out of it)
+      const uint64_t da0 = umma_smem_desc<Cfg::SWZ>(smem_u32(smem));
+      uint32_t s = 0, ph = 0, it = 0;
+      for (int tile = cl_id; tile < total_tiles; tile += cl_num, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait_a(tempty0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue(s) drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-          const uint64_t da = umma_smem_desc<Cfg::SWZ>(sa);
-          const uint64_t db = umma_smem_desc<Cfg::SWZ>(sb);
+        const uint32_t tmem_acc = tmem_base + acc * uint32_t(BLOCK_N);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait_a(full0 + 8u * s, ph);
+          tc_fence_after();
+          const uint64_t da = da0 + uint64_t(s * uint32_t(Cfg::STAGE_BYTES >> 4));
+          const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
+          // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
+          if constexpr (CG == 2) {
+            umma_f16_cg2(tmem_acc, da, db, idesc, kb ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
-            umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 1; k < BLOCK_K / 16; ++k)
+              umma_f16_cg2(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
+            umma_commit_cg2(empty0 + 8u * s);  // frees this stage in BOTH CTAs
+          } else {
+            umma_f16(tmem_acc, da, db, idesc, kb ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < BLOCK_K / 16; ++k) umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
+            umma_commit_a(empty0 + 8u * s);  // frees this smem stage once the MMAs above have read it
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
-          if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
-        __syncwarp();
+        if constexpr (CG == 2) umma_commit_cg2(tfull0 + 8u * acc);  // accumulators complete -> both epilogues
+        else umma_commit_a(tfull0 + 8u * acc);
       }
     }
   } else if (GATHER && warp >= 10) {
@@ -366,10 +408,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool use_res = p.res_mode != RES_NONE;
     int it = 0;
     uint32_t chunk_ctr = 0;                  // running chunk index: ring buffer = chunk_ctr % NBUF
-    float bias_next = (blockIdx.x < total_tiles && et < BLOCK_N) ? __ldg(p.bias + (blockIdx.x % p.n_tiles) * BLOCK_N + et) : 0.f;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    float bias_next = (cl_id < total_tiles && et < BLOCK_N) ? __ldg(p.bias + (cl_id % p.n_tiles) * BLOCK_N + et) : 0.f;
+    const uint32_t tempty_arrive0 = CG == 2 ? leader_addr(smem_u32(&tmem_empty_bar[0])) : smem_u32(&tmem_empty_bar[0]);
+    for (int tile = cl_id; tile < total_tiles; tile += cl_num, ++it) {
       const int n_tile = tile % p.n_tiles;
-      const int m0 = (tile / p.n_tiles) * Cfg::BLOCK_M;
+      const int m0 = ((tile / p.n_tiles) * CG + int(rank)) * Cfg::BLOCK_M;
       const int n0 = n_tile * BLOCK_N;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
@@ -378,12 +421,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* bias_s = s_bias[it & 1];
       if (et < BLOCK_N) bias_s[et] = bias_next;
       {  // bias of the next tile: in flight during this tile's epilogue
-        const int nt = tile + gridDim.x;
+        const int nt = tile + cl_num;
         if (nt < total_tiles && et < BLOCK_N) bias_next = __ldg(p.bias + (nt % p.n_tiles) * BLOCK_N + et);
       }
       if (p.tma_store && use_res && leader) {
         // residual tile -> ring buffers (one TMA load per chunk); the stores that last used them must have read them
-        bulk_wait_group_read<Cfg::NBUF - N_CHUNKS>();
+        bulk_wait_group_read<(Cfg::NBUF > N_CHUNKS ? Cfg::NBUF - N_CHUNKS : 0)>();  // (residual layers need NBUF >= N_CHUNKS: planner)
         for (int c = 0; c < live; ++c) {
           const uint32_t rb = (chunk_ctr + c) % Cfg::NBUF;
           mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
@@ -409,7 +452,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c == live - 1) {  // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster_a(tempty_arrive0 + 8u * acc);
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
           }
           uint8_t* buf = ring + bsel * Cfg::CHUNK_BYTES;
           if (use_res) {
@@ -442,7 +488,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (hsel >= live32) {  // nothing to read for this warp in this tile
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster_a(tempty_arrive0 + 8u * acc);
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
         }
 #pragma unroll 1
         for (int c = hsel; c < live32; c += 2) {
@@ -453,7 +502,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (c + 2 >= live32) {  // this warp's last chunk of the tile
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster_a(tempty_arrive0 + 8u * acc);
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
           }
           if (!row_ok) continue;
 
@@ -542,8 +594,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  if constexpr (CG == 2) cluster_sync_all();  // the peer may still be reading our shared memory / signalling our barriers
+  else __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
 }
 
 }  // namespace bp

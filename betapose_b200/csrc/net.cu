@@ -1,6 +1,7 @@
 // bp_net: ordered list of fused layer ops over NHWC fp16 tensors (C-ABI in include/betapose_b200.h).
 // Build time: BN folding (fp64), weight packing to [Cout_pad][R][S][Cin] fp16, buffer allocation, TMA
 // descriptor encoding for max_batch.  Run time: one kernel launch per op, no host sync, graph-capturable.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +20,8 @@ namespace {
 
 enum OpKind { OP_CONV, OP_MAXPOOL, OP_AVGPOOL, OP_SCALE_ADD_RELU, OP_PIXSHUF, OP_UPSAMPLE, OP_COPYC, OP_ADD };
 
+constexpr int kAvgSplitMax = 32;
+
 struct Tensor {
   void* ptr = nullptr;  // includes the channel offset
   int H = 0, W = 0, C = 0, pitch = 0, coff = 0;
@@ -34,6 +37,8 @@ struct Op {
   std::map<int, ConvPlan> plans;
   int pq = 0;     // output pixels per image (conv) for batch scaling
   int a = -1, b = -1, c = -1, dst = -1;  // tensor ids for aux ops
+  float* scratch = nullptr;              // OP_AVGPOOL: [max_batch][kAvgSplitMax][C] partial sums
+  unsigned* counters = nullptr;          // OP_AVGPOOL: [max_batch][C/256] arrival counters (zero between launches)
   double flops = 0, bytes = 0;  // per image
   std::string desc;
 };
@@ -290,7 +295,15 @@ int bp_net_global_avgpool(bp_net* n, int src) {
   const Tensor s = n->tensors[src];
   const int dst = new_tensor(n, 1, 1, s.C, false);
   if (dst < 0) return bp_fail(BP_ERR_CUDA, "cudaMalloc failed");
-  return push_aux(n, OP_AVGPOOL, src, -1, -1, dst, (double)s.H * s.W * s.C * 2, "global_avgpool");
+  const int cblks = (s.C + 255) / 256;
+  float* scratch = (float*)net_alloc_weights(n, (size_t)n->max_batch * kAvgSplitMax * s.C * sizeof(float));
+  unsigned* counters = (unsigned*)net_alloc_weights(n, (size_t)n->max_batch * cblks * sizeof(unsigned));
+  if (!scratch || !counters || cudaMemset(counters, 0, (size_t)n->max_batch * cblks * sizeof(unsigned)) != cudaSuccess)
+    return bp_fail(BP_ERR_CUDA, "bp_net_global_avgpool: cudaMalloc (scratch) failed");
+  const int r = push_aux(n, OP_AVGPOOL, src, -1, -1, dst, (double)s.H * s.W * s.C * 2, "global_avgpool");
+  n->ops.back().scratch = scratch;
+  n->ops.back().counters = counters;
+  return r;
 }
 
 int bp_net_scale_add_relu(bp_net* n, int y, int gates, int skip) {
@@ -403,8 +416,12 @@ int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream
       }
       case OP_AVGPOOL: {
         const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
-        dim3 grid((s.C + 255) / 256, batch);
-        global_avgpool_kernel<<<grid, 256, 0, st>>>(view_of(s), (__half*)d.ptr, d.pitch);
+        const int cblks = (s.C + 255) / 256;
+        // slices per image: enough blocks for ~4 per SM, at least 32 pixels per slice
+        int S = (4 * n->eng->num_sms + cblks * batch - 1) / (cblks * batch);
+        S = std::max(1, std::min(S, std::min(kAvgSplitMax, (s.H * s.W + 31) / 32)));
+        dim3 grid(cblks, batch, S);
+        global_avgpool_kernel<<<grid, 256, 0, st>>>(view_of(s), (__half*)d.ptr, d.pitch, op.scratch, op.counters, S);
         e = cudaGetLastError();
         break;
       }

@@ -93,6 +93,7 @@ struct Case {
   int force_bn = 0, force_st = 0;
   int iters = 0;  // >0: also time it
   int gather = 0;  // stem mode: C must be 4, K laid out (tap, 4)
+  int cg = 0;      // 0 = planner's choice, 1 = single CTA, 2 = CTA pairs (cta_group::2)
 };
 
 static int run_case(const Case& cs) {
@@ -145,7 +146,7 @@ static int run_case(const Case& cs) {
   d.R = cs.R; d.S = cs.S; d.stride = cs.stride; d.pad = cs.pad; d.act = cs.act;
   d.res = dres; d.res_pitch = cs.Cout; d.res_mode = cs.res_mode;
   d.out = dout; d.out_pitch = opitch; d.out_coff = cs.out_coff; d.out_f32 = cs.out_f32; d.store_mode = cs.store_mode;
-  d.force_block_n = cs.force_bn; d.force_stages = cs.force_st;
+  d.force_block_n = cs.force_bn; d.force_stages = cs.force_st; d.force_cg = cs.cg;
   d.gather = cs.gather;
   ConvPlan pl;
   std::string err;
@@ -220,8 +221,8 @@ static int run_case(const Case& cs) {
     CK(cudaEventElapsedTime(&t, e0, e1));
     ms = t / cs.iters;
   }
-  printf("[%-28s] bn=%3d bk=%2d st=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", cs.name,
-         pl.block_n, pl.block_k, pl.stages, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
+  printf("[%-28s] bn=%3d bk=%2d st=%d cg=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", cs.name,
+         pl.block_n, pl.block_k, pl.stages, pl.cg, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
   if (bad) printf(" first_bad: m=%ld co=%ld", first_bad / cs.Cout, first_bad % cs.Cout);
   if (ms > 0) printf("  %.3f ms  %.1f TFLOP/s", ms, pl.flops / ms * 1e-9);
   printf("\n");
@@ -364,27 +365,38 @@ int main(int argc, char** argv) {
   };
   for (auto& c : conv) fails += run_case(c);
 
+  // CTA pairs (cta_group::2): odd m-tile counts, several n-tiles, residual, fused stores, strided / padded layouts
+  std::vector<Case> pairs = {
+      {"pair gemm 256->256 1 mtile", 1, 8, 16, 256, 256, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair gemm 256->512 res", 2, 20, 16, 256, 512, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair gemm bn128 odd tiles", 3, 31, 29, 64, 128, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 128, 0, 0, 0, 2},
+      {"pair gemm many tiles", 40, 33, 31, 128, 512, 1, 1, 1, 0, ACT_LEAKY, RES_BEFORE_ACT, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair gemm coff+res pitch", 2, 26, 26, 128, 256, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 64, 128, 64, 256, 0, 0, 0, 2},
+      {"pair gemm upsample2 store", 2, 13, 13, 512, 256, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_UPSAMPLE2, 0, 0, 512, 0, 256, 0, 0, 0, 2},
+      {"pair 3x3 s1 C128->256 52x52", 3, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair 3x3 s2 C128->256 26x26", 2, 26, 26, 128, 256, 3, 3, 2, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair 3x3 s1 C64->128 13x13", 5, 13, 13, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 128, 0, 0, 0, 2},
+      {"pair 3x3 pixshuf C512->1024", 1, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair 3x3 x_pitch 768", 1, 26, 26, 512, 256, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 256, 0, 0, 256, 0, 0, 0, 2},
+      {"pair 1x1 s2 C256->512 40x32", 2, 40, 32, 256, 512, 1, 1, 2, 0, ACT_NONE, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+      {"pair 3x3 C512->1024 res 13", 2, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 256, 0, 0, 0, 2},
+  };
+  for (auto& c : pairs) fails += run_case(c);
+
   if (!quick && fails == 0) {
     printf("---- timing (batch 64 production shapes) ----\n");
     std::vector<Case> perf = {
-        {"Y 3x3 128->256 @52 B64", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 3x3 128->256 @52 bn128", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 3, 10},
-        {"Y 3x3 128->256 @52 bn256s2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 2, 10},
-        {"Y 1x1 256->128 @52 B64", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 3x3 256->512 @26 B64", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 3x3 512->1024 @13 B64", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 3x3 512->1024 @13 bn128", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 6, 10},
-        {"Y 3x3 32->64 s2 @416", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
-        {"K 3x3 256->256 @20x16", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"K 1x1 256->1024 @20x16", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_NONE, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"K 1x1 1024->256 @20x16", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"K 1x1 64->256 @80x64", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_NONE, 0, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"K 1x1 64->256 @80x64 +res", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 3x3 128->256 @52 +res", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 3x3 64->128 @104 +res", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 5},
-        {"Y 1x1 64->32 @208", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
-        {"K 1x1 256->1024 +res", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"K 3x3 512->1024 ps2", 64, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 0, 0, 10},
+        // pure GEMMs with the FLOPs of the 3x3 layers (A through 2-D tiled TMA instead of im2col)
+        {"G 1x1 1152->256 M173056 cg1", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"G 1x1 1152->256 M173056 cg2", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"G 1x1 2304->512 M43264 cg1", 64, 26, 26, 2304, 512, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"G 1x1 2304->512 M43264 cg2", 64, 26, 26, 2304, 512, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"G 1x1 1152->256 cg2 bn128", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 2},
+        {"G 1x1 1152->256 cg1 bn128", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1},
+        {"G 1x1 1152->256 cg1 bn64", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 10, 0, 1},
+        {"Y 3x3 128->256 @52 cg1", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"Y 3x3 128->256 @52 cg2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 3x3 256->512 @26 cg2 st4", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
     };
     for (auto& c : perf) fails += run_case(c);
   }
