@@ -24,7 +24,8 @@ EXPORTS = (
 ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 RES_NONE, RES_AFTER_ACT, RES_BEFORE_ACT = 0, 1, 2
 STORE_PLAIN, STORE_UPSAMPLE2, STORE_PIXSHUF2 = 0, 1, 2
-IN_U8X4, IN_F16X4 = 0, 1
+IN_RAW255, IN_F16 = 0, 1  # network-input kinds (include/betapose_b200.h)
+IN_PAD_LEFT, IN_PAD_COLS = 3, 8  # network-input buffers are fp16 [N, H, W + IN_PAD_COLS, 8], data from column IN_PAD_LEFT
 
 
 class ConvSpec(C.Structure):

@@ -68,7 +68,7 @@ class Darknet:
             raise _lib.BetaposeError("Darknet: load_weights() first")
         if self._net is None or self._net.max_batch < batch:
             self.max_batch = max(self.max_batch, batch)
-            self._net = _net.Net(self.max_batch, self.reso, self.reso, _lib.IN_F16X4)
+            self._net = _net.Net(self.max_batch, self.reso, self.reso, _lib.IN_F16)
             self._heads = _net.build_darknet(self._net, self.blocks, self._params)
 
     def __call__(self, x: torch.Tensor, CUDA: bool = True) -> torch.Tensor:
@@ -77,8 +77,7 @@ class Darknet:
         assert tuple(x.shape[1:]) == (3, self.reso, self.reso), x.shape
         self._build(B)
         inp = self._net.input(B)
-        inp[..., :3] = x.to(dev, non_blocking=True).permute(0, 2, 3, 1).to(torch.float16)
-        inp[..., 3] = 0
+        inp.copy_(x.to(dev, non_blocking=True).permute(0, 2, 3, 1))  # data pixels R,G,B of the padded fp16 input buffer
         self._net.forward(B)
         heads = [self._net.tensor(h["tensor"], B) for h in self._heads]
         out = stages.yolo_decode_argmax(heads, [h["anchors"] for h in self._heads], B, reso=self.reso, conf=opt.confidence,
@@ -152,7 +151,7 @@ class InferenNet_fast:
     def _build(self, n):
         if self._net is None or self._net.max_batch < n:
             self.max_batch = max(self.max_batch, n)
-            self._net = _net.Net(self.max_batch, opt.inputResH, opt.inputResW, _lib.IN_F16X4)
+            self._net = _net.Net(self.max_batch, opt.inputResH, opt.inputResW, _lib.IN_F16)
             self._hm = _net.build_fastpose(self._net, self.sd, self.n_maps)
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
@@ -160,8 +159,7 @@ class InferenNet_fast:
         n = int(x.shape[0])
         self._build(n)
         inp = self._net.input(n)
-        inp[..., :3] = x.to(dev, non_blocking=True).permute(0, 2, 3, 1).to(torch.float16)
-        inp[..., 3] = 0
+        inp.copy_(x.to(dev, non_blocking=True).permute(0, 2, 3, 1))  # data pixels R,G,B of the padded fp16 input buffer
         self._net.forward(n)
         return self._net.tensor(self._hm, n).permute(0, 3, 1, 2).contiguous().to(x.device)
 

@@ -1,5 +1,5 @@
 // Host-side planning + launch of one conv_umma_kernel instance: picks the tile configuration, encodes the
-// two TMA descriptors once (buffers are owned by the engine, so addresses are stable) and replays the launch.
+// TMA descriptors once (buffers are owned by the engine, so addresses are stable) and replays the launch.
 #pragma once
 #include <algorithm>
 #include <string>
@@ -13,12 +13,14 @@ struct ConvDesc {
   // input activation, NHWC fp16 (for matrix mode: N=1, H=1, W=rows, C=K)
   const __half* x = nullptr;
   int N = 0, H = 0, W = 0, C = 0, x_pitch = 0;
+  long x_row_pitch = 0, x_img_pitch = 0;  // elements between input rows / images, 0 = dense (W * x_pitch, H * row)
   // weights [Cout_pad][R][S][C] fp16 (row pitch w_pitch elements, >= R*S*C, multiple of 8), bias [Cout_pad] fp32
   const __half* w = nullptr;
   const float* bias = nullptr;
   int w_pitch = 0;
   int Cout = 0, Cout_pad = 0;
   int R = 1, S = 1, stride = 1, pad = 0;
+  int pad_w = -1;  // horizontal padding, -1 = same as `pad` (the packed stem convolutions use 0, see net.cu)
   int act = ACT_NONE;
   const __half* res = nullptr;
   int res_pitch = 0, res_mode = RES_NONE;
@@ -26,10 +28,9 @@ struct ConvDesc {
   int out_pitch = 0, out_coff = 0, out_f32 = 0, store_mode = STORE_PLAIN;
   int force_block_n = 0;  // 0 = heuristic
   int force_cg = 0;       // 0 = heuristic, 1 = single CTA, 2 = CTA pairs (cta_group::2)
-  int force_stages = 0;   // kept for the harness; the stage count now follows from the tile configuration
+  int force_stages = 0;   // kept for the harness; the stage count follows from the tile configuration
   int num_sms = 148;
-  // gather mode (stem): x is [N, H, W, 4] uint8 or fp16, C = 4, weights packed [Cout_pad][taps_pad16 * 4]
-  int gather = 0, gather_u8 = 0;
+  double real_k = 0;      // reduction length that counts as work (0 = R*S*C); the stems pad K with zero weights
 };
 
 struct ConvPlan {
@@ -43,12 +44,12 @@ struct ConvPlan {
   double flops = 0;
 };
 
-template <int BN, int BK, int ST, bool GATHER = false, int CG = 1, int NB = 4>
+template <int BN, int BK, int ST, int CG = 1, int NB = 4>
 inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   using Cfg = ConvCfg<BN, BK, ST, CG, NB>;
   static bool attr_done = false;  // per-instantiation; set once per process (single device per process)
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, GATHER, CG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -66,23 +67,18 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, GATHER, CG, NB>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
   } else {
-    conv_umma_kernel<BN, BK, ST, GATHER, CG, NB><<<pl.grid, Cfg::THREADS + (GATHER ? 128 : 0), Cfg::SMEM_BYTES, st>>>(
-        pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+    conv_umma_kernel<BN, BK, ST, CG, NB><<<pl.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pl.tmOut, pl.tmRes,
+                                                                                       pl.args);
     return cudaGetLastError();
   }
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
-  if (pl.args.a_im2col == 2) {
-    if (pl.block_n == 32) return launch_cfg<32, 64, 6, true>(pl, st);
-    if (pl.block_n == 64) return launch_cfg<64, 64, 6, true>(pl, st);
-    return cudaErrorInvalidConfiguration;
-  }
   if (pl.cg == 2) {
-    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 4, false, 2>(pl, st);
-    if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, false, 2>(pl, st);
+    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 4, 2>(pl, st);
+    if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, 2>(pl, st);
     return cudaErrorInvalidConfiguration;
   }
 #define BP_CASE(BN, BK, ST) \
@@ -98,96 +94,83 @@ inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
 }
 
 inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::string* err) {
+  const int pad_w = d.pad_w < 0 ? d.pad : d.pad_w;
   const int P = (d.H + 2 * d.pad - d.R) / d.stride + 1;
-  const int Q = (d.W + 2 * d.pad - d.S) / d.stride + 1;
+  const int Q = (d.W + 2 * pad_w - d.S) / d.stride + 1;
   const int M = d.N * P * Q;
-  const bool matrix = !d.gather && (d.R == 1 && d.S == 1 && d.stride == 1 && d.pad == 0);
-  // matrix mode may have a ragged K (explicit im2col of the 3-channel stems): TMA zero-fills the tail
-  const int block_k = d.gather ? 64 : (matrix ? (d.C >= 64 ? 64 : 32) : ((d.C % 64 == 0) ? 64 : 32));
-  if (!matrix && !d.gather && d.C % 32 != 0) {
+  const bool matrix = d.R == 1 && d.S == 1 && d.stride == 1 && d.pad == 0 && pad_w == 0 && d.x_row_pitch == 0;
+  // matrix mode may have a ragged K: TMA zero-fills the tail
+  const int block_k = matrix ? (d.C >= 64 ? 64 : 32) : ((d.C % 64 == 0) ? 64 : 32);
+  if (!matrix && d.C % 32 != 0) {
     if (err) *err = "im2col conv needs Cin % 32 == 0";
     return false;
   }
+  const int K = d.R * d.S * d.C;
+  const int num_kb = (K + block_k - 1) / block_k;
+  const int m_tiles = (M + 127) / 128;
+
   // Tile configuration by a small cost model fitted to B200 measurements (tests/harness/conv_harness.cu, batch 64):
   // a persistent grid walks the tiles round-robin, so a launch takes ceil(tiles / CTAs) rounds of one tile each, and a
   // k-block costs ~500 + (BLOCK_K / 16) * bn / 2 cycles (bn = 64 / 128 / 256: 628 / 758 / 1000-1040 measured; the
   // second term is the tensor-pipe time, the first does not shrink with the tile).  Wider tiles therefore win unless
   // they leave most of the machine idle.  CTA pairs (cta_group::2, M = 256) measured within +-5 % of single CTAs on
   // every production shape, so they are only used when forced (d.force_cg = 2).
-  int bn = d.force_block_n, cg = d.force_cg;
+  int bn = 0, cg = 0;
   {
     int cap = 32;
     while (cap < d.Cout && cap < 256) cap *= 2;
-    if (block_k == 32 || d.gather) cap = std::min(cap, 64);
-    const long m_tiles_ = (M + 127) / 128;
-    const int K_ = d.gather ? (d.R * d.S + 15) / 16 * 64 : d.R * d.S * d.C;
-    const long nkb = (K_ + block_k - 1) / block_k;
+    if (block_k == 32) cap = std::min(cap, 64);
     double best = 0;
-    int best_bn = 0, best_cg = 0;
     for (int c = cap; c >= 32; c /= 2) {
       if (d.force_block_n && c != d.force_block_n) continue;
       if (d.Cout_pad % c) continue;
-      for (int g = 1; g <= 2; ++g) {
-        if (g != (d.force_cg ? d.force_cg : 1)) continue;
-        if (g == 2 && (block_k != 64 || c < 128 || d.gather || d.num_sms < 2)) continue;
-        const long tiles = ((m_tiles_ + g - 1) / g) * ((d.Cout + c - 1) / c);
-        const long units = g == 2 ? d.num_sms / 2 : d.num_sms;
-        const long rounds = (tiles + units - 1) / units;
-        const double per_kb = 500.0 + (block_k / 16) * (c / 2.0);
-        const double cost = rounds * (nkb * per_kb + 400.0 + 200.0 * ((c + 63) / 64));
-        if (!best_bn || cost < 0.97 * best) {  // later candidates (narrower / paired) must win by 3 %
-          best_bn = c;
-          best_cg = g;
-          best = cost;
-        }
+      const int g = d.force_cg ? d.force_cg : 1;
+      if (g == 2 && (block_k != 64 || c < 128 || d.num_sms < 2)) continue;
+      const long tiles = (long)((m_tiles + g - 1) / g) * ((d.Cout + c - 1) / c);
+      const long units = g == 2 ? d.num_sms / 2 : d.num_sms;
+      const long rounds = (tiles + units - 1) / units;
+      const double per_kb = 500.0 + (block_k / 16) * (c / 2.0);
+      const double cost = rounds * (num_kb * per_kb + 400.0 + 200.0 * ((c + 63) / 64));
+      if (!bn || cost < 0.97 * best) {  // a narrower tile must win by 3 %: wider tiles read A fewer times
+        bn = c;
+        cg = g;
+        best = cost;
       }
     }
-    if (!best_bn) {
+    if (!bn) {
       if (err) *err = "no tile configuration fits (forced block_n / cg?)";
       return false;
     }
-    bn = best_bn;
-    cg = best_cg;
   }
   if (d.Cout_pad % bn != 0) {
     if (err) *err = "Cout_pad must be a multiple of BLOCK_N";
     return false;
   }
   const int st = cg == 2 ? (bn == 256 ? 4 : 6) : (bn == 256 ? 3 : (bn == 128 ? 4 : (block_k == 64 ? 6 : 8)));
-  const int K = d.gather ? (d.R * d.S + 15) / 16 * 64 : d.R * d.S * d.C;  // gather: 16 taps x 4 channels per k-block
-  const int num_kb = (K + block_k - 1) / block_k;
 
   pl->block_n = bn;
   pl->block_k = block_k;
   pl->stages = st;
+  pl->cg = cg;
   pl->P = P;
   pl->Q = Q;
-  const int n_tiles = d.Cout_pad / bn;
   // tiles whose channels are all padding are never launched
   const int n_tiles_live = (d.Cout + bn - 1) / bn;
-  const int m_tiles = (M + 127) / 128;
-  pl->cg = cg;
   // persistent: one CTA per SM (pairs: one cluster of 2 per TPC)
   pl->grid = cg == 2 ? 2 * std::min(((m_tiles + 1) / 2) * n_tiles_live, d.num_sms / 2) : std::min(m_tiles * n_tiles_live, d.num_sms);
-  (void)n_tiles;
-  pl->flops = 2.0 * M * (double)d.Cout * (d.gather ? d.R * d.S * 3 : K);
+  pl->flops = 2.0 * M * (double)d.Cout * (d.real_k > 0 ? d.real_k : (double)K);
 
   ConvArgs& a = pl->args;
   a.M = M;
   a.n_tiles = n_tiles_live;
   a.m_tiles = m_tiles;
   a.num_kb = num_kb;
-  a.a_im2col = d.gather ? 2 : (matrix ? 0 : 1);
-  a.gx = d.x;
-  a.gH = d.H;
-  a.gW = d.W;
-  a.g_u8 = d.gather_u8;
-  a.R = d.R;
+  a.a_im2col = matrix ? 0 : 1;
   a.P = P;
   a.Q = Q;
   a.stride = d.stride;
   a.pad = d.pad;
-  a.pad_w = d.pad;
+  a.pad_w = pad_w;
   a.C = d.C;
   a.S = d.S;
   a.cblocks = d.C / block_k;
@@ -207,22 +190,16 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.res = d.res;
   a.out = d.out;
 
-  if (d.gather) {
-    if (bn > 64) {
-      if (err) *err = "gather (stem) convolutions support Cout <= 64";
-      return false;
-    }
-  } else if (matrix) {
+  if (matrix) {
     if (!make_tmap_2d(api, &pl->tmA, d.x, (uint64_t)M, (uint64_t)d.C, (uint64_t)d.x_pitch, 128, block_k, err))
       return false;
   } else {
-    if (!make_tmap_im2col(api, &pl->tmA, d.x, d.N, d.H, d.W, d.C, d.x_pitch, d.R, d.S, d.stride, d.pad, block_k,
-                          err))
+    if (!make_tmap_im2col(api, &pl->tmA, d.x, d.N, d.H, d.W, d.C, d.x_pitch, d.R, d.S, d.stride, d.pad, pad_w, block_k, err,
+                          d.x_row_pitch, d.x_img_pitch))
       return false;
   }
   if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn / cg, block_k, err))
     return false;
-  if (d.gather) pl->tmA = pl->tmB;
   pl->tmOut = pl->tmB;  // placeholders keep the kernel parameters well-formed when the TMA epilogue is off
   pl->tmRes = pl->tmB;
   if (a.tma_store) {

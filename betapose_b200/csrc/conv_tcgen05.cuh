@@ -31,7 +31,7 @@ struct ConvArgs {
   int n_tiles;   // live N tiles (ceil(Cout / BLOCK_N))
   int m_tiles;   // ceil(M / 128)
   int num_kb;    // K / BLOCK_K
-  int a_im2col;  // 1: A through the im2col tensor map over NHWC; 0: A is a row-major [M, K] matrix; 2: gathered (stem)
+  int a_im2col;  // 1: A through the im2col tensor map over NHWC; 0: A is a row-major [M, K] matrix
   int P, Q;      // output height / width
   int stride, pad;  // pad = vertical padding
   int pad_w;        // horizontal padding (== pad except for the packed stem convolutions)
@@ -47,10 +47,6 @@ struct ConvArgs {
   int out_pitch;  // elements between consecutive output pixels
   int out_coff;   // channel offset inside the output pixel
   int res_pitch;
-  // gather mode (3-channel stem convolutions): A rows are built in shared memory by four extra warps straight from
-  // the 4-wide input pixels, K ordered (tap, c4), 16 taps per 64-wide k-block
-  const void* gx;      // input [N, gH, gW, 4]: uint8 (RGBX, raw 0..255: the 1/255 is folded into the weights) or fp16
-  int gH, gW, g_u8, R;
   const float* bias;   // [n_tiles * BLOCK_N], zero padded
   const __half* res;   // residual, same pixel order as the output, res_pitch elements per pixel
   void* out;
@@ -160,13 +156,13 @@ __device__ __forceinline__ void epi_dispatch(int act, int res_mode, const uint32
 #undef BP_EPI
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, bool GATHER = false, int CG = 1, int NB = 4>
-__global__ void __launch_bounds__(GATHER ? 448 : 320, 1)
+template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4>
+__global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB>;
-  static_assert(CG == 1 || (CG == 2 && !GATHER && BLOCK_N >= 64), "pairs: plain convolutions with BLOCK_N >= 64");
+  static_assert(CG == 1 || (CG == 2 && BLOCK_N >= 64), "pairs need BLOCK_N >= 64");
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
   constexpr int CHUNK = Cfg::CHUNK;
@@ -202,7 +198,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], GATHER ? 129 : 1);  // gather: + one arrive per A-row writer
+      mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
 #pragma unroll
@@ -260,13 +256,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tma_load_2d_cg2(&tmB, fb, sa + uint32_t(Cfg::A_BYTES), kcol, n0);
           } else {
-            mbar_expect_tx_a(fb, GATHER ? Cfg::B_BYTES : Cfg::STAGE_BYTES);
-            if constexpr (!GATHER) {
-              if (p.a_im2col == 1) {
-                tma_load_im2col_4d_a(&tmA, fb, sa, cb, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
-              } else {
-                tma_load_2d_a(&tmA, fb, sa, kcol, m0);
-              }
+            mbar_expect_tx_a(fb, Cfg::STAGE_BYTES);
+            if (p.a_im2col == 1) {
+              tma_load_im2col_4d_a(&tmA, fb, sa, cb, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
+            } else {
+              tma_load_2d_a(&tmA, fb, sa, kcol, m0);
             }
             tma_load_2d_a(&tmB, fb, sa + uint32_t(Cfg::A_BYTES), kcol, n0);
           }
@@ -326,75 +320,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if constexpr (CG == 2) umma_commit_cg2(tfull0 + 8u * acc);  // accumulators complete -> both epilogues
         else umma_commit_a(tfull0 + 8u * acc);
-      }
-    }
-  } else if (GATHER && warp >= 10) {
-    // ------------------------------------------------------------ A gather (warps 10..13, one tile row per thread)
-    if constexpr (GATHER) {
-      static_assert(BLOCK_K == 64, "gather mode uses 64-wide k-blocks (16 taps x 4 channels)");
-      const int gt = threadIdx.x - 320;
-      const int taps = p.R * p.S;
-      const int pq = p.P * p.Q;
-      int kc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_raw = (tile / p.n_tiles) * Cfg::BLOCK_M + gt;
-        const bool valid = m_raw < p.M;
-        const int m = valid ? m_raw : p.M - 1;  // clamped so that every load below stays inside the input
-        const int img = m / pq;
-        const int rem = m - img * pq;
-        const int op = rem / p.Q;
-        const int oq = rem - op * p.Q;
-        const int h0 = op * p.stride - p.pad, w0 = oq * p.stride - p.pad;
-        const size_t img_base = (size_t)img * p.gH * p.gW;
-        int fr = 0, fs = 0, tap = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
-          const int s = kc % STAGES;
-          const uint32_t ph = (kc / STAGES) & 1;
-          // all 16 tap loads of this k-block are issued back to back (clamped addresses, masked afterwards) so their
-          // latencies overlap; only then wait for the smem slot
-          uint32_t okmask = 0;
-          uint2 raw[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int h = h0 + fr, w = w0 + fs;
-            const bool ok = valid && tap < taps && h >= 0 && h < p.gH && w >= 0 && w < p.gW;
-            okmask |= (ok ? 1u : 0u) << e;
-            const int hc = min(max(h, 0), p.gH - 1), wc = min(max(w, 0), p.gW - 1);
-            const size_t pix = img_base + (size_t)hc * p.gW + wc;
-            if (p.g_u8) {
-              raw[e].x = __ldg(reinterpret_cast<const uint32_t*>(p.gx) + pix);
-              raw[e].y = 0u;
-            } else {
-              raw[e] = __ldg(reinterpret_cast<const uint2*>(p.gx) + pix);
-            }
-            ++tap;
-            if (++fs == p.S) {
-              fs = 0;
-              ++fr;
-            }
-          }
-          if (p.g_u8) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const uint32_t u = raw[e].x;
-              const __half2 lo = __floats2half2_rn((float)(u & 0xffu), (float)((u >> 8) & 0xffu));
-              const __half2 hi = __floats2half2_rn((float)((u >> 16) & 0xffu), 0.f);
-              raw[e].x = *reinterpret_cast<const uint32_t*>(&lo);
-              raw[e].y = *reinterpret_cast<const uint32_t*>(&hi);
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (!((okmask >> e) & 1u)) raw[e] = make_uint2(0u, 0u);
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* arow = smem + s * Cfg::STAGE_BYTES;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)  // 16-byte unit j = taps 2j, 2j+1 of this k-block
-            *reinterpret_cast<uint4*>(arow + swz_off<128>(gt, j)) =
-                make_uint4(raw[2 * j].x, raw[2 * j].y, raw[2 * j + 1].x, raw[2 * j + 1].y);
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          mbar_arrive(&full_bar[s]);
-        }
       }
     }
   } else {

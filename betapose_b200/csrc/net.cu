@@ -27,6 +27,7 @@ struct Tensor {
   int H = 0, W = 0, C = 0, pitch = 0, coff = 0;
   bool f32 = false;
   int in_kind = -1;  // >= 0 for the network input
+  int row_px = 0;    // network input only: pixels per buffer row (W + BP_IN_PAD_COLS); data starts at column BP_IN_PAD_LEFT
 };
 
 struct Op {
@@ -100,7 +101,7 @@ extern "C" {
 
 int bp_net_create(bp_engine* e, int max_batch, int in_h, int in_w, int in_kind, bp_net* share, bp_net** out) {
   if (!e || !out || max_batch <= 0) return bp_fail(BP_ERR_INVALID, "bp_net_create: bad arguments");
-  if (in_kind != BP_IN_U8X4 && in_kind != BP_IN_F16X4) return bp_fail(BP_ERR_INVALID, "bp_net_create: in_kind");
+  if (in_kind != BP_IN_RAW255 && in_kind != BP_IN_F16) return bp_fail(BP_ERR_INVALID, "bp_net_create: in_kind");
   if (share && share->max_batch < max_batch) return bp_fail(BP_ERR_INVALID, "bp_net_create: shared net is smaller");
   cudaSetDevice(e->device);
   bp_net* n = new bp_net();
@@ -109,9 +110,11 @@ int bp_net_create(bp_engine* e, int max_batch, int in_h, int in_w, int in_kind, 
   n->max_batch = max_batch;
   n->in_kind = in_kind;
   Tensor t;
-  t.H = in_h; t.W = in_w; t.C = 3; t.pitch = 4; t.in_kind = in_kind;
-  const size_t esz = in_kind == BP_IN_U8X4 ? 1 : 2;
-  t.ptr = net_alloc_act(n, (size_t)max_batch * in_h * in_w * 4 * esz + 256);
+  // network input: fp16 [N, H, W + BP_IN_PAD_COLS, 8]; the pad columns and channels 3..7 stay zero for ever (the
+  // buffer is zeroed at allocation and the stage kernels write only data pixels, channels 3..7 as zeros), which is
+  // what lets the first convolution read whole filter rows as one "virtual pixel" (see bp_net_conv)
+  t.H = in_h; t.W = in_w; t.C = 3; t.pitch = 8; t.in_kind = in_kind; t.row_px = in_w + BP_IN_PAD_COLS;
+  t.ptr = net_alloc_act(n, (size_t)max_batch * in_h * t.row_px * 8 * 2 + 256);
   if (!t.ptr) {
     delete n;
     return bp_fail(BP_ERR_CUDA, "bp_net_create: cudaMalloc failed");
@@ -161,17 +164,22 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (s->store_mode != BP_STORE_PLAIN && Cout % 8) return bp_fail(BP_ERR_UNSUPPORTED, "fused stores need Cout % 8 == 0");
 
   // ---- fold BN (fp64) and pack weights [Cout_pad][R][S][Cin] fp16
-  // stem (3-channel network input): K is laid out (tap, 4 channels) with 16 taps per 64-wide k-block, the 4th
-  // channel and the taps beyond k*k are zero; uint8 inputs are fed as raw 0..255 and ToTensor's 1/255
-  // (dataloader.py:94-99) is folded into the weights
-  const int K = stem ? (k * k + 15) / 16 * 64 : k * k * Cin;
+  // Stem (3-channel network input, stored [N, H, W + 8, 8] fp16 with zero pad columns): one filter ROW of k pixels x 8
+  // channels is contiguous in memory, so the convolution is run as a k x 1 convolution over "virtual pixels" of
+  // Cv = 32 (k <= 4) or 64 (k <= 8) channels = 4 or 8 neighbouring real pixels, whose pixel stride (16 B) is smaller than
+  // their extent (overlapping TMA im2col map).  K = k * Cv, ordered (row, pixel-in-row, 8 channels); entries beyond the
+  // k real pixels / 3 real channels are zero weights.  For RAW255 inputs ToTensor's 1/255 (dataloader.py:94-99) is
+  // folded into the weights, so the 0..255 pixel values are exact in fp16.
+  const int Cv = stem ? (k * 8 <= 32 ? 32 : 64) : 0;
+  if (stem && (k > 8 || s->pad > BP_IN_PAD_LEFT || (Q - 1) * s->stride + Cv / 8 > src.row_px - (BP_IN_PAD_LEFT - s->pad)))
+    return bp_fail(BP_ERR_UNSUPPORTED, "bp_net_conv: stem convolution geometry (k <= 8, pad <= 3)");
+  const int K = stem ? k * Cv : k * k * Cin;
   const int wpitch = (K + 7) / 8 * 8;
   const int Cout_pad = (Cout + 255) / 256 * 256;
-  if (stem && Cout > 64) return bp_fail(BP_ERR_UNSUPPORTED, "bp_net_conv: a stem convolution supports at most 64 output channels");
   std::vector<__half> hw((size_t)Cout_pad * wpitch, __float2half(0.f));
   std::vector<float> hb(Cout_pad, 0.f);
   const int c4 = Cout / 4;
-  const double in_scale = (stem && src.in_kind == BP_IN_U8X4) ? 1.0 / 255.0 : 1.0;
+  const double in_scale = (stem && src.in_kind == BP_IN_RAW255) ? 1.0 / 255.0 : 1.0;
   for (int o = 0; o < Cout; ++o) {
     double scale = 1.0, shift = s->bias ? (double)s->bias[o] : 0.0;
     if (s->bn_gamma) {
@@ -184,11 +192,12 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
     hb[row] = (float)shift;
     const float* wsrc = s->weight + (size_t)o * Cin * k * k;
     __half* wdst = hw.data() + (size_t)row * wpitch;
-    const int cstride = stem ? 4 : Cin;
     for (int ci = 0; ci < Cin; ++ci)
       for (int r = 0; r < k; ++r)
-        for (int q = 0; q < k; ++q)
-          wdst[(r * k + q) * cstride + ci] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale * in_scale));
+        for (int q = 0; q < k; ++q) {
+          const size_t kidx = stem ? (size_t)r * Cv + q * 8 + ci : (size_t)(r * k + q) * Cin + ci;
+          wdst[kidx] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale * in_scale));
+        }
   }
   __half* dw = (__half*)net_alloc_weights(n, hw.size() * 2);
   float* db = (float*)net_alloc_weights(n, hb.size() * 4);
@@ -216,10 +225,12 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
 
   ConvDesc d;
   if (stem) {
-    d.x = (const __half*)src.ptr; d.N = n->max_batch; d.H = src.H; d.W = src.W; d.C = 4; d.x_pitch = 4;
-    d.R = k; d.S = k; d.stride = s->stride; d.pad = s->pad;
-    d.gather = 1;
-    d.gather_u8 = src.in_kind == BP_IN_U8X4 ? 1 : 0;
+    // virtual pixel w' = buffer column (BP_IN_PAD_LEFT - pad) + w'; the window of output column q starts at w' = q*stride
+    d.x = (const __half*)src.ptr + (size_t)(BP_IN_PAD_LEFT - s->pad) * 8;
+    d.N = n->max_batch; d.H = src.H; d.W = (Q - 1) * s->stride + 1; d.C = Cv; d.x_pitch = 8;
+    d.x_row_pitch = (long)src.row_px * 8; d.x_img_pitch = (long)src.H * src.row_px * 8;
+    d.R = k; d.S = 1; d.stride = s->stride; d.pad = s->pad; d.pad_w = 0;
+    d.real_k = (double)k * k * Cin;
   } else {
     d.x = (const __half*)src.ptr; d.N = n->max_batch; d.H = src.H; d.W = src.W; d.C = Cin; d.x_pitch = src.pitch;
     d.R = k; d.S = k; d.stride = s->stride; d.pad = s->pad;
@@ -249,7 +260,7 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (!conv_plan_build(n->eng->tmap, &plan0, d, &err)) return bp_fail(BP_ERR_CUDA, ("bp_net_conv: " + err).c_str());
   op.dst = dst;
   op.flops = 2.0 * P * Q * (double)Cout * (k * k * Cin);
-  op.bytes = (stem ? (double)src.H * src.W * 4 * (src.in_kind == BP_IN_U8X4 ? 1 : 2) : (double)src.H * src.W * Cin * 2) +
+  op.bytes = (stem ? (double)src.H * src.row_px * 16 : (double)src.H * src.W * Cin * 2) +
              (double)K * Cout * 2 / n->max_batch +
              (double)P * Q * Cout * (s->out_f32 ? 4 : 2) * (s->store_mode == BP_STORE_UPSAMPLE2 ? 4 : 1) +
              (s->res >= 0 ? (double)P * Q * Cout * 2 : 0.0);
@@ -362,6 +373,8 @@ int bp_net_tensor_info(bp_net* n, int tensor, int* dims, void** ptr) {
   const Tensor& t = n->tensors[tensor];
   if (dims) {
     dims[0] = t.H; dims[1] = t.W; dims[2] = t.C; dims[3] = t.pitch; dims[4] = t.f32 ? 1 : 0; dims[5] = t.coff;
+    dims[6] = t.row_px ? t.row_px : t.W;      // pixels per buffer row
+    dims[7] = t.row_px ? BP_IN_PAD_LEFT : 0;  // first data column
   }
   if (ptr) *ptr = t.ptr;
   return BP_OK;

@@ -102,9 +102,10 @@ __global__ void resize_h_kernel(const uint8_t* __restrict__ in, int rows, int W,
   dst[2] = (uint8_t)clip8(s2);
 }
 
-// vertical pass: [B,H,ow,3] u8 -> [B,oh,ow,4] u8 (RGBX) and/or fp32 [B,3,oh,ow] (value/255)
+// vertical pass: [B,H,ow,3] u8 -> network input fp16 [B,oh,ow+BP_IN_PAD_COLS,8] (raw 0..255, exact in fp16) and/or
+// fp32 [B,3,oh,ow] (value/255)
 __global__ void resize_v_kernel(const uint8_t* __restrict__ in, int B, int H, int oh, int ow, const int32_t* __restrict__ bounds,
-                                const int32_t* __restrict__ kk, int ksize, uint8_t* __restrict__ out_u8x4,
+                                const int32_t* __restrict__ kk, int ksize, __half* __restrict__ out_net,
                                 float* __restrict__ out_f32) {
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (idx >= (long)B * oh * ow) return;
@@ -123,7 +124,13 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ in, int B, int H, in
     s2 += p[2] * c;
   }
   const int r = clip8(s0), g = clip8(s1), bl = clip8(s2);
-  if (out_u8x4) reinterpret_cast<uchar4*>(out_u8x4)[idx] = make_uchar4((unsigned char)r, (unsigned char)g, (unsigned char)bl, 0);
+  if (out_net) {
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    __half2* h = reinterpret_cast<__half2*>(&pk);
+    h[0] = __floats2half2_rn((float)r, (float)g);
+    h[1] = __floats2half2_rn((float)bl, 0.f);
+    reinterpret_cast<uint4*>(out_net)[((long)b * oh + yy) * (ow + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + xx] = pk;
+  }
   if (out_f32) {
     const long plane = (long)oh * ow;
     float* o = out_f32 + (long)b * 3 * plane + (long)yy * ow + xx;
@@ -136,8 +143,8 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ in, int B, int H, in
 }  // namespace
 
 extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int H, int W, int oh, int ow,
-                                 uint8_t* out_u8x4, float* out_f32_chw, void* stream) {
-  if (!e || !frames || B <= 0 || (!out_u8x4 && !out_f32_chw)) return bp_fail(BP_ERR_INVALID, "bp_resize_bicubic: bad arguments");
+                                 void* out_net, float* out_f32_chw, void* stream) {
+  if (!e || !frames || B <= 0 || (!out_net && !out_f32_chw)) return bp_fail(BP_ERR_INVALID, "bp_resize_bicubic: bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const ResizeTables* th = get_tables(e, W, ow);
   const ResizeTables* tv = get_tables(e, H, oh);
@@ -158,7 +165,7 @@ extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int
                                                               e->resize_tmp);
   const long n2 = (long)B * oh * ow;
   resize_v_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(e->resize_tmp, B, H, oh, ow, tv->bounds, tv->coeffs,
-                                                              tv->ksize, out_u8x4, out_f32_chw);
+                                                              tv->ksize, (__half*)out_net, out_f32_chw);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }
@@ -449,12 +456,13 @@ __global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, int H, in
   } else if (pix == 0) {
     pt1[2 * i] = pt1[2 * i + 1] = pt2[2 * i] = pt2[2 * i + 1] = 0.f;
   }
-  if (out16) {
-    uint2 pk;
+  if (out16) {  // network input layout: [n, rh, rw + BP_IN_PAD_COLS, 8]
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
     __half2* h = reinterpret_cast<__half2*>(&pk);
     h[0] = __floats2half2_rn(v[0], v[1]);
     h[1] = __floats2half2_rn(v[2], 0.f);
-    reinterpret_cast<uint2*>(out16)[(long)i * rh * rw + pix] = pk;
+    const int oy = pix / rw, ox = pix - oy * rw;
+    reinterpret_cast<uint4*>(out16)[((long)i * rh + oy) * (rw + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + ox] = pk;
   }
   if (out32) {
     const long plane = (long)rh * rw;
@@ -468,13 +476,13 @@ __global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, int H, in
 }  // namespace
 
 extern "C" int bp_crop_resize(bp_engine* e, const uint8_t* frames, int H, int W, const float* box, const int32_t* img_idx,
-                              const uint8_t* valid, int n, int rh, int rw, void* out_f16x4, float* out_f32_chw, float* pt1,
+                              const uint8_t* valid, int n, int rh, int rw, void* out_net, float* out_f32_chw, float* pt1,
                               float* pt2, void* stream) {
-  if (!e || !frames || !box || !img_idx || !pt1 || !pt2 || n <= 0 || (!out_f16x4 && !out_f32_chw))
+  if (!e || !frames || !box || !img_idx || !pt1 || !pt2 || n <= 0 || (!out_net && !out_f32_chw))
     return bp_fail(BP_ERR_INVALID, "bp_crop_resize: bad arguments");
   dim3 grid((rh * rw + 255) / 256, n);
   crop_resize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(frames, H, W, box, img_idx, valid, rh, rw,
-                                                                              (__half*)out_f16x4, out_f32_chw, pt1, pt2);
+                                                                              (__half*)out_net, out_f32_chw, pt1, pt2);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }

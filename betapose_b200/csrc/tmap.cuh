@@ -62,13 +62,19 @@ inline bool make_tmap_2d(TmapApi& api, CUtensorMap* out, const void* base, uint6
 }
 
 // NHWC fp16 activation [N, H, W, C] with `pitch` elements per pixel, traversed as the im2col matrix of an
-// R x S convolution with the given stride / symmetric padding. One load = 128 output pixels x block_k channels.
+// R x S convolution with the given stride and padding (pad_h rows above/below, pad_w columns left/right).
+// One load = 128 output pixels x block_k channels.  row_pitch / img_pitch (elements) default to the dense layout;
+// the packed stem convolutions pass a pixel pitch SMALLER than C (overlapping "virtual pixels", see net.cu) and the
+// padded row pitch of the network-input buffer.
 inline bool make_tmap_im2col(TmapApi& api, CUtensorMap* out, const void* base, int N, int H, int W, int C,
-                             int pitch, int R, int S, int stride, int pad, uint32_t block_k, std::string* err) {
+                             int pitch, int R, int S, int stride, int pad_h, int pad_w, uint32_t block_k, std::string* err,
+                             long row_pitch = 0, long img_pitch = 0) {
+  if (row_pitch <= 0) row_pitch = (long)W * pitch;
+  if (img_pitch <= 0) img_pitch = (long)H * row_pitch;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-  int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (S - 1), pad - (R - 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)row_pitch * 2, (cuuint64_t)img_pitch * 2};
+  int lower[2] = {-pad_w, -pad_h};
+  int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = api.im2col(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
                           upper, block_k, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
@@ -79,7 +85,7 @@ inline bool make_tmap_im2col(TmapApi& api, CUtensorMap* out, const void* base, i
   }
   // Drivers up to 13.1 mis-encode im2col maps of tensors smaller than 128 KiB; clearing bit 21 of the second
   // descriptor word is the documented-by-practice fix (same guard as CUTLASS' make_im2col_tma_copy_desc).
-  const uint64_t bytes = (uint64_t)N * H * W * pitch * 2;
+  const uint64_t bytes = (uint64_t)N * img_pitch * 2;
   if (api.driver_version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(out)[1] &= ~(1ull << 21);
   return true;
 }

@@ -54,11 +54,11 @@ class BetaposeEngine:
         self.hm_id: list[int] = []
         with torch.cuda.device(self.device):
             for s in range(self.n_slots):
-                y = _net.Net(self.B, reso, reso, _lib.IN_U8X4, share=self.yolo[0] if s else None, device=self.device.index)
+                y = _net.Net(self.B, reso, reso, _lib.IN_RAW255, share=self.yolo[0] if s else None, device=self.device.index)
                 params, used = _net.split_darknet_stream(blocks, np.asarray(yolo_streams[s], np.float32))
                 self.heads.append(_net.build_darknet(y, blocks, params))
                 self.yolo.append(y)
-                k = _net.Net(self.B, inp_h, inp_w, _lib.IN_F16X4, share=self.kpd[0] if s else None, device=self.device.index)
+                k = _net.Net(self.B, inp_h, inp_w, _lib.IN_F16, share=self.kpd[0] if s else None, device=self.device.index)
                 self.hm_id.append(_net.build_fastpose(k, kpd_state_dicts[s], self.K))
                 self.kpd.append(k)
             kp3d = np.asarray(kp3d, np.float64)

@@ -105,18 +105,19 @@ class Net:
 
     # ---- introspection --------------------------------------------------------------------------------
     def tensor_info(self, t):
-        dims = (C.c_int * 6)()
+        dims = (C.c_int * 8)()
         p = C.c_void_p()
         _lib.check(_lib.lib().bp_net_tensor_info(self.handle, int(t), dims, C.byref(p)), "bp_net_tensor_info")
-        return dict(H=dims[0], W=dims[1], C=dims[2], pitch=dims[3], f32=bool(dims[4]), coff=dims[5], ptr=p.value)
+        return dict(H=dims[0], W=dims[1], C=dims[2], pitch=dims[3], f32=bool(dims[4]), coff=dims[5], row_px=dims[6],
+                    col0=dims[7], ptr=p.value)
 
     def tensor(self, t, batch=None) -> torch.Tensor:
         """torch view [batch, H, W, C] (strided over the pitch) aliasing the engine's buffer."""
         i = self.tensor_info(t)
         n = self.max_batch if batch is None else int(batch)
-        if t == 0:
-            typ, dt = ("|u1", torch.uint8) if self.in_kind == _lib.IN_U8X4 else ("<f2", torch.float16)
-            return torch.as_tensor(_DevArray(i["ptr"], (n, i["H"], i["W"], 4), typ), device=self.device)
+        if t == 0:  # network input: fp16 [n, H, W + pad columns, 8]; the view covers the data pixels, channels R,G,B
+            full = torch.as_tensor(_DevArray(i["ptr"], (n, i["H"], i["row_px"], 8), "<f2"), device=self.device)
+            return full[:, :, i["col0"]:i["col0"] + i["W"], :3]
         typ = "<f4" if i["f32"] else "<f2"
         full = torch.as_tensor(_DevArray(i["ptr"], (n * i["H"] * i["W"] * i["pitch"],), typ), device=self.device)
         return full.as_strided((n, i["H"], i["W"], i["C"]), (i["H"] * i["W"] * i["pitch"], i["W"] * i["pitch"], i["pitch"], 1))

@@ -22,19 +22,31 @@ def _eng(t: torch.Tensor):
     return _lib.Engine.get(t.device.index)
 
 
-def resize_bicubic(frames_u8: torch.Tensor, out_h: int = 416, out_w: int = 416, want_u8x4: bool = True,
-                   want_f32: bool = False, out_u8x4: torch.Tensor | None = None):
-    """frames uint8 [B,H,W,3] RGB (cuda) -> (u8x4 [B,oh,ow,4] | None, fp32 [B,3,oh,ow] | None); Pillow-exact."""
+def net_input_buffer(n: int, h: int, w: int, device) -> torch.Tensor:
+    """A zeroed network-input buffer fp16 [n, h, w + IN_PAD_COLS, 8] (layout of include/betapose_b200.h, BP_IN_*)."""
+    return torch.zeros((n, h, w + _lib.IN_PAD_COLS, 8), dtype=torch.float16, device=device)
+
+
+def net_input_pixels(buf: torch.Tensor) -> torch.Tensor:
+    """The data pixels [n, h, w, 3] of a network-input buffer (a view)."""
+    w = buf.shape[2] - _lib.IN_PAD_COLS
+    return buf[:, :, _lib.IN_PAD_LEFT:_lib.IN_PAD_LEFT + w, :3]
+
+
+def resize_bicubic(frames_u8: torch.Tensor, out_h: int = 416, out_w: int = 416, want_net: bool = True,
+                   want_f32: bool = False, out_net: torch.Tensor | None = None):
+    """frames uint8 [B,H,W,3] RGB (cuda) -> (network-input buffer fp16 [B,oh,ow+8,8] holding the raw 0..255 values | None,
+    fp32 [B,3,oh,ow] | None); Pillow-exact."""
     assert frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 and frames_u8.shape[3] == 3 and frames_u8.is_contiguous()
     e = _eng(frames_u8)
     B, H, W, _ = frames_u8.shape
-    if want_u8x4 and out_u8x4 is None:
-        out_u8x4 = torch.empty((B, out_h, out_w, 4), dtype=torch.uint8, device=frames_u8.device)
+    if want_net and out_net is None:
+        out_net = net_input_buffer(B, out_h, out_w, frames_u8.device)
     f32 = torch.empty((B, 3, out_h, out_w), dtype=torch.float32, device=frames_u8.device) if want_f32 else None
     _lib.check(_lib.lib().bp_resize_bicubic(e.handle, _lib.ptr(frames_u8), B, H, W, out_h, out_w,
-                                            _lib.ptr(out_u8x4 if want_u8x4 else None), _lib.ptr(f32), _lib.stream_ptr()),
+                                            _lib.ptr(out_net if want_net else None), _lib.ptr(f32), _lib.stream_ptr()),
                "bp_resize_bicubic")
-    return (out_u8x4 if want_u8x4 else None), f32
+    return (out_net if want_net else None), f32
 
 
 def yolo_decode_argmax(heads, anchors, B: int, reso: int = 416, conf: float = 0.01, frame_w: int = 640, frame_h: int = 480,
@@ -78,23 +90,24 @@ def write_results(pred: torch.Tensor, conf: float = 0.01):
 
 
 def crop_resize(frames_u8: torch.Tensor, box: torch.Tensor, img_idx: torch.Tensor, valid: torch.Tensor | None = None,
-                res_h: int = 320, res_w: int = 256, out_f16x4: torch.Tensor | None = None, want_f16: bool = True,
+                res_h: int = 320, res_w: int = 256, out_net: torch.Tensor | None = None, want_f16: bool = True,
                 want_f32: bool = False):
-    """frames uint8 [F,H,W,3]; box fp32 [n,4]; img_idx int32 [n] -> dict(f16x4 [n,rh,rw,4], f32 [n,3,rh,rw], pt1, pt2)."""
+    """frames uint8 [F,H,W,3]; box fp32 [n,4]; img_idx int32 [n] -> dict(net = network-input buffer fp16 [n,rh,rw+8,8],
+    f32 [n,3,rh,rw], pt1, pt2)."""
     e = _eng(frames_u8)
     n = int(box.shape[0])
     _, H, W, _ = frames_u8.shape
     dev = frames_u8.device
-    if want_f16 and out_f16x4 is None:
-        out_f16x4 = torch.empty((n, res_h, res_w, 4), dtype=torch.float16, device=dev)
+    if want_f16 and out_net is None:
+        out_net = net_input_buffer(n, res_h, res_w, dev)
     f32 = torch.empty((n, 3, res_h, res_w), dtype=torch.float32, device=dev) if want_f32 else None
     pt1 = torch.empty((n, 2), dtype=torch.float32, device=dev)
     pt2 = torch.empty((n, 2), dtype=torch.float32, device=dev)
     _lib.check(_lib.lib().bp_crop_resize(e.handle, _lib.ptr(frames_u8), H, W, _lib.ptr(box.contiguous()),
                                          _lib.ptr(img_idx.contiguous()), _lib.ptr(valid), n, res_h, res_w,
-                                         _lib.ptr(out_f16x4 if want_f16 else None), _lib.ptr(f32), _lib.ptr(pt1),
+                                         _lib.ptr(out_net if want_f16 else None), _lib.ptr(f32), _lib.ptr(pt1),
                                          _lib.ptr(pt2), _lib.stream_ptr()), "bp_crop_resize")
-    return dict(f16x4=out_f16x4 if want_f16 else None, f32=f32, pt1=pt1, pt2=pt2)
+    return dict(net=out_net if want_f16 else None, f32=f32, pt1=pt1, pt2=pt2)
 
 
 def heatmap_decode(hm: torch.Tensor, pt1: torch.Tensor, pt2: torch.Tensor, layout: str = "nchw", inp_h: int = 320,

@@ -55,8 +55,13 @@ void bp_engine_destroy(bp_engine* e);
  *   FastPose / SEResnet / Bottleneck / SELayer / DUC (KPD/src/models/FastPose.py:13-35, layers/{SE_Resnet,SE_module,DUC}.py).
  * Tensors are named by small integer ids returned by the builder calls.
  */
-#define BP_IN_U8X4 0  /* input tensor is uint8 [N,H,W,4] (RGBX), scaled by 1/255 when read  */
-#define BP_IN_F16X4 1 /* input tensor is fp16  [N,H,W,4] (RGB + pad)                        */
+/* The network input is always fp16 [N, H, W + BP_IN_PAD_COLS, 8]: pixel (h, w) at column BP_IN_PAD_LEFT + w, channels
+ * 0..2 = R,G,B, channels 3..7 and the pad columns zero (zeroed once at creation; bp_resize_bicubic / bp_crop_resize
+ * write only the data pixels).  This is what lets the first convolution fetch a whole filter row per TMA row. */
+#define BP_IN_RAW255 0 /* pixel values 0..255; ToTensor's 1/255 is folded into the first conv's weights */
+#define BP_IN_F16 1    /* values used as they are (the key-point net's mean-subtracted crop)            */
+#define BP_IN_PAD_LEFT 3
+#define BP_IN_PAD_COLS 8
 
 int bp_net_create(bp_engine* e, int max_batch, int in_h, int in_w, int in_kind, bp_net* share_buffers_with,
                   bp_net** out);
@@ -108,7 +113,8 @@ int bp_net_copy_channels(bp_net* n, int src, int dst, int dst_coff);
 /* element-wise sum (darknet [shortcut] whose producer could not absorb it) */
 int bp_net_add(bp_net* n, int a, int b);
 
-/* query a tensor: dims[0..5] = {H, W, C, pitch (elements per pixel), is_f32, coff}; *ptr = device address */
+/* query a tensor: dims[0..7] = {H, W, C, pitch (elements per pixel), is_f32, coff, pixels per buffer row, first data
+ * column}; *ptr = device address of the buffer */
 int bp_net_tensor_info(bp_net* n, int tensor, int* dims, void** ptr);
 int bp_net_num_launches(bp_net* n);
 double bp_net_flops_per_image(bp_net* n);
@@ -122,9 +128,10 @@ int bp_net_op_desc(bp_net* n, int op, char* buf, int buflen, double* flops_per_i
 
 /* ---------------------------------------------------------------------------------------------- stages */
 /* a1: transforms.Resize((oh,ow), BICUBIC) + ToTensor  (dataloader.py:94-99,162) -- Pillow's two integer
- * passes, bit-exact.  frames: uint8 [B,H,W,3] RGB.  out_u8x4: uint8 [B,oh,ow,4] (detector input) and/or
- * out_f32_chw: fp32 [B,3,oh,ow] in 0..1 (what the reference feeds Darknet); either may be NULL. */
-int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int H, int W, int oh, int ow, uint8_t* out_u8x4,
+ * passes, bit-exact.  frames: uint8 [B,H,W,3] RGB.  out_net: a BP_IN_RAW255 network input buffer
+ * (fp16 [B,oh,ow+BP_IN_PAD_COLS,8], raw 0..255 values) and/or out_f32_chw: fp32 [B,3,oh,ow] in 0..1 (what the
+ * reference feeds Darknet); either may be NULL. */
+int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int H, int W, int oh, int ow, void* out_net,
                       float* out_f32_chw, void* stream);
 
 /* a3+a4+a5: DetectionLayer.forward (yolo/darknet.py:129-169) + write_results (yolo/util.py:118-223, nms off,
@@ -147,10 +154,10 @@ int bp_write_results(bp_engine* e, const float* pred, int B, int R, int n_attr, 
 
 /* a6: im_to_torch + crop_from_dets + cropBox (KPD/src/utils/img.py:13-18,242-262; dataloader.py:794-835).
  * frames uint8 [F,H,W,3] RGB; box[n,4]; img_idx[n] (frame of each box); valid[n] (may be NULL).
- * Outputs: out_f16x4 fp16 [n,rh,rw,4] (keypoint-net input) and/or out_f32_chw fp32 [n,3,rh,rw]; pt1/pt2 [n,2]
- * fp32 un-truncated expanded corners. */
+ * Outputs: out_net = a BP_IN_F16 network input buffer (fp16 [n,rh,rw+BP_IN_PAD_COLS,8]) and/or out_f32_chw fp32
+ * [n,3,rh,rw]; pt1/pt2 [n,2] fp32 un-truncated expanded corners. */
 int bp_crop_resize(bp_engine* e, const uint8_t* frames, int H, int W, const float* box, const int32_t* img_idx,
-                   const uint8_t* valid, int n, int rh, int rw, void* out_f16x4, float* out_f32_chw, float* pt1,
+                   const uint8_t* valid, int n, int rh, int rw, void* out_net, float* out_f32_chw, float* pt1,
                    float* pt2, void* stream);
 
 /* a8: getPrediction + transformBoxInvert_batch (KPD/src/utils/eval.py:113-147; img.py:216-239).

@@ -92,7 +92,7 @@ struct Case {
   int x_pitch_extra = 0, out_pitch_extra = 0, out_coff = 0;
   int force_bn = 0, force_st = 0;
   int iters = 0;  // >0: also time it
-  int gather = 0;  // stem mode: C must be 4, K laid out (tap, 4)
+  int gather = 0;  // unused (kept so the positional initialisers below stay valid)
   int cg = 0;      // 0 = planner's choice, 1 = single CTA, 2 = CTA pairs (cta_group::2)
 };
 
@@ -100,7 +100,7 @@ static int run_case(const Case& cs) {
   Rng rng(1234);
   const int xp = cs.C + cs.x_pitch_extra;
   const int K = cs.R * cs.S * cs.C;
-  const int wp = cs.gather ? (cs.R * cs.S + 15) / 16 * 64 : (K + 7) / 8 * 8;
+  const int wp = (K + 7) / 8 * 8;
   const int Cout_pad = (cs.Cout + 255) / 256 * 256;
   const int P = (cs.H + 2 * cs.pad - cs.R) / cs.stride + 1, Q = (cs.W + 2 * cs.pad - cs.S) / cs.stride + 1;
   const long M = (long)cs.N * P * Q;
@@ -147,7 +147,6 @@ static int run_case(const Case& cs) {
   d.res = dres; d.res_pitch = cs.Cout; d.res_mode = cs.res_mode;
   d.out = dout; d.out_pitch = opitch; d.out_coff = cs.out_coff; d.out_f32 = cs.out_f32; d.store_mode = cs.store_mode;
   d.force_block_n = cs.force_bn; d.force_stages = cs.force_st; d.force_cg = cs.cg;
-  d.gather = cs.gather;
   ConvPlan pl;
   std::string err;
   if (!conv_plan_build(g_api, &pl, d, &err)) {
@@ -232,6 +231,112 @@ static int run_case(const Case& cs) {
   return bad ? 1 : 0;
 }
 
+// Stem convolution exactly as betapose_b200/csrc/net.cu builds it: input fp16 [N, H, W + 8, 8] (data from column 3,
+// channels 3..7 and pad columns zero), a k x 1 convolution over "virtual pixels" of Cv channels whose pixel stride
+// (16 B) is smaller than their extent; weights [Cout][r][q*8 + c].  Reference: the naive kernel on a dense C = 8 copy.
+static int run_stem_case(const char* name, int N, int H, int W, int k, int stride, int pad, int Cout, int act, int iters) {
+  Rng rng(4321);
+  const int PADL = 3, PADC = 8, Wp = W + PADC;
+  const int Cv = k * 8 <= 32 ? 32 : 64;
+  const int K = k * Cv, wp = K;
+  const int Cout_pad = (Cout + 255) / 256 * 256;
+  const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
+  const long M = (long)N * P * Q;
+  std::vector<__half> hx((size_t)N * H * Wp * 8, __float2half(0.f)), hd((size_t)N * H * W * 8, __float2half(0.f));
+  for (int n = 0; n < N; ++n)
+    for (int h = 0; h < H; ++h)
+      for (int w = 0; w < W; ++w)
+        for (int c = 0; c < 3; ++c) {
+          const __half v = __float2half((float)(int)rng.uni(0.f, 255.99f));
+          hx[(((size_t)n * H + h) * Wp + PADL + w) * 8 + c] = v;
+          hd[(((size_t)n * H + h) * W + w) * 8 + c] = v;
+        }
+  std::vector<__half> hw((size_t)Cout_pad * wp, __float2half(0.f)), hwd((size_t)Cout_pad * k * k * 8, __float2half(0.f));
+  std::vector<float> hb(Cout_pad, 0.f);
+  const float ws = 1.0f / (255.f * sqrtf((float)(k * k * 3)));
+  for (int co = 0; co < Cout; ++co) {
+    for (int r = 0; r < k; ++r)
+      for (int q = 0; q < k; ++q)
+        for (int c = 0; c < 3; ++c) {
+          const __half v = __float2half(rng.uni(-1.f, 1.f) * ws * 3.4f);
+          hw[(size_t)co * wp + r * Cv + q * 8 + c] = v;
+          hwd[(size_t)co * k * k * 8 + (r * k + q) * 8 + c] = v;
+        }
+    hb[co] = rng.uni(-0.5f, 0.5f);
+  }
+  __half *dx, *dd, *dw, *dwd, *dout;
+  float *db, *dref;
+  CK(cudaMalloc(&dx, hx.size() * 2)); CK(cudaMalloc(&dd, hd.size() * 2));
+  CK(cudaMalloc(&dw, hw.size() * 2)); CK(cudaMalloc(&dwd, hwd.size() * 2));
+  CK(cudaMalloc(&db, hb.size() * 4)); CK(cudaMalloc(&dref, (size_t)M * Cout * 4)); CK(cudaMalloc(&dout, (size_t)M * Cout * 2));
+  CK(cudaMemset(dout, 0xFF, (size_t)M * Cout * 2));
+  CK(cudaMemcpy(dx, hx.data(), hx.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dd, hd.data(), hd.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dwd, hwd.data(), hwd.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
+
+  ConvDesc d;
+  d.x = dx + (size_t)(PADL - pad) * 8;
+  d.N = N; d.H = H; d.W = (Q - 1) * stride + 1; d.C = Cv; d.x_pitch = 8;
+  d.x_row_pitch = (long)Wp * 8; d.x_img_pitch = (long)H * Wp * 8;
+  d.R = k; d.S = 1; d.stride = stride; d.pad = pad; d.pad_w = 0; d.real_k = k * k * 3;
+  d.w = dw; d.bias = db; d.w_pitch = wp; d.Cout = Cout; d.Cout_pad = Cout_pad; d.act = act;
+  d.out = dout; d.out_pitch = Cout;
+  ConvPlan pl;
+  std::string err;
+  if (!conv_plan_build(g_api, &pl, d, &err)) {
+    printf("[%-28s] PLAN FAILED: %s\n", name, err.c_str());
+    return 1;
+  }
+  cudaError_t le = conv_plan_launch(pl, 0);
+  cudaError_t se = cudaDeviceSynchronize();
+  if (le != cudaSuccess || se != cudaSuccess) {
+    printf("[%-28s] LAUNCH/RUN FAILED: %s / %s\n", name, cudaGetErrorString(le), cudaGetErrorString(se));
+    exit(3);
+  }
+  const long total = M * Cout;
+  ref_conv_kernel<<<(unsigned)((total + 255) / 256), 256>>>(dd, N, H, W, 8, 8, dwd, k * k * 8, db, k, k, stride, pad, P, Q, Cout,
+                                                           act, nullptr, 0, RES_NONE, dref);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> href((size_t)total);
+  std::vector<__half> hout((size_t)total);
+  CK(cudaMemcpy(href.data(), dref, href.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hout.data(), dout, hout.size() * 2, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0;
+  long bad = 0, first_bad = -1;
+  for (long i = 0; i < total; ++i) {
+    const double r = href[i], g = __half2float(hout[i]), e = fabs(g - r);
+    if (!(e <= 2e-2 + 4e-3 * fabs(r))) {
+      if (first_bad < 0) first_bad = i;
+      ++bad;
+    }
+    if (e > max_err || e != e) max_err = e;
+    if (fabs(r) > max_ref) max_ref = fabs(r);
+  }
+  double ms = 0;
+  if (iters > 0 && bad == 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) conv_plan_launch(pl, 0);
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) conv_plan_launch(pl, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float t;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    ms = t / iters;
+  }
+  printf("[%-28s] bn=%3d bk=%2d st=%d cg=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", name, pl.block_n,
+         pl.block_k, pl.stages, pl.cg, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
+  if (bad) printf(" first_bad: m=%ld co=%ld", first_bad / Cout, first_bad % Cout);
+  if (ms > 0) printf("  %.3f ms  %.1f GB/s out", ms, (double)total * 2 / ms * 1e-6);
+  printf("\n");
+  fflush(stdout);
+  cudaFree(dx); cudaFree(dd); cudaFree(dw); cudaFree(dwd); cudaFree(db); cudaFree(dref); cudaFree(dout);
+  return bad ? 1 : 0;
+}
+
 // Dump what one im2col TMA load actually fetches, against the expected gather, to pin the coordinate semantics.
 static int run_probe(int N, int H, int W, int C, int R, int S, int stride, int pad, int m0, int fr, int fs) {
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
@@ -249,7 +354,7 @@ static int run_probe(int N, int H, int W, int C, int R, int S, int stride, int p
   CK(cudaMalloc(&dout, bytes));
   alignas(64) CUtensorMap tm;
   std::string err;
-  if (!make_tmap_im2col(g_api, &tm, dx, N, H, W, C, C, R, S, stride, pad, bk, &err)) {
+  if (!make_tmap_im2col(g_api, &tm, dx, N, H, W, C, C, R, S, stride, pad, pad, bk, &err)) {
     printf("probe: tmap failed %s\n", err.c_str());
     return 1;
   }
@@ -341,14 +446,14 @@ int main(int argc, char** argv) {
   printf("probe failures: %d\n", pf);
   if (probe_only) return pf ? 1 : 0;
 
-  std::vector<Case> stem = {
-      {"stem 3x3 s1 4->32 40x36", 3, 40, 36, 4, 32, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 1},
-      {"stem 7x7 s2 4->64 64x48", 3, 64, 48, 4, 64, 7, 7, 2, 3, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 1},
-      {"stem 3x3 s1 4->32 @416 B64", 64, 416, 416, 4, 32, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 5, 1},
-      {"stem 7x7 s2 4->64 @320x256 B64", 64, 320, 256, 4, 64, 7, 7, 2, 3, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 5, 1},
-  };
-  if (!probe_only)
-    for (auto& c : stem) fails += run_case(c);
+  if (!probe_only) {
+    // packed stem convolutions over the padded network-input layout [N, H, W + 8, 8] (overlapping im2col map)
+    fails += run_stem_case("stem 3x3 s1 3->32 40x36", 3, 40, 36, 3, 1, 1, 32, ACT_LEAKY, 0);
+    fails += run_stem_case("stem 7x7 s2 3->64 64x48", 3, 64, 48, 7, 2, 3, 64, ACT_RELU, 0);
+    fails += run_stem_case("stem 3x3 s1 3->32 53x47", 2, 53, 47, 3, 1, 1, 32, ACT_LEAKY, 0);
+    fails += run_stem_case("stem 3x3 s1 3->32 @416 B64", 64, 416, 416, 3, 1, 1, 32, ACT_LEAKY, 5);
+    fails += run_stem_case("stem 7x7 s2 3->64 @320x256 B64", 64, 320, 256, 7, 2, 3, 64, ACT_RELU, 5);
+  }
 
   std::vector<Case> conv = {
       {"3x3 s1 C64->128 13x13", 2, 13, 13, 64, 128, 3, 3, 1, 1},

@@ -24,7 +24,7 @@ def test_engine_stagewise_parity(engine, frames8, kp_model):
     torch.cuda.synchronize()
     B = 8
     # a1
-    yin = e.yolo[0].input(B).cpu().numpy()
+    yin = e.yolo[0].input(B).float().cpu().numpy()  # raw 0..255 pixel values, exact in fp16
     for b in range(B):
         assert np.array_equal(yin[b, :, :, :3], R.pil_resize_bicubic(frames8[b], 416, 416))
     # a3-a5 from the engine's fp32 heads

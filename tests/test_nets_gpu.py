@@ -150,12 +150,11 @@ def _run_yolo(blocks, stream, x_u8, reso):
     from betapose_b200 import _lib, net as bnet
 
     B = x_u8.shape[0]
-    n = bnet.Net(B, reso, reso, _lib.IN_U8X4)
+    n = bnet.Net(B, reso, reso, _lib.IN_RAW255)
     params, used = bnet.split_darknet_stream(blocks, stream)
     assert used == stream.size
     heads = bnet.build_darknet(n, blocks, params)
-    inp = n.input(B)
-    inp[..., :3] = torch.from_numpy(x_u8).cuda()
+    n.input(B).copy_(torch.from_numpy(x_u8).cuda())  # data pixels of the padded fp16 buffer, raw 0..255
     n.forward(B)
     torch.cuda.synchronize()
     return n, [n.tensor(h["tensor"], B).permute(0, 3, 1, 2).contiguous().cpu() for h in heads]
@@ -193,10 +192,10 @@ def test_yolov3_full_vs_oracle(yolo_blocks, yolo_stream, frames8):
 
     B = 2
     fr = torch.from_numpy(frames8[:B]).cuda()
-    u8x4, _ = stages.resize_bicubic(fr, 416, 416)
-    x = u8x4[..., :3].cpu().numpy()
+    buf, _ = stages.resize_bicubic(fr, 416, 416)
+    x = stages.net_input_pixels(buf).cpu().numpy().astype(np.uint8)
     n, got = _run_yolo(yolo_blocks, yolo_stream, x, 416)
-    assert n.num_ops == 75  # 75 convs: every shortcut / route / upsample fused away, the stem gathers its own operand
+    assert n.num_ops == 75  # 75 convs: every shortcut / route / upsample fused away, the stem reads the padded input through an overlapping im2col map
     assert abs(n.flops_per_image - 65.29e9) < 0.05e9
     params, used = onets.split_darknet_weights(yolo_blocks, yolo_stream)
     assert used == yolo_stream.size
@@ -225,9 +224,9 @@ def test_fastpose_full_vs_oracle(kpd_sd, frames8):
     fr = torch.from_numpy(frames8[:B]).cuda()
     box = torch.tensor([[200.0, 100.0, 420.0, 380.0], [50.0, 60.0, 300.0, 400.0]], device="cuda")
     crop = stages.crop_resize(fr, box, torch.arange(B, dtype=torch.int32, device="cuda"), want_f32=True)
-    n = bnet.Net(B, 320, 256, _lib.IN_F16X4)
+    n = bnet.Net(B, 320, 256, _lib.IN_F16)
     hm_id = bnet.build_fastpose(n, kpd_sd, 50)
-    n.input(B).copy_(crop["f16x4"])
+    n.input(B).copy_(stages.net_input_pixels(crop["net"]))
     n.forward(B)
     torch.cuda.synchronize()
     got = n.tensor(hm_id, B).permute(0, 3, 1, 2).contiguous().cpu()
@@ -253,9 +252,9 @@ def test_net_batch_smaller_than_max(yolo_blocks):
     blocks = yolo_cfg.parse_cfg_text(MINI_CFG.replace("ROUTE1", "-3"))
     stream = _stream_for(blocks, 3)
     params, _ = bnet.split_darknet_stream(blocks, stream)
-    n = bnet.Net(4, 64, 64, _lib.IN_U8X4)
+    n = bnet.Net(4, 64, 64, _lib.IN_RAW255)
     heads = bnet.build_darknet(n, blocks, params)
-    x = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (4, 64, 64, 4), dtype=np.uint8)).cuda()
+    x = torch.from_numpy(np.random.default_rng(2).integers(0, 256, (4, 64, 64, 3), dtype=np.uint8)).cuda()
     n.input(4).copy_(x)
     n.forward(4)
     torch.cuda.synchronize()

@@ -21,11 +21,13 @@ def test_resize_bicubic_bit_exact(shape, out):
 
     rng = np.random.default_rng(0)
     fr = rng.integers(0, 256, (3,) + shape + (3,), dtype=np.uint8)
-    u8, f32 = stages.resize_bicubic(_cuda(fr), out[0], out[1], want_u8x4=True, want_f32=True)
+    buf, f32 = stages.resize_bicubic(_cuda(fr), out[0], out[1], want_net=True, want_f32=True)
+    u8 = stages.net_input_pixels(buf)
+    assert float(buf[..., 3:].abs().max()) == 0.0 and float(buf[:, :, :3].abs().max()) == 0.0  # pad channels / columns
     torch.cuda.synchronize()
     for b in range(fr.shape[0]):
         ref = R.pil_resize_bicubic(fr[b], out[0], out[1])
-        assert np.array_equal(u8[b, :, :, :3].cpu().numpy(), ref)
+        assert np.array_equal(u8[b].float().cpu().numpy(), ref.astype(np.float32))
         assert np.array_equal(f32[b].cpu().numpy(), (ref.astype(np.float32) / np.float32(255)).transpose(2, 0, 1))
 
 
@@ -34,9 +36,10 @@ def test_resize_matches_pillow_directly():
     from betapose_b200 import stages
 
     fr = np.random.default_rng(1).integers(0, 256, (1, 480, 640, 3), dtype=np.uint8)
-    u8, _ = stages.resize_bicubic(_cuda(fr), 416, 416)
+    buf, _ = stages.resize_bicubic(_cuda(fr), 416, 416)
+    u8 = stages.net_input_pixels(buf)
     ref = np.asarray(PIL.fromarray(fr[0]).resize((416, 416), PIL.BICUBIC))
-    assert np.array_equal(u8[0, :, :, :3].cpu().numpy(), ref)
+    assert np.array_equal(u8[0].float().cpu().numpy(), ref.astype(np.float32))
 
 
 # ------------------------------------------------------------------------------------------------ a3-a5
@@ -125,9 +128,9 @@ def test_crop_resize_matches_oracle(frames8):
         ref = R.crop_box(frames8[idx[i]], pt1, pt2)
         got = out["f32"][i].cpu().numpy()
         np.testing.assert_allclose(got, ref, rtol=0, atol=2.4e-7)  # <= 2 fp32 ulp at |x| <= 1
-        got16 = out["f16x4"][i, :, :, :3].float().cpu().numpy().transpose(2, 0, 1)
+        got16 = stages.net_input_pixels(out["net"])[i].float().cpu().numpy().transpose(2, 0, 1)
         np.testing.assert_allclose(got16, ref, rtol=0, atol=5e-4)    # fp16 rounding of values in [-0.5, 0.6]
-        assert float(out["f16x4"][i, :, :, 3].abs().max()) == 0.0
+        assert float(out["net"][i, :, :, 3:].abs().max()) == 0.0
 
 
 def test_crop_resize_invalid_rows_are_zero(frames8):
@@ -136,7 +139,7 @@ def test_crop_resize_invalid_rows_are_zero(frames8):
     valid = np.array([1, 0, 1], np.uint8)
     out = stages.crop_resize(_cuda(frames8), _cuda(BOXES[:3]), _cuda(np.zeros(3, np.int32)), valid=_cuda(valid))
     torch.cuda.synchronize()
-    assert float(out["f16x4"][1].abs().max()) == 0.0 and float(out["f16x4"][0].abs().max()) > 0.0
+    assert float(out["net"][1].abs().max()) == 0.0 and float(out["net"][0].abs().max()) > 0.0
 
 
 # ------------------------------------------------------------------------------------------------ a8
