@@ -77,18 +77,20 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
   if (pl.cg == 2) {
-    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 4, 2>(pl, st);
+    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 5, 2>(pl, st);
     if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, 2>(pl, st);
     return cudaErrorInvalidConfiguration;
   }
 #define BP_CASE(BN, BK, ST) \
   if (pl.block_n == BN && pl.block_k == BK && pl.stages == ST) return launch_cfg<BN, BK, ST>(pl, st);
+  // as many stages as fit beside the epilogue ring: the loop TMA issue -> data lands -> MMA -> commit -> slot free
+  // takes ~3000 cycles under load, and a CTA sustains (bytes in flight) / (that latency)
   BP_CASE(256, 64, 3)
-  BP_CASE(128, 64, 4)
+  BP_CASE(128, 64, 5)
   BP_CASE(64, 64, 6)
-  BP_CASE(32, 64, 6)
-  BP_CASE(64, 32, 8)
-  BP_CASE(32, 32, 8)
+  BP_CASE(32, 64, 9)
+  BP_CASE(64, 32, 13)
+  BP_CASE(32, 32, 16)
 #undef BP_CASE
   return cudaErrorInvalidConfiguration;
 }
@@ -112,9 +114,11 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   // Tile configuration by a small cost model fitted to B200 measurements (tests/harness/conv_harness.cu, batch 64):
   // a persistent grid walks the tiles round-robin, so a launch takes ceil(tiles / CTAs) rounds of one tile each, and a
   // k-block costs ~500 + (BLOCK_K / 16) * bn / 2 cycles (bn = 64 / 128 / 256: 628 / 758 / 1000-1040 measured; the
-  // second term is the tensor-pipe time, the first does not shrink with the tile).  Wider tiles therefore win unless
-  // they leave most of the machine idle.  CTA pairs (cta_group::2, M = 256) measured within +-5 % of single CTAs on
-  // every production shape, so they are only used when forced (d.force_cg = 2).
+  // second term is the tensor-pipe time, the first is the TMA -> MMA -> commit loop latency spread over the stages that
+  // fit in shared memory).  Wider tiles therefore win unless they leave most of the machine idle.
+  // CTA pairs (cta_group::2, M = 256): each CTA stages only half of B, so five 32 KB stages fit instead of three
+  // 48 KB ones; measured +6-8 % on every 256-wide 3x3 layer (K >= 1152: 1260 vs 1168, 1411 vs 1334, 1404 vs 1319
+  // TFLOP/s) and -5-20 % on the short-K 1x1 layers, where the cluster launch and cross-CTA hand-offs do not amortise.
   int bn = 0, cg = 0;
   {
     int cap = 32;
@@ -124,7 +128,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
     for (int c = cap; c >= 32; c /= 2) {
       if (d.force_block_n && c != d.force_block_n) continue;
       if (d.Cout_pad % c) continue;
-      const int g = d.force_cg ? d.force_cg : 1;
+      const int g = d.force_cg ? d.force_cg : ((c == 256 && block_k == 64 && num_kb >= 18 && m_tiles >= d.num_sms) ? 2 : 1);
       if (g == 2 && (block_k != 64 || c < 128 || d.num_sms < 2)) continue;
       const long tiles = (long)((m_tiles + g - 1) / g) * ((d.Cout + c - 1) / c);
       const long units = g == 2 ? d.num_sms / 2 : d.num_sms;
@@ -146,7 +150,8 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
     if (err) *err = "Cout_pad must be a multiple of BLOCK_N";
     return false;
   }
-  const int st = cg == 2 ? (bn == 256 ? 4 : 6) : (bn == 256 ? 3 : (bn == 128 ? 4 : (block_k == 64 ? 6 : 8)));
+  const int st = cg == 2 ? (bn == 256 ? 5 : 6)
+                         : (block_k == 64 ? (bn == 256 ? 3 : bn == 128 ? 5 : bn == 64 ? 6 : 9) : (bn == 64 ? 13 : 16));
 
   pl->block_n = bn;
   pl->block_k = block_k;

@@ -79,7 +79,12 @@ struct ConvCfg {
   static constexpr int N_CHUNKS = BLOCK_N / CHUNK;
   static constexpr int NBUF = NB;                      // ring of chunk buffers: residual lands in it, result leaves from it
   static constexpr int EPI_BYTES = NBUF * CHUNK_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;  // + slack for 1024B alignment
+  // The kernel has NO static shared memory, so the dynamic window starts at the (1024-byte aligned) base of the CTA's
+  // shared memory and the swizzled tiles need no alignment slack: [stages][epilogue ring][bias x2][mbarriers].
+  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + NBUF) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, each takes half of a chunk's columns
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -168,19 +173,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int CHUNK = Cfg::CHUNK;
   constexpr int N_CHUNKS = Cfg::N_CHUNKS;
 
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
-  __shared__ __align__(8) uint64_t res_full_bar[Cfg::NBUF];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float s_bias[2][BLOCK_N];
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;  // NBUF x CHUNK_BYTES
+  float(*s_bias)[BLOCK_N] = reinterpret_cast<float(*)[BLOCK_N]>(ring + Cfg::EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Cfg::EPI_BYTES + Cfg::BIAS_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_base_slot_p = reinterpret_cast<uint32_t*>(res_full_bar + Cfg::NBUF);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem + STAGES * Cfg::STAGE_BYTES;  // NBUF x CHUNK_BYTES
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+    printf("bp: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
 
   // tile walk: cluster c of the grid takes (pair-)tiles c, c + num_clusters, ...; inside a pair CTA `rank` owns the
   // rows of m-tile 2 * pair_m_tile + rank
@@ -211,14 +219,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 1) {
-    if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(&tmem_base_slot);
-    else tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_slot);
+    if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_base_slot_p);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_base_slot_p);
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = *tmem_base_slot_p;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one thread: the loop is pure issue

@@ -491,17 +491,34 @@ int main(int argc, char** argv) {
   if (!quick && fails == 0) {
     printf("---- timing (batch 64 production shapes) ----\n");
     std::vector<Case> perf = {
-        // pure GEMMs with the FLOPs of the 3x3 layers (A through 2-D tiled TMA instead of im2col)
-        {"G 1x1 1152->256 M173056 cg1", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"G 1x1 1152->256 M173056 cg2", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"G 1x1 2304->512 M43264 cg1", 64, 26, 26, 2304, 512, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"G 1x1 2304->512 M43264 cg2", 64, 26, 26, 2304, 512, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"G 1x1 1152->256 cg2 bn128", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 2},
-        {"G 1x1 1152->256 cg1 bn128", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1},
-        {"G 1x1 1152->256 cg1 bn64", 64, 52, 52, 1152, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 10, 0, 1},
         {"Y 3x3 128->256 @52 cg1", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
         {"Y 3x3 128->256 @52 cg2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 3x3 256->512 @26 cg2 st4", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 3x3 128->256 @52 +res cg2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 3x3 256->512 @26 cg1", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"Y 3x3 256->512 @26 cg2", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 3x3 512->1024 @13 cg1", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"Y 3x3 512->1024 @13 cg2", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 1x1 256->128 @52 cg1", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1},
+        {"Y 1x1 256->128 @52 cg2", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 2},
+        {"Y 1x1 512->256 @26 cg1", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"Y 1x1 512->256 @26 cg2", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 3x3 64->128 @104 cg1", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1},
+        {"Y 3x3 64->128 @104 cg2", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 2},
+        {"K 3x3 256->256 @20x16 cg1", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"K 3x3 256->256 @20x16 cg2", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"K 1x1 256->1024 +res cg1", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"K 1x1 256->1024 +res cg2", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"K 1x1 1024->256 cg1", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"K 1x1 1024->256 cg2", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"K 3x3 512->1024 ps2 cg1", 64, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 256, 0, 10, 0, 1},
+        {"K 3x3 512->1024 ps2 cg2", 64, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 256, 0, 10, 0, 2},
+        {"Y 3x3 32->64 s2 @416 bn64", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 5},
+        {"Y 3x3 32->64 s1 @208 +res", 64, 208, 208, 32, 64, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 64, 0, 5},
+        {"K 3x3 64->64 @80x64 bn64", 64, 80, 64, 64, 64, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 64, 0, 10},
+        {"K 1x1 64->256 @80x64 +res", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 1x1 64->32 @208", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
+        {"Y 1x1 128->64 @104", 64, 104, 104, 128, 64, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
+        {"K 3x3 128->50 f32 head", 64, 80, 64, 128, 50, 3, 3, 1, 1, ACT_NONE, RES_NONE, STORE_PLAIN, 1, 0, 2, 0, 0, 0, 10},
     };
     for (auto& c : perf) fails += run_case(c);
   }
