@@ -78,6 +78,13 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still draining; everything before griddep_wait() (barrier init, TMEM allocation, descriptor prefetch)
+// overlaps the predecessor's tail, everything after it sees the predecessor's memory writes.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cluster of 2, tcgen05 cta_group::2)
 // shared::cluster address of the same shared-memory location in the pair's leader CTA (rank 0): bit 24 carries the
 // CTA rank inside a 2-CTA cluster (same convention as cute::Sm100MmaPeerBitMask)

@@ -52,6 +52,7 @@ void bp_engine_destroy(bp_engine* e) {
   cudaSetDevice(e->device);
   for (void* p : e->owned) cudaFree(p);
   if (e->resize_tmp) cudaFree(e->resize_tmp);
+  if (e->pnp_scratch) cudaFree(e->pnp_scratch);
   delete e;
 }
 

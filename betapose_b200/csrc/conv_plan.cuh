@@ -54,25 +54,28 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
+  // programmatic dependent launch: this kernel's prologue overlaps the tail of the previous kernel in the stream
+  // (conv_umma_kernel calls griddepcontrol.wait before it touches global memory)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
   if constexpr (CG == 2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl.grid);
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
-  } else {
-    conv_umma_kernel<BN, BK, ST, CG, NB><<<pl.grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pl.tmOut, pl.tmRes,
-                                                                                       pl.args);
-    return cudaGetLastError();
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
   }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {

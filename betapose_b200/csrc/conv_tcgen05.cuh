@@ -222,10 +222,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_base_slot_p);
     else tmem_alloc<Cfg::TMEM_COLS>(tmem_base_slot_p);
   }
+  griddep_launch_dependents();  // the next kernel of the stream may start its own set-up as soon as an SM frees up
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   else __syncthreads();
   tc_fence_after();
+  griddep_wait();  // from here on the previous kernel's outputs (our activations / residual) are complete and visible
   const uint32_t tmem_base = *tmem_base_slot_p;
 
   if (warp == 0) {

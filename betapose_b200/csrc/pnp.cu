@@ -1,7 +1,16 @@
-// a9 (single-proposal pose-NMS) + a10 (key-point selection) + a11 (PnP) in one launch: one CTA per detection.
-//   threads k < K      : score floor / threshold / -0.3 shift / rank-based selection
-//   threads h < n_hyp  : one 5-point EPnP hypothesis each (fp64), scored against all selected points
-//   warp 0             : picks the consensus set (shuffle arg-max) and runs the LM refit lane-parallel over points
+// a9 (single-proposal pose-NMS) + a10 (key-point selection) + a11 (PnP) in two launches:
+//   pnp_hypotheses_kernel : grid (n_hyp / 8, images).  Every CTA redoes the (cheap) pose-NMS + selection of its image,
+//                           then solves 8 five-point EPnP hypotheses, 16 cooperating lanes each: the 12 x 12 M^T M
+//                           eigen-problem -- 80 % of the serial work of a hypothesis -- runs as a parallel-order Jacobi
+//                           (the 6 disjoint rotations of a round at once, 72 column / row updates spread over the
+//                           lanes) on matrices held in shared memory; the rest of EPnP is executed redundantly by the
+//                           16 lanes (identical inputs, identical results, no divergence).  Each hypothesis is scored
+//                           against all selected points (12 px) and left in a global scratch row.
+//   pnp_refine_kernel     : one warp per image picks the consensus winner (shuffle arg-max) and alternates
+//                           {classify points against the current pose, Levenberg-Marquardt refit, lane-parallel over
+//                           points} until the consensus set is stable.
+// 512 small CTAs instead of 64 keep ~3.5 CTAs per SM in flight, so the fp64 dependency chains of different
+// hypotheses hide each other's latency.
 // Reference: pPose_nms.py:24-122 (n = 1 branch), dataloader.py:715-726, utils/utils.py:17-41.
 #include <cuda_runtime.h>
 
@@ -13,6 +22,8 @@ namespace {
 
 constexpr int kMaxK = 64;
 constexpr int kMaxHyp = 128;
+constexpr int kHypPerCta = 8;       // x 16 lanes = 128 threads
+constexpr int kHypRow = 16;         // doubles per hypothesis in the scratch: count, total, R[9], t[3], pad
 
 struct WarpLanes {
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
@@ -27,170 +38,302 @@ struct WarpLanes {
   }
 };
 
-__global__ void __launch_bounds__(kMaxHyp)
-pose_pnp_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
-                const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d, const int32_t* __restrict__ model_idx,
-                double fx, double fy, double cx, double cy, int left_number, int mode, int flags, double thr2, int n_hyp, uint32_t seed,
-                float* __restrict__ keypoints, float* __restrict__ kp_score, float* __restrict__ proposal,
-                uint8_t* __restrict__ selected, double* __restrict__ R_out, double* __restrict__ t_out,
-                uint8_t* __restrict__ inlier, int32_t* __restrict__ status) {
-  __shared__ double s_pw[kMaxK * 3];
-  __shared__ double s_uv[kMaxK * 2];
-  __shared__ float s_sc[kMaxK];
-  __shared__ uint8_t s_sel[kMaxK];
-  __shared__ uint8_t s_inl[kMaxK];
-  __shared__ int s_cnt[kMaxHyp];
-  __shared__ double s_tot[kMaxHyp];
-  __shared__ double s_R[kMaxHyp * 9];
-  __shared__ double s_t[kMaxHyp * 3];
-  __shared__ int s_state;  // 1 = run PnP, 0 = rejected
-  __shared__ int s_nsel;
+// ---- 12 x 12 symmetric eigen-solver on 16 cooperating lanes (half a warp), A and V in shared memory.
+// Parallel-order cyclic Jacobi: a sweep is 11 rounds of 6 disjoint pairs (circle method); the rotations of a round
+// commute, so A <- J^T A J is applied as "all column updates, then all row updates".  Same rotation formulas as the
+// serial jacobi_eig<12> (pnp_math.cuh), different rotation order.
+struct GroupEig12 {
+  double* A;      // [144] shared, this group's
+  double* V;      // [144] shared
+  unsigned mask;  // the 16 lanes of this group inside the warp
+  int gl;         // lane inside the group
 
-  const int i = blockIdx.x;
+  __device__ __forceinline__ double gsum(double x) const {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, 16);
+    return x;
+  }
+
+  __device__ const double* solve(double* M, double* w) {
+    if (gl < 12) {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) {
+        A[gl * 12 + c] = M[gl * 12 + c];
+        V[gl * 12 + c] = gl == c ? 1.0 : 0.0;
+      }
+    }
+    __syncwarp(mask);
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      double off = 0.0, diag = 0.0;
+      if (gl < 12) {
+        diag = A[gl * 13] * A[gl * 13];
+        for (int q = gl + 1; q < 12; ++q) off += A[gl * 12 + q] * A[gl * 12 + q];
+      }
+      off = gsum(off);
+      diag = gsum(diag);
+      if (off < 1e-300) break;
+      const bool last = off <= 1e-22 * diag;  // quadratic convergence: one more sweep reaches the rounding floor
+      for (int r = 0; r < 11; ++r) {
+        // this lane's pair of the round (lanes 0..5): (11, r) and ((r + i) % 11, (r - i) % 11), i = 1..5
+        int p = 0, q = 1;
+        double c = 1.0, s = 0.0;
+        if (gl < 6) {
+          int a = gl == 0 ? 11 : (r + gl) % 11;
+          int b = gl == 0 ? r : (r - gl + 11) % 11;
+          p = a < b ? a : b;
+          q = a < b ? b : a;
+          const double apq = A[p * 12 + q];
+          if (fabs(apq) >= 1e-300) {
+            const double theta = (A[q * 12 + q] - A[p * 12 + p]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            s = t * c;
+          }
+        }
+        __syncwarp(mask);  // every pair has read its 2 x 2 block before anything is rewritten
+        // columns of A and V: item (pair j, row k), 72 items over 16 lanes
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+          const int i = gl + 16 * it;
+          const int j = i < 72 ? i / 12 : 0;
+          const int k = i - (i / 12) * 12;
+          const int pj = __shfl_sync(mask, p, j, 16), qj = __shfl_sync(mask, q, j, 16);
+          const double cj = __shfl_sync(mask, c, j, 16), sj = __shfl_sync(mask, s, j, 16);
+          if (i < 72) {
+            const double akp = A[k * 12 + pj], akq = A[k * 12 + qj];
+            A[k * 12 + pj] = cj * akp - sj * akq;
+            A[k * 12 + qj] = sj * akp + cj * akq;
+            const double vkp = V[k * 12 + pj], vkq = V[k * 12 + qj];
+            V[k * 12 + pj] = cj * vkp - sj * vkq;
+            V[k * 12 + qj] = sj * vkp + cj * vkq;
+          }
+        }
+        __syncwarp(mask);
+        // rows of A
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+          const int i = gl + 16 * it;
+          const int j = i < 72 ? i / 12 : 0;
+          const int k = i - (i / 12) * 12;
+          const int pj = __shfl_sync(mask, p, j, 16), qj = __shfl_sync(mask, q, j, 16);
+          const double cj = __shfl_sync(mask, c, j, 16), sj = __shfl_sync(mask, s, j, 16);
+          if (i < 72) {
+            const double apk = A[pj * 12 + k], aqk = A[qj * 12 + k];
+            A[pj * 12 + k] = cj * apk - sj * aqk;
+            A[qj * 12 + k] = sj * apk + cj * aqk;
+          }
+        }
+        __syncwarp(mask);
+      }
+      if (last) break;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[i] = A[i * 13];
+    return V;
+  }
+};
+
+// ---- a9 + a10 for one image, by the first K threads of the CTA; leaves the selected points in shared memory.
+// Returns (to every thread) whether PnP should run; writes the per-image outputs when `write_out`.
+struct ImageState {
+  double pw[kMaxK * 3];
+  double uv[kMaxK * 2];
+  float sc[kMaxK];
+  uint8_t sel[kMaxK];
+  int state;  // 1 = passed pose-NMS
+  int nsel;
+};
+
+__device__ __forceinline__ void stage_a(ImageState& S, int i, int K, const float* preds_img, const float* maxval,
+                                        const float* det_score, const uint8_t* valid, const double* kp3d,
+                                        const int32_t* model_idx, int left_number, int flags, bool write_out, float* keypoints,
+                                        float* kp_score, float* proposal, uint8_t* selected) {
   const int tid = threadIdx.x;
   const bool ok_in = !valid || valid[i];
-
-  // ---- stage A: pose-NMS (n = 1) and selection
-  if (tid < K) {
-    const bool raw = flags & BP_PNP_RAW_POINTS;  // inputs are final key-points: no pose-NMS arithmetic
-    float sc = ok_in ? (raw ? 1.f : maxval[(long)i * K + tid]) : 0.f;
+  const bool raw = flags & BP_PNP_RAW_POINTS;  // inputs are final key-points: no pose-NMS arithmetic
+  for (int k = tid; k < K; k += blockDim.x) {
+    float sc = ok_in ? (raw ? 1.f : maxval[(long)i * K + k]) : 0.f;
     if (sc == 0.f) sc = 1e-5f;
-    s_sc[tid] = sc;
-    const double* mp = kp3d + ((long)(model_idx ? model_idx[i] : 0) * K + tid) * 3;
-    s_pw[3 * tid] = mp[0];
-    s_pw[3 * tid + 1] = mp[1];
-    s_pw[3 * tid + 2] = mp[2];
+    S.sc[k] = sc;
+    const double* mp = kp3d + ((long)(model_idx ? model_idx[i] : 0) * K + k) * 3;
+    S.pw[3 * k] = mp[0];
+    S.pw[3 * k + 1] = mp[1];
+    S.pw[3 * k + 2] = mp[2];
     const float shift = raw ? 0.f : 0.3f;
-    const float kx = ok_in ? __fsub_rn(preds_img[((long)i * K + tid) * 2], shift) : 0.f;
-    const float ky = ok_in ? __fsub_rn(preds_img[((long)i * K + tid) * 2 + 1], shift) : 0.f;
-    s_uv[2 * tid] = (double)kx;
-    s_uv[2 * tid + 1] = (double)ky;
-    keypoints[((long)i * K + tid) * 2] = kx;
-    keypoints[((long)i * K + tid) * 2 + 1] = ky;
-    kp_score[(long)i * K + tid] = sc;
+    const float kx = ok_in ? __fsub_rn(preds_img[((long)i * K + k) * 2], shift) : 0.f;
+    const float ky = ok_in ? __fsub_rn(preds_img[((long)i * K + k) * 2 + 1], shift) : 0.f;
+    S.uv[2 * k] = (double)kx;
+    S.uv[2 * k + 1] = (double)ky;
+    if (write_out) {
+      keypoints[((long)i * K + k) * 2] = kx;
+      keypoints[((long)i * K + k) * 2 + 1] = ky;
+      kp_score[(long)i * K + k] = sc;
+    }
   }
   __syncthreads();
-  if (tid < K) {
+  for (int k = tid; k < K; k += blockDim.x) {
     // delete arg-min (first on ties) until left_number remain  <=>  drop the (K - left) lowest by (score, index)
     int rank = 0;
-    const float me = s_sc[tid];
-    for (int j = 0; j < K; ++j) rank += (s_sc[j] < me || (s_sc[j] == me && j < tid)) ? 1 : 0;
+    const float me = S.sc[k];
+    for (int j = 0; j < K; ++j) rank += (S.sc[j] < me || (S.sc[j] == me && j < k)) ? 1 : 0;
     const int drop = K > left_number ? K - left_number : 0;
-    s_sel[tid] = rank >= drop ? 1 : 0;
+    S.sel[k] = rank >= drop ? 1 : 0;
   }
   if (tid == 0) {
-    float mx = s_sc[0], sum = 0.f;
+    float mx = S.sc[0], sum = 0.f;
     for (int j = 0; j < K; ++j) {
-      mx = fmaxf(mx, s_sc[j]);
-      sum = __fadd_rn(sum, s_sc[j]);
+      mx = fmaxf(mx, S.sc[j]);
+      sum = __fadd_rn(sum, S.sc[j]);
     }
-    const bool pass = ok_in && ((flags & BP_PNP_RAW_POINTS) || !(mx < 0.3f));
-    s_state = pass ? 1 : 0;
-    proposal[i] = pass ? __fadd_rn(__fadd_rn(__fdiv_rn(sum, (float)K), det_score ? det_score[i] : 0.f), __fmul_rn(1.25f, mx)) : 0.f;
+    const bool pass = ok_in && (raw || !(mx < 0.3f));
+    S.state = pass ? 1 : 0;
+    if (write_out)
+      proposal[i] = pass ? __fadd_rn(__fadd_rn(__fdiv_rn(sum, (float)K), det_score ? det_score[i] : 0.f), __fmul_rn(1.25f, mx)) : 0.f;
   }
   __syncthreads();
   if (tid == 0) {
     int c = 0;
-    for (int j = 0; j < K; ++j) c += s_sel[j];
-    s_nsel = c;
+    for (int j = 0; j < K; ++j) c += S.sel[j];
+    S.nsel = c;
   }
-  if (tid < K) {
-    selected[(long)i * K + tid] = s_state ? s_sel[tid] : 0;
-    s_inl[tid] = 0;
-  }
+  if (write_out)
+    for (int k = tid; k < K; k += blockDim.x) selected[(long)i * K + k] = S.state ? S.sel[k] : 0;
   __syncthreads();
+}
 
-  const bool run = s_state == 1 && s_nsel >= 4 && !(flags & BP_PNP_NMS_ONLY);
-  const bool ransac = run && mode == 0 && s_nsel >= 6;
+__global__ void __launch_bounds__(kHypPerCta * 16)
+pnp_hypotheses_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
+                      const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d,
+                      const int32_t* __restrict__ model_idx, double fx, double fy, double cx, double cy, int left_number, int mode,
+                      int flags, double thr2, int n_hyp, uint32_t seed, float* __restrict__ keypoints,
+                      float* __restrict__ kp_score, float* __restrict__ proposal, uint8_t* __restrict__ selected,
+                      double* __restrict__ hyp /* [images][kMaxHyp][kHypRow] */) {
+  __shared__ ImageState S;
+  __shared__ double s_A[kHypPerCta][144];
+  __shared__ double s_V[kHypPerCta][144];
 
-  // ---- stage B: hypotheses (RANSAC: one 5-point EPnP per thread; all-points mode: thread 0 solves all selected)
-  if (tid < kMaxHyp) s_cnt[tid] = -1;
-  __syncthreads();
-  if (run && (ransac ? tid < n_hyp : tid == 0)) {
+  const int i = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int g = tid >> 4;                    // hypothesis slot inside the CTA
+  const int gl = tid & 15;
+  const int h = blockIdx.x * kHypPerCta + g;  // hypothesis index
+  stage_a(S, i, K, preds_img, maxval, det_score, valid, kp3d, model_idx, left_number, flags, blockIdx.x == 0, keypoints, kp_score,
+          proposal, selected);
+
+  const bool run = S.state == 1 && S.nsel >= 4 && !(flags & BP_PNP_NMS_ONLY);
+  const bool ransac = run && mode == 0 && S.nsel >= 6;
+  double* row = hyp + ((long)i * kMaxHyp + h) * kHypRow;
+  bool solved = false;
+  int cnt = 0;
+  double tot = 0.0;
+  double R[9], t[3];
+  if (run && h < kMaxHyp && (ransac ? h < n_hyp : h == 0)) {
     int pool[kMaxK];
     int m = 0;
     for (int j = 0; j < K; ++j)
-      if (s_sel[j]) pool[m++] = j;
+      if (S.sel[j]) pool[m++] = j;
     if (ransac) {
-      bp::pnp::sample_subset(pool, m, tid, seed, 5);
+      bp::pnp::sample_subset(pool, m, h, seed, 5);
       m = 5;
     }
-    double R[9], t[3];
-    if (bp::pnp::epnp(s_pw, s_uv, pool, m, fx, fy, cx, cy, R, t)) {
-      int cnt = m;
-      double tot = 0.0;
-      if (ransac) bp::pnp::score_hypothesis(R, t, s_pw, s_uv, s_sel, K, fx, fy, cx, cy, thr2, &cnt, &tot);
-      s_cnt[tid] = cnt;
-      s_tot[tid] = tot;
-      for (int k = 0; k < 9; ++k) s_R[tid * 9 + k] = R[k];
-      for (int k = 0; k < 3; ++k) s_t[tid * 3 + k] = t[k];
+    GroupEig12 eig{s_A[g], s_V[g], 0xFFFFu << (16 * ((tid >> 4) & 1)), gl};
+    if (bp::pnp::epnp(eig, S.pw, S.uv, pool, m, fx, fy, cx, cy, R, t)) {
+      solved = true;
+      cnt = m;
+      if (ransac) bp::pnp::score_hypothesis(R, t, S.pw, S.uv, S.sel, K, fx, fy, cx, cy, thr2, &cnt, &tot);
     }
   }
-  __syncthreads();
+  if (gl == 0 && h < kMaxHyp) {
+    row[0] = solved ? (double)cnt : -1.0;
+    row[1] = tot;
+    if (solved) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) row[2 + k] = R[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) row[11 + k] = t[k];
+    }
+  }
+}
 
-  // ---- stage C + D (warp 0): pick the consensus winner, then alternate {classify points against the current
-  // pose, LM refit on the consensus set} until the set is stable (at most BP_PNP_LO_ROUNDS refits)
-  if (tid < 32) {
-    int bc = -1, bh = 0x7fffffff;
-    double bt = INFINITY;
-    for (int h = tid; h < kMaxHyp; h += 32) {
-      const int c = s_cnt[h];
-      if (c < 0) continue;
-      const double tt = s_tot[h];
-      if (c > bc || (c == bc && (tt < bt || (tt == bt && h < bh)))) {
-        bc = c;
-        bt = tt;
-        bh = h;
-      }
+__global__ void __launch_bounds__(32)
+pnp_refine_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const uint8_t* __restrict__ valid, int K,
+                  const double* __restrict__ kp3d, const int32_t* __restrict__ model_idx, double fx, double fy, double cx, double cy,
+                  int left_number, int mode, int flags, double thr2, int n_hyp, const double* __restrict__ hyp,
+                  double* __restrict__ R_out, double* __restrict__ t_out, uint8_t* __restrict__ inlier, int32_t* __restrict__ status) {
+  __shared__ ImageState S;
+  __shared__ uint8_t s_inl[kMaxK];
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x;
+  stage_a(S, i, K, preds_img, maxval, nullptr, valid, kp3d, model_idx, left_number, flags, false, nullptr, nullptr, nullptr, nullptr);
+  for (int k = tid; k < K; k += 32) s_inl[k] = 0;
+  __syncwarp();
+
+  const bool run = S.state == 1 && S.nsel >= 4 && !(flags & BP_PNP_NMS_ONLY);
+  const bool ransac = run && mode == 0 && S.nsel >= 6;
+  const int nh = run ? (ransac ? n_hyp : 1) : 0;
+
+  // consensus winner: most inliers, then smallest summed squared error, then lowest hypothesis index
+  int bc = -1, bh = 0x7fffffff;
+  double bt = INFINITY;
+  const double* rows = hyp + (long)i * kMaxHyp * kHypRow;
+  for (int h = tid; h < nh; h += 32) {
+    const int c = (int)rows[h * kHypRow];
+    if (c < 0) continue;
+    const double tt = rows[h * kHypRow + 1];
+    if (c > bc || (c == bc && (tt < bt || (tt == bt && h < bh)))) {
+      bc = c;
+      bt = tt;
+      bh = h;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-      const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
-      const int oh = __shfl_xor_sync(0xffffffffu, bh, o);
-      if (oc > bc || (oc == bc && (ot < bt || (ot == bt && oh < bh)))) {
-        bc = oc;
-        bt = ot;
-        bh = oh;
-      }
-    }
-    bool ok = run && bc >= 4;
-    double R[9], t[3];
-    for (int k = 0; k < 9; ++k) R[k] = ok ? s_R[bh * 9 + k] : 0.0;
-    for (int k = 0; k < 3; ++k) t[k] = ok ? s_t[bh * 3 + k] : 0.0;
-    if (ok) {
-      WarpLanes ln;
-      for (int round = 0; round < BP_PNP_LO_ROUNDS; ++round) {
-        int changed = 0, cnt = 0;
-        for (int j = tid; j < K; j += 32) {
-          const uint8_t in = s_sel[j] && (!ransac || bp::pnp::within_threshold(R, t, s_pw, s_uv, j, fx, fy, cx, cy, thr2)) ? 1 : 0;
-          changed |= in != s_inl[j];
-          s_inl[j] = in;
-          cnt += in;
-        }
-        __syncwarp();
-        changed = __any_sync(0xffffffffu, changed);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (round > 0 && !changed) break;
-        if (cnt < 4) {
-          ok = false;
-          break;
-        }
-        bp::pnp::lm_refine(ln, R, t, s_pw, s_uv, s_inl, K, fx, fy, cx, cy, 50);
-        if (!ransac) break;
-      }
-    }
-    if (tid == 0) {
-      for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = ok ? R[k] : 0.0;
-      for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = ok ? t[k] : 0.0;
-      status[i] = s_state == 0 ? 0 : ((ok || (flags & BP_PNP_NMS_ONLY)) ? 1 : -1);
-    }
-    if (!ok)
-      for (int j = tid; j < K; j += 32) s_inl[j] = 0;
   }
-  __syncthreads();
-  if (tid < K) inlier[(long)i * K + tid] = s_inl[tid];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+    const double ot = __shfl_xor_sync(0xffffffffu, bt, o);
+    const int oh = __shfl_xor_sync(0xffffffffu, bh, o);
+    if (oc > bc || (oc == bc && (ot < bt || (ot == bt && oh < bh)))) {
+      bc = oc;
+      bt = ot;
+      bh = oh;
+    }
+  }
+  bool ok = run && bc >= 4;
+  double R[9], t[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = ok ? rows[bh * kHypRow + 2 + k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = ok ? rows[bh * kHypRow + 11 + k] : 0.0;
+  if (ok) {
+    // alternate {classify points against the current pose, LM refit on the consensus set} until the set is stable
+    WarpLanes ln;
+    for (int round = 0; round < BP_PNP_LO_ROUNDS; ++round) {
+      int changed = 0, cnt = 0;
+      for (int j = tid; j < K; j += 32) {
+        const uint8_t in = S.sel[j] && (!ransac || bp::pnp::within_threshold(R, t, S.pw, S.uv, j, fx, fy, cx, cy, thr2)) ? 1 : 0;
+        changed |= in != s_inl[j];
+        s_inl[j] = in;
+        cnt += in;
+      }
+      __syncwarp();
+      changed = __any_sync(0xffffffffu, changed);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (round > 0 && !changed) break;
+      if (cnt < 4) {
+        ok = false;
+        break;
+      }
+      bp::pnp::lm_refine(ln, R, t, S.pw, S.uv, s_inl, K, fx, fy, cx, cy, 50);
+      if (!ransac) break;
+    }
+  }
+  if (tid == 0) {
+    for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = ok ? R[k] : 0.0;
+    for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = ok ? t[k] : 0.0;
+    status[i] = S.state == 0 ? 0 : ((ok || (flags & BP_PNP_NMS_ONLY)) ? 1 : -1);
+  }
+  __syncwarp();
+  for (int j = tid; j < K; j += 32) inlier[(long)i * K + j] = ok ? s_inl[j] : 0;
 }
 
 }  // namespace
@@ -204,9 +347,25 @@ extern "C" int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* ma
   if (K < 1 || K > kMaxK) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pose_pnp: K must be in [1, 64]");
   if (n_hyp < 1 || n_hyp > kMaxHyp) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pose_pnp: n_hyp must be in [1, 128]");
   if (mode != 0 && mode != 1) return bp_fail(BP_ERR_INVALID, "bp_pose_pnp: mode");
-  pose_pnp_kernel<<<n, kMaxHyp, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode, flags,
-      (double)reproj_thr * (double)reproj_thr, n_hyp, seed, keypoints, kp_score, proposal, selected, R, t, inlier, status);
+  // hypothesis scratch (grow-only; (re)allocated at most once per batch size, outside steady state)
+  const size_t need = (size_t)n * kMaxHyp * kHypRow * sizeof(double);
+  if (e->pnp_scratch_bytes < need) {
+    if (e->pnp_scratch) cudaFree(e->pnp_scratch);
+    if (cudaMalloc(&e->pnp_scratch, need) != cudaSuccess) {
+      e->pnp_scratch = nullptr;
+      e->pnp_scratch_bytes = 0;
+      return bp_fail(BP_ERR_CUDA, "bp_pose_pnp: scratch allocation failed");
+    }
+    e->pnp_scratch_bytes = need;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const double thr2 = (double)reproj_thr * (double)reproj_thr;
+  const int groups = mode == 0 ? (n_hyp + kHypPerCta - 1) / kHypPerCta : 1;
+  pnp_hypotheses_kernel<<<dim3(groups, n), kHypPerCta * 16, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0],
+                                                                   cam[1], cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed,
+                                                                   keypoints, kp_score, proposal, selected, e->pnp_scratch);
+  pnp_refine_kernel<<<n, 32, 0, st>>>(preds_img, maxval, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode,
+                                      flags, thr2, n_hyp, e->pnp_scratch, R, t, inlier, status);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }

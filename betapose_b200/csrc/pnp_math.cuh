@@ -194,10 +194,22 @@ BP_HD_NOINLINE void horn_rotation(const double S[9], double* R) {
 }
 
 // ------------------------------------------------------------------ EPnP
+// Eigen-solver policy for the 12 x 12 M^T M: `solve` destroys A, fills w with the eigenvalues and returns the
+// eigenvectors (columns, row-major 12 x 12).  SerialEig12 is the single-thread cyclic Jacobi (host build, tests);
+// the device kernel passes a policy that runs the rotations of one Jacobi round on 16 cooperating lanes (pnp.cu).
+struct SerialEig12 {
+  double V[144];
+  BP_HD const double* solve(double* A, double* w) {
+    jacobi_eig<12>(A, V, w);
+    return V;
+  }
+};
+
 // pw[n][3] world points, uv[n][2] pixels, ids[0..n) selects the correspondences.  Returns false on a
 // degenerate configuration.  Scratch lives on the caller's stack/local memory (~3.5 KB).
-BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* ids, int n, double fx, double fy, double cx,
-                         double cy, double* R_out, double* t_out
+template <class Eig>
+BP_HD_NOINLINE bool epnp(Eig& eig, const double* pw_all, const double* uv_all, const int* ids, int n, double fx, double fy,
+                         double cx, double cy, double* R_out, double* t_out
 #ifdef BP_PNP_DEBUG
                          , double* dbg
 #endif
@@ -264,8 +276,8 @@ BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* 
   }
   for (int r = 0; r < 12; ++r)
     for (int c = 0; c < r; ++c) MtM[r * 12 + c] = MtM[c * 12 + r];
-  double V12[144], w12[12];
-  jacobi_eig<12>(MtM, V12, w12);
+  double w12[12];
+  const double* V12 = eig.solve(MtM, w12);
   // the four eigenvectors of smallest eigenvalue, v[0] = smallest
   int order[4];
   {
@@ -397,6 +409,14 @@ BP_HD_NOINLINE bool epnp(const double* pw_all, const double* uv_all, const int* 
   }
   return have;
 }
+
+#ifndef BP_PNP_DEBUG
+BP_HD bool epnp(const double* pw_all, const double* uv_all, const int* ids, int n, double fx, double fy, double cx, double cy,
+                double* R_out, double* t_out) {
+  SerialEig12 eig;
+  return epnp(eig, pw_all, uv_all, ids, n, fx, fy, cx, cy, R_out, t_out);
+}
+#endif
 
 // ------------------------------------------------------------------ Levenberg-Marquardt refit
 // Accumulate, over this lane's share of the masked points, J^T J (21 upper entries), J^T r (6) and the cost.
