@@ -25,6 +25,9 @@ constexpr int kMaxHyp = 128;
 constexpr int kHypPerCta = 8;       // x 16 lanes = 128 threads
 constexpr int kHypRow = 16;         // doubles per hypothesis in the scratch: count, total, R[9], t[3], pad
 
+// One warp, lanes over points; the 28 sums of an LM step are all-reduced by shuffles (independent chains: they
+// pipeline).  A shared-memory variant in which lane l adds up sum number l over the points measured 1.6x slower:
+// 50-long dependent fp64 add chains.
 struct WarpLanes {
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
   __device__ __forceinline__ int count() const { return 32; }
@@ -35,6 +38,11 @@ struct WarpLanes {
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       v[i] = x;
     }
+  }
+  __device__ __forceinline__ void accumulate(const double* R, const double* t, const double* pw, const double* uv,
+                                             const uint8_t* mask, int n, double fx, double fy, double cx, double cy,
+                                             double* acc) const {
+    bp::pnp::lm_accumulate(*this, R, t, pw, uv, mask, n, fx, fy, cx, cy, acc);
   }
 };
 
@@ -201,7 +209,7 @@ __device__ __forceinline__ void stage_a(ImageState& S, int i, int K, const float
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kHypPerCta * 16)
+__global__ void __launch_bounds__(kHypPerCta * 16, 4)
 pnp_hypotheses_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
                       const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d,
                       const int32_t* __restrict__ model_idx, double fx, double fy, double cx, double cy, int left_number, int mode,
