@@ -233,7 +233,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one thread: the loop is pure issue
     // overhead, so it is kept to a handful of instructions per k-block; the other 31 lanes idle at the final barrier)
-    if (lane == 0) {
+    {  // the whole warp walks the loop (uniform control flow); one elected lane issues the copies
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, ph = 0;
@@ -256,6 +256,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
           const uint32_t sa = smem_base + s * uint32_t(Cfg::STAGE_BYTES);
           const uint32_t fb = CG == 2 ? leader_addr(full0 + 8u * s) : full0 + 8u * s;
+          if (elect_one()) {
           if constexpr (CG == 2) {
             // the leader's barrier collects the bytes of both CTAs
             if (rank == 0) mbar_expect_tx_a(fb, 2 * Cfg::STAGE_BYTES);
@@ -274,6 +275,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             tma_load_2d_a(&tmB, fb, sa + uint32_t(Cfg::A_BYTES), kcol, n0);
           }
+          }
+          __syncwarp();
           kcol += BLOCK_K;
           // advance (tap, channel block) without divisions
           cb += BLOCK_K;
@@ -293,7 +296,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread; pairs: the leader CTA's)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the whole warp walks the loop (uniform control flow); one elected lane issues
       constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N, 128 * CG);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
@@ -311,25 +314,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t da = da0 + uint64_t(s * uint32_t(Cfg::STAGE_BYTES >> 4));
           const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
           // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
-          if constexpr (CG == 2) {
-            umma_f16_cg2(tmem_acc, da, db, idesc, kb ? 1u : 0u);
+          if (elect_one()) {
+            if constexpr (CG == 2) {
+              umma_f16_cg2(tmem_acc, da, db, idesc, kb ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BLOCK_K / 16; ++k)
-              umma_f16_cg2(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
-            umma_commit_cg2(empty0 + 8u * s);  // frees this stage in BOTH CTAs
-          } else {
-            umma_f16(tmem_acc, da, db, idesc, kb ? 1u : 0u);
+              for (int k = 1; k < BLOCK_K / 16; ++k)
+                umma_f16_cg2(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
+              umma_commit_cg2(empty0 + 8u * s);  // frees this stage in BOTH CTAs
+            } else {
+              umma_f16(tmem_acc, da, db, idesc, kb ? 1u : 0u);
 #pragma unroll
-            for (int k = 1; k < BLOCK_K / 16; ++k) umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
-            umma_commit_a(empty0 + 8u * s);  // frees this smem stage once the MMAs above have read it
+              for (int k = 1; k < BLOCK_K / 16; ++k) umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
+              umma_commit_a(empty0 + 8u * s);  // frees this smem stage once the MMAs above have read it
+            }
           }
+          __syncwarp();
           if (++s == STAGES) {
             s = 0;
             ph ^= 1u;
           }
         }
-        if constexpr (CG == 2) umma_commit_cg2(tfull0 + 8u * acc);  // accumulators complete -> both epilogues
-        else umma_commit_a(tfull0 + 8u * acc);
+        if (elect_one()) {
+          if constexpr (CG == 2) umma_commit_cg2(tfull0 + 8u * acc);  // accumulators complete -> both epilogues
+          else umma_commit_a(tfull0 + 8u * acc);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -408,6 +408,15 @@ int main(int argc, char** argv) {
   const bool probe_only = argc > 1 && !strcmp(argv[1], "probe");
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   int fails = 0;
+  if (argc > 1 && !strcmp(argv[1], "small")) {
+    // the small-tile, bandwidth-class layers only (profiling target)
+    fails += run_stem_case("stem 3x3 s1 3->32 @416 B64", 64, 416, 416, 3, 1, 1, 32, ACT_LEAKY, 3);
+    Case c1 = {"Y 3x3 32->64 s2 @416 bn64", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 3};
+    Case c2 = {"Y 1x1 64->32 @208", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 3};
+    fails += run_case(c1);
+    fails += run_case(c2);
+    return fails ? 1 : 0;
+  }
 
   if (!probe_only) {
     // 1) plain GEMM path (2-D TMA only) first: isolates descriptor/idesc/TMEM plumbing from im2col
