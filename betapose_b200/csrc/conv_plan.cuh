@@ -194,6 +194,14 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.out_pitch = d.out_pitch;
   a.out_coff = d.out_coff;
   a.res_pitch = d.res_pitch;
+  if (M >= (1 << 26) || P * Q >= (1 << 18) || (long)m_tiles * n_tiles_live >= (1 << 26)) {
+    if (err) *err = "problem too large for the kernel's tile arithmetic (M < 2^26 pixels, P*Q < 2^18)";
+    return false;
+  }
+  auto magic = [](int dv) { return (unsigned long long)(((1ull << 44) + (unsigned long long)dv - 1) / (unsigned long long)dv); };
+  a.mul_nt = magic(n_tiles_live);
+  a.mul_pq = magic(P * Q);
+  a.mul_q = magic(Q);
   a.bias = d.bias;
   a.res = d.res;
   a.out = d.out;

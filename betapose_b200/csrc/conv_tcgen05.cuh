@@ -47,10 +47,18 @@ struct ConvArgs {
   int out_pitch;  // elements between consecutive output pixels
   int out_coff;   // channel offset inside the output pixel
   int res_pitch;
+  // exact division of x < 2^26 by a constant d < 2^18 (quotient < 2^20) as (x * ceil(2^44 / d)) >> 44 (host: conv_plan_build); the tile
+  // walk decodes (tile -> m-tile, n-tile) and (pixel -> image, row, column) once per tile, and on the 1-3 k-block
+  // layers a hardware-less integer division (~25 instructions) per decode is a visible share of the producer's time
+  unsigned long long mul_nt, mul_pq, mul_q;
   const float* bias;   // [n_tiles * BLOCK_N], zero padded
   const __half* res;   // residual, same pixel order as the output, res_pitch elements per pixel
   void* out;
 };
+
+__device__ __forceinline__ int fast_div(int x, unsigned long long mul) {
+  return (int)(((unsigned long long)(unsigned)x * mul) >> 44);
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -238,15 +246,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, ph = 0;
       for (int tile = cl_id; tile < total_tiles; tile += cl_num) {
-        const int pm_tile = tile / p.n_tiles;
+        const int pm_tile = fast_div(tile, p.mul_nt);
         const int n0 = (tile - pm_tile * p.n_tiles) * BLOCK_N + int(rank) * (BLOCK_N / CG);  // this CTA's share of B
         const int m0 = (pm_tile * CG + int(rank)) * Cfg::BLOCK_M;
         int w0 = 0, h0 = 0, img = 0;
         if (p.a_im2col == 1) {
           const int pq = p.P * p.Q;
-          img = m0 / pq;
+          img = fast_div(m0, p.mul_pq);
           const int rem = m0 - img * pq;
-          const int op = rem / p.Q;
+          const int op = fast_div(rem, p.mul_q);
           const int oq = rem - op * p.Q;
           w0 = oq * p.stride - p.pad_w;
           h0 = op * p.stride - p.pad;
@@ -353,10 +361,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int it = 0;
     uint32_t chunk_ctr = 0;                  // running chunk index: ring buffer = chunk_ctr % NBUF
     float bias_next = (cl_id < total_tiles && et < BLOCK_N) ? __ldg(p.bias + (cl_id % p.n_tiles) * BLOCK_N + et) : 0.f;
+    const uint32_t tfull_wait0 = smem_u32(&tmem_full_bar[0]);
     const uint32_t tempty_arrive0 = CG == 2 ? leader_addr(smem_u32(&tmem_empty_bar[0])) : smem_u32(&tmem_empty_bar[0]);
     for (int tile = cl_id; tile < total_tiles; tile += cl_num, ++it) {
-      const int n_tile = tile % p.n_tiles;
-      const int m0 = ((tile / p.n_tiles) * CG + int(rank)) * Cfg::BLOCK_M;
+      const int pm_tile = fast_div(tile, p.mul_nt);
+      const int n_tile = tile - pm_tile * p.n_tiles;
+      const int m0 = (pm_tile * CG + int(rank)) * Cfg::BLOCK_M;
       const int n0 = n_tile * BLOCK_N;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
@@ -366,7 +376,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (et < BLOCK_N) bias_s[et] = bias_next;
       {  // bias of the next tile: in flight during this tile's epilogue
         const int nt = tile + cl_num;
-        if (nt < total_tiles && et < BLOCK_N) bias_next = __ldg(p.bias + (nt % p.n_tiles) * BLOCK_N + et);
+        if (nt < total_tiles && et < BLOCK_N) bias_next = __ldg(p.bias + (nt - fast_div(nt, p.mul_nt) * p.n_tiles) * BLOCK_N + et);
       }
       if (p.tma_store && use_res && leader) {
         // residual tile -> ring buffers (one TMA load per chunk); the stores that last used them must have read them
@@ -379,7 +389,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       bar_sync_named(1, Cfg::EPI_THREADS);  // bias visible
 
-      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      mbar_wait_a(tfull_wait0 + 8u * acc, acc_ph);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + uint32_t(acc * BLOCK_N) + ((uint32_t(q4) * 32u) << 16);
 
@@ -423,9 +433,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int img = 0, op = 0, oq = 0;
         if (p.store_mode != STORE_PLAIN) {
           const int pq = p.P * p.Q;
-          img = row / pq;
+          img = fast_div(row, p.mul_pq);
           const int rem = row - img * pq;
-          op = rem / p.Q;
+          op = fast_div(rem, p.mul_q);
           oq = rem - op * p.Q;
         }
         const int live32 = min(BLOCK_N / 32, (p.Cout - n0 + 31) / 32);
