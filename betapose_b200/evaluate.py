@@ -70,10 +70,14 @@ def main(argv=None):
                          left_number=left, conf=o.confidence, pnp_mode=mode)
     recs = []
     t0 = time.time()
-    for b0 in range(lo, hi, B):
-        b1 = min(hi, b0 + B)
-        frames = synth.synth_frames(b1 - b0, seed=b0) if o.synthetic else _load_frames(names[b0:b1])
-        recs.append(eng.run(frames, image_index0=b0).copy())
+
+    def batches():  # frame decoding / generation of batch i+1 overlaps the GPU work of batch i (BetaposeEngine.run_stream)
+        for b0 in range(lo, hi, B):
+            b1 = min(hi, b0 + B)
+            yield synth.synth_frames(b1 - b0, seed=b0) if o.synthetic else _load_frames(names[b0:b1])
+
+    for rec in eng.run_stream(batches(), graph=True, image_index0=lo):
+        recs.append(rec)
     torch.cuda.synchronize()
     dt = time.time() - t0
     mine = np.concatenate(recs) if recs else np.zeros(0, stages.RECORD_DTYPE)

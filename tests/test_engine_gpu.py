@@ -161,3 +161,16 @@ def test_evaluate_cli_synthetic(tmp_path):
         assert set(e) == {"image_id", "cam_R", "cam_t", "keypoints", "score"}
         assert len(e["cam_R"]) == 9 and len(e["cam_t"]) == 3 and len(e["keypoints"]) == 150
         assert e["image_id"].startswith("synthetic_")
+
+
+def test_run_stream_matches_run(engine, frames8):
+    """The pipelined streaming API (side-stream uploads, graph replay, ragged last batch) returns exactly what the
+    plain per-batch call returns, in order, with global image indices."""
+    batches = [frames8[0:3], frames8[3:8], frames8[1:2]]
+    ref = [engine.run(b, image_index0=i0).copy() for b, i0 in zip(batches, (10, 13, 18))]
+    got = list(engine.run_stream(iter(batches), graph=True, image_index0=10))
+    assert len(got) == 3
+    for g, r in zip(got, ref):
+        assert g.dtype == r.dtype and len(g) == len(r)
+        for f in g.dtype.names:
+            assert np.array_equal(g[f], r[f]), f
