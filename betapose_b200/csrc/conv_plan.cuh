@@ -28,6 +28,7 @@ struct ConvDesc {
   int out_pitch = 0, out_coff = 0, out_f32 = 0, store_mode = STORE_PLAIN;
   int force_block_n = 0;  // 0 = heuristic
   int force_cg = 0;       // 0 = heuristic, 1 = single CTA, 2 = CTA pairs (cta_group::2)
+  int force_mt = 0;       // 0 = heuristic, 1 = 128-pixel tiles, 2 = 256-pixel tiles (narrow layers)
   int force_stages = 0;   // kept for the harness; the stage count follows from the tile configuration
   int num_sms = 148;
   double real_k = 0;      // reduction length that counts as work (0 = R*S*C); the stems pad K with zero weights
@@ -39,17 +40,17 @@ struct ConvPlan {
   alignas(64) CUtensorMap tmOut;  // valid when args.tma_store
   alignas(64) CUtensorMap tmRes;  // valid when args.tma_store && residual
   ConvArgs args;
-  int block_n = 0, block_k = 0, stages = 0, grid = 0, cg = 1;
+  int block_n = 0, block_k = 0, stages = 0, grid = 0, cg = 1, mt = 1;
   int P = 0, Q = 0;
   double flops = 0;
 };
 
-template <int BN, int BK, int ST, int CG = 1, int NB = 4>
+template <int BN, int BK, int ST, int CG = 1, int NB = 4, int MT = 1>
 inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, BK, ST, CG, NB>;
+  using Cfg = ConvCfg<BN, BK, ST, CG, NB, MT>;
   static bool attr_done = false;  // per-instantiation; set once per process (single device per process)
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
@@ -75,13 +76,21 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB, MT>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
   if (pl.cg == 2) {
     if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 5, 2>(pl, st);
     if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, 2>(pl, st);
+    return cudaErrorInvalidConfiguration;
+  }
+  if (pl.mt == 2) {  // 256-pixel tiles (narrow layers)
+    if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 3, 1, 4, 2>(pl, st);
+    if (pl.block_n == 64 && pl.block_k == 64) return launch_cfg<64, 64, 4, 1, 4, 2>(pl, st);
+    if (pl.block_n == 32 && pl.block_k == 64) return launch_cfg<32, 64, 5, 1, 4, 2>(pl, st);
+    if (pl.block_n == 64 && pl.block_k == 32) return launch_cfg<64, 32, 8, 1, 4, 2>(pl, st);
+    if (pl.block_n == 32 && pl.block_k == 32) return launch_cfg<32, 32, 10, 1, 4, 2>(pl, st);
     return cudaErrorInvalidConfiguration;
   }
 #define BP_CASE(BN, BK, ST) \
@@ -153,25 +162,37 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
     if (err) *err = "Cout_pad must be a multiple of BLOCK_N";
     return false;
   }
-  const int st = cg == 2 ? (bn == 256 ? 5 : 6)
-                         : (block_k == 64 ? (bn == 256 ? 3 : bn == 128 ? 5 : bn == 64 ? 6 : 9) : (bn == 64 ? 13 : 16));
+  // 256-pixel tiles for the narrow, TMA-stored layers with plenty of tiles: they are bound by the issue overhead per
+  // tile and per k-block of the producer / MMA warps, which a 256-row tile halves per pixel
+  const bool tma_store_ok = !d.out_f32 && d.store_mode == STORE_PLAIN && d.Cout % 8 == 0 && d.out_pitch % 8 == 0 &&
+                            d.out_coff % 8 == 0 && (!d.res || d.res_pitch % 8 == 0);
+  // (measured: stem 0.54 -> 0.41 ms, 3x3 32->64 0.35 -> 0.21 ms, 3x3 64->64 0.050 -> 0.035 ms, 3x3 64->128 @104 0.125 -> 0.113 ms;
+  // no gain on 128-wide 1x1 layers)
+  int mt = d.force_mt ? d.force_mt
+                      : ((cg == 1 && tma_store_ok && m_tiles >= 4 * d.num_sms && (bn <= 64 || (bn == 128 && block_k == 64 && num_kb >= 9))) ? 2 : 1);
+  if (mt == 2 && (cg != 1 || bn > 128 || (bn == 128 && block_k != 64) || !tma_store_ok)) mt = 1;
+  const int st = mt == 2 ? (block_k == 64 ? (bn == 128 ? 3 : bn == 64 ? 4 : 5) : (bn == 64 ? 8 : 10))
+                 : cg == 2 ? (bn == 256 ? 5 : 6)
+                           : (block_k == 64 ? (bn == 256 ? 3 : bn == 128 ? 5 : bn == 64 ? 6 : 9) : (bn == 64 ? 13 : 16));
+  const int m_tiles_cta = (M + 128 * mt - 1) / (128 * mt);  // tiles as the kernel walks them
 
   pl->block_n = bn;
   pl->block_k = block_k;
   pl->stages = st;
   pl->cg = cg;
+  pl->mt = mt;
   pl->P = P;
   pl->Q = Q;
   // tiles whose channels are all padding are never launched
   const int n_tiles_live = (d.Cout + bn - 1) / bn;
   // persistent: one CTA per SM (pairs: one cluster of 2 per TPC)
-  pl->grid = cg == 2 ? 2 * std::min(((m_tiles + 1) / 2) * n_tiles_live, d.num_sms / 2) : std::min(m_tiles * n_tiles_live, d.num_sms);
+  pl->grid = cg == 2 ? 2 * std::min(((m_tiles + 1) / 2) * n_tiles_live, d.num_sms / 2) : std::min(m_tiles_cta * n_tiles_live, d.num_sms);
   pl->flops = 2.0 * M * (double)d.Cout * (d.real_k > 0 ? d.real_k : (double)K);
 
   ConvArgs& a = pl->args;
   a.M = M;
   a.n_tiles = n_tiles_live;
-  a.m_tiles = m_tiles;
+  a.m_tiles = m_tiles_cta;
   a.num_kb = num_kb;
   a.a_im2col = matrix ? 0 : 1;
   a.P = P;
@@ -207,11 +228,11 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.out = d.out;
 
   if (matrix) {
-    if (!make_tmap_2d(api, &pl->tmA, d.x, (uint64_t)M, (uint64_t)d.C, (uint64_t)d.x_pitch, 128, block_k, err))
+    if (!make_tmap_2d(api, &pl->tmA, d.x, (uint64_t)M, (uint64_t)d.C, (uint64_t)d.x_pitch, 128 * mt, block_k, err))
       return false;
   } else {
     if (!make_tmap_im2col(api, &pl->tmA, d.x, d.N, d.H, d.W, d.C, d.x_pitch, d.R, d.S, d.stride, d.pad, pad_w, block_k, err,
-                          d.x_row_pitch, d.x_img_pitch))
+                          d.x_row_pitch, d.x_img_pitch, 128 * mt))
       return false;
   }
   if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn / cg, block_k, err))

@@ -74,16 +74,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // shared memory, and each CTA's TMEM receives its own 128 x BLOCK_N accumulator (so the epilogue is unchanged).
 // Per CTA and k-block that is 128*SWZ + BLOCK_N/2*SWZ bytes from L2 instead of 128*SWZ + BLOCK_N*SWZ: the L2->SM
 // fabric (~43 B/clk/SM on B200) is what bounds the single-CTA kernel on every compute-heavy layer.
-template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4>
+// MT = 2: a CTA tile is 256 pixels = two M = 128 MMAs per K step against the same B (two accumulators); one TMA load
+// stages 256 A rows.  Halves the tile count -- and with it the producer / MMA warps' per-tile and per-k-block
+// instruction overhead per pixel -- on the narrow (BLOCK_N <= 64) layers, which are bound by exactly that.
+template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1>
 struct ConvCfg {
-  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_M = 128 * MT;
   static constexpr int SWZ = BLOCK_K * 2;  // bytes per smem row == swizzle span
   static constexpr int A_BYTES = BLOCK_M * SWZ;
+  static constexpr int A_SUB_BYTES = 128 * SWZ;  // one M = 128 operand
   static constexpr int B_BYTES = (BLOCK_N / CG) * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CHUNK = BLOCK_N >= 64 ? 64 : 32;  // output channels per epilogue chunk / TMA store box
   static constexpr int OUT_SWZ = CHUNK * 2;
-  static constexpr int CHUNK_BYTES = BLOCK_M * OUT_SWZ;
+  static constexpr int CHUNK_BYTES = 128 * OUT_SWZ;
   static constexpr int N_CHUNKS = BLOCK_N / CHUNK;
   static constexpr int NBUF = NB;                      // ring of chunk buffers: residual lands in it, result leaves from it
   static constexpr int EPI_BYTES = NBUF * CHUNK_BYTES;
@@ -93,7 +97,7 @@ struct ConvCfg {
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + NBUF) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
   static constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, each takes half of a chunk's columns
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;
@@ -169,12 +173,13 @@ __device__ __forceinline__ void epi_dispatch(int act, int res_mode, const uint32
 #undef BP_EPI
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1>
 __global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB, MT>;
+  static_assert(MT == 1 || (MT == 2 && CG == 1 && BLOCK_N <= 128 && 2 * (BLOCK_N / (BLOCK_N >= 64 ? 64 : 32)) <= NB), "256-pixel tiles: single-CTA layers up to 128 wide");
   static_assert(CG == 1 || (CG == 2 && BLOCK_N >= 64), "pairs need BLOCK_N >= 64");
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
@@ -315,7 +320,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t acc = it & 1u;
         mbar_wait_a(tempty0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue(s) drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * uint32_t(BLOCK_N);
+        const uint32_t tmem_acc = tmem_base + acc * uint32_t(MT * BLOCK_N);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait_a(full0 + 8u * s, ph);
           tc_fence_after();
@@ -330,9 +335,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_f16_cg2(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
               umma_commit_cg2(empty0 + 8u * s);  // frees this stage in BOTH CTAs
             } else {
-              umma_f16(tmem_acc, da, db, idesc, kb ? 1u : 0u);
 #pragma unroll
-              for (int k = 1; k < BLOCK_K / 16; ++k) umma_f16(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+#pragma unroll
+                for (int sub = 0; sub < MT; ++sub)
+                  umma_f16(tmem_acc + uint32_t(sub * BLOCK_N), da + uint64_t(2 * k + sub * (Cfg::A_SUB_BYTES >> 4)),
+                           db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+              }
               umma_commit_a(empty0 + 8u * s);  // frees this smem stage once the MMAs above have read it
             }
           }
@@ -380,20 +389,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (p.tma_store && use_res && leader) {
         // residual tile -> ring buffers (one TMA load per chunk); the stores that last used them must have read them
-        bulk_wait_group_read<(Cfg::NBUF > N_CHUNKS ? Cfg::NBUF - N_CHUNKS : 0)>();  // (residual layers need NBUF >= N_CHUNKS: planner)
-        for (int c = 0; c < live; ++c) {
-          const uint32_t rb = (chunk_ctr + c) % Cfg::NBUF;
-          mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
-          tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, n0 + c * CHUNK, m0);
-        }
+        bulk_wait_group_read<(Cfg::NBUF > MT * N_CHUNKS ? Cfg::NBUF - MT * N_CHUNKS : 0)>();  // (residual layers need NBUF >= MT * N_CHUNKS: planner)
+        for (int sub = 0; sub < MT; ++sub)
+          for (int c = 0; c < live; ++c) {
+            const uint32_t rb = (chunk_ctr + sub * live + c) % Cfg::NBUF;
+            mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
+            tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, n0 + c * CHUNK, m0 + sub * 128);
+          }
       }
       bar_sync_named(1, Cfg::EPI_THREADS);  // bias visible
 
       mbar_wait_a(tfull_wait0 + 8u * acc, acc_ph);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + uint32_t(acc * BLOCK_N) + ((uint32_t(q4) * 32u) << 16);
+      const uint32_t tmem_acc0 = tmem_base + uint32_t(acc * MT * BLOCK_N) + ((uint32_t(q4) * 32u) << 16);
 
       if (p.tma_store) {
+#pragma unroll 1
+        for (int sub = 0; sub < MT; ++sub) {
+        const uint32_t tmem_acc = tmem_acc0 + uint32_t(sub * BLOCK_N);
         for (int c = 0; c < live; ++c, ++chunk_ctr) {
           const uint32_t bsel = chunk_ctr % Cfg::NBUF;
           uint32_t a[32];
@@ -403,7 +416,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_32x16(tmem_acc + uint32_t(c * CHUNK + hsel * 16), a);
           }
           tmem_ld_wait();
-          if (c == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+          if (c == live - 1 && sub == MT - 1) {  // accumulators fully read: hand them back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -422,11 +435,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           bar_sync_named(1, Cfg::EPI_THREADS);
           if (leader) {
-            tma_store_2d(&tmOut, buf, n0 + c * CHUNK, m0);
+            tma_store_2d(&tmOut, buf, n0 + c * CHUNK, m0 + sub * 128);
             bulk_commit_group();
           }
         }
+        }
       } else {
+        if constexpr (MT != 1) __trap();  // 256-pixel tiles are planned for TMA-store layers only
+        const uint32_t tmem_acc = tmem_acc0;
         // -------- per-thread stores: fp32 heads, fused nearest-x2 upsample, fused PixelShuffle(2)
         const int row = m0 + row_l;
         const bool row_ok = row < p.M;

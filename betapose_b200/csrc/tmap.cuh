@@ -63,12 +63,12 @@ inline bool make_tmap_2d(TmapApi& api, CUtensorMap* out, const void* base, uint6
 
 // NHWC fp16 activation [N, H, W, C] with `pitch` elements per pixel, traversed as the im2col matrix of an
 // R x S convolution with the given stride and padding (pad_h rows above/below, pad_w columns left/right).
-// One load = 128 output pixels x block_k channels.  row_pitch / img_pitch (elements) default to the dense layout;
+// One load = `pixels` (128 or 256) output pixels x block_k channels.  row_pitch / img_pitch (elements) default to the dense layout;
 // the packed stem convolutions pass a pixel pitch SMALLER than C (overlapping "virtual pixels", see net.cu) and the
 // padded row pitch of the network-input buffer.
 inline bool make_tmap_im2col(TmapApi& api, CUtensorMap* out, const void* base, int N, int H, int W, int C,
                              int pitch, int R, int S, int stride, int pad_h, int pad_w, uint32_t block_k, std::string* err,
-                             long row_pitch = 0, long img_pitch = 0) {
+                             long row_pitch = 0, long img_pitch = 0, uint32_t pixels = 128) {
   if (row_pitch <= 0) row_pitch = (long)W * pitch;
   if (img_pitch <= 0) img_pitch = (long)H * row_pitch;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -77,7 +77,7 @@ inline bool make_tmap_im2col(TmapApi& api, CUtensorMap* out, const void* base, i
   int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = api.im2col(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
-                          upper, block_k, 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
+                          upper, block_k, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeIm2col failed: " + std::to_string((int)r);

@@ -94,6 +94,7 @@ struct Case {
   int iters = 0;  // >0: also time it
   int gather = 0;  // unused (kept so the positional initialisers below stay valid)
   int cg = 0;      // 0 = planner's choice, 1 = single CTA, 2 = CTA pairs (cta_group::2)
+  int mt = 0;      // 0 = planner's choice, 1 = 128-pixel tiles, 2 = 256-pixel tiles
 };
 
 static int run_case(const Case& cs) {
@@ -146,7 +147,7 @@ static int run_case(const Case& cs) {
   d.R = cs.R; d.S = cs.S; d.stride = cs.stride; d.pad = cs.pad; d.act = cs.act;
   d.res = dres; d.res_pitch = cs.Cout; d.res_mode = cs.res_mode;
   d.out = dout; d.out_pitch = opitch; d.out_coff = cs.out_coff; d.out_f32 = cs.out_f32; d.store_mode = cs.store_mode;
-  d.force_block_n = cs.force_bn; d.force_stages = cs.force_st; d.force_cg = cs.cg;
+  d.force_block_n = cs.force_bn; d.force_stages = cs.force_st; d.force_cg = cs.cg; d.force_mt = cs.mt;
   ConvPlan pl;
   std::string err;
   if (!conv_plan_build(g_api, &pl, d, &err)) {
@@ -220,8 +221,8 @@ static int run_case(const Case& cs) {
     CK(cudaEventElapsedTime(&t, e0, e1));
     ms = t / cs.iters;
   }
-  printf("[%-28s] bn=%3d bk=%2d st=%d cg=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", cs.name,
-         pl.block_n, pl.block_k, pl.stages, pl.cg, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
+  printf("[%-28s] bn=%3d bk=%2d st=%2d cg=%d mt=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", cs.name,
+         pl.block_n, pl.block_k, pl.stages, pl.cg, pl.mt, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
   if (bad) printf(" first_bad: m=%ld co=%ld", first_bad / cs.Cout, first_bad % cs.Cout);
   if (ms > 0) printf("  %.3f ms  %.1f TFLOP/s", ms, pl.flops / ms * 1e-9);
   printf("\n");
@@ -327,8 +328,8 @@ static int run_stem_case(const char* name, int N, int H, int W, int k, int strid
     CK(cudaEventElapsedTime(&t, e0, e1));
     ms = t / iters;
   }
-  printf("[%-28s] bn=%3d bk=%2d st=%d cg=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", name, pl.block_n,
-         pl.block_k, pl.stages, pl.cg, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
+  printf("[%-28s] bn=%3d bk=%2d st=%2d cg=%d mt=%d grid=%6d M=%7ld K=%5d  max_err=%.4g (max|ref|=%.3g) bad=%ld%s", name, pl.block_n,
+         pl.block_k, pl.stages, pl.cg, pl.mt, pl.grid, M, K, max_err, max_ref, bad, bad ? "  <-- FAIL" : "  ok");
   if (bad) printf(" first_bad: m=%ld co=%ld", first_bad / Cout, first_bad % Cout);
   if (ms > 0) printf("  %.3f ms  %.1f GB/s out", ms, (double)total * 2 / ms * 1e-6);
   printf("\n");
@@ -497,6 +498,21 @@ int main(int argc, char** argv) {
   };
   for (auto& c : pairs) fails += run_case(c);
 
+  // 256-pixel tiles (MT = 2): ragged last tile (second half empty / partial), residual, BK = 32 and 64, strided
+  std::vector<Case> wide = {
+      {"mt2 gemm Cout32 res", 3, 31, 29, 64, 32, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 gemm Cout64 129 rows", 1, 1, 129, 64, 64, 1, 1, 1, 0, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 gemm C32->64 bk32 res", 2, 33, 31, 32, 64, 1, 1, 1, 0, ACT_LEAKY, RES_BEFORE_ACT, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 3x3 s2 C32->64 bk32", 2, 48, 40, 32, 64, 3, 3, 2, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 3x3 s1 C32->64 res", 3, 24, 27, 32, 64, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 3x3 s1 C64->64", 2, 80, 64, 64, 64, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 1x1 C128->64 coff", 2, 52, 52, 128, 64, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 64, 64, 0, 0, 0, 0, 0, 2},
+      {"mt2 many tiles C64->32", 40, 33, 31, 64, 32, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt2 bn128 3x3 C64->128 res", 3, 52, 50, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 128, 0, 0, 0, 1, 2},
+      {"mt2 bn128 gemm 256->384", 3, 31, 29, 256, 384, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, STORE_PLAIN, 0, 0, 0, 0, 128, 0, 0, 0, 1, 2},
+  };
+  for (auto& c : wide) fails += run_case(c);
+
   if (!quick && fails == 0) {
     printf("---- timing (batch 64 production shapes) ----\n");
     std::vector<Case> perf = {
@@ -512,7 +528,14 @@ int main(int argc, char** argv) {
         {"Y 1x1 512->256 @26 cg1", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
         {"Y 1x1 512->256 @26 cg2", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
         {"Y 3x3 64->128 @104 cg1", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1},
-        {"Y 3x3 64->128 @104 cg2", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 2},
+        {"Y 3x3 64->128 @104 mt2", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1, 2},
+        {"Y 3x3/2 64->128 @104 mt1", 64, 208, 208, 64, 128, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1, 1},
+        {"Y 3x3/2 64->128 @104 mt2", 64, 208, 208, 64, 128, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1, 2},
+        {"Y 1x1 256->128 @52 mt2", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 2},
+        {"K 1x1 512->128 @40x32 mt1", 64, 40, 32, 512, 128, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 1},
+        {"K 1x1 512->128 @40x32 mt2", 64, 40, 32, 512, 128, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 2},
+        {"K 3x3 128->128 @40x32 mt1", 64, 40, 32, 128, 128, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 1},
+        {"K 3x3 128->128 @40x32 mt2", 64, 40, 32, 128, 128, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 2},
         {"K 3x3 256->256 @20x16 cg1", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
         {"K 3x3 256->256 @20x16 cg2", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
         {"K 1x1 256->1024 +res cg1", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
