@@ -53,6 +53,7 @@ void bp_engine_destroy(bp_engine* e) {
   for (void* p : e->owned) cudaFree(p);
   if (e->resize_tmp) cudaFree(e->resize_tmp);
   if (e->pnp_scratch) cudaFree(e->pnp_scratch);
+  if (e->hm_scratch) cudaFree(e->hm_scratch);
   delete e;
 }
 

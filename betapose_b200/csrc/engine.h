@@ -24,6 +24,9 @@ struct bp_engine {
   std::map<std::pair<int, int>, ResizeTables> resize_tables;
   uint8_t* resize_tmp = nullptr;  // horizontal-pass intermediate
   size_t resize_tmp_bytes = 0;
+  void* hm_scratch = nullptr;  // heat-map decode: per-slice partial arg-max + arrival counters
+  size_t hm_scratch_bytes = 0;
+  int hm_scratch_n = 0;
   double* pnp_scratch = nullptr;  // per-hypothesis rows between the two PnP kernels
   size_t pnp_scratch_bytes = 0;
   std::vector<void*> owned;

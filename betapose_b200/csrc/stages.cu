@@ -499,14 +499,20 @@ __device__ __forceinline__ void argmax_merge(float& v, int& i, float ov, int oi)
   }
 }
 
-// one block (1024 threads) per image.  NHWC heat-maps (k_stride == 1): thread = (position lane, map) so a warp
-// reads 32 consecutive maps of one position (coalesced); NCHW (pos_stride == 1): thread = (map lane, position).
+// grid (images, S), 1024 threads.  NHWC heat-maps (k_stride == 1): thread = (position lane, map) so a warp reads 32
+// consecutive maps of one position (coalesced); the positions of an image are cut into S slices (one block each, so a
+// 64-image batch fills the machine), every block leaves its per-map partial (max, lowest index) in `part`, and the last
+// block of an image to finish merges the S partials in slice order and finalises.  NCHW (pos_stride == 1, the
+// getPrediction seam): thread = (map lane, position), S = 1.
 __global__ void heatmap_decode_kernel(const float* __restrict__ hm, long img_stride, long k_stride, long pos_stride, int K,
                                       int res_h, int res_w, float inp_ratio_hw, float inp_ratio_wh, const float* __restrict__ pt1,
                                       const float* __restrict__ pt2, float* __restrict__ preds_hm, float* __restrict__ preds_img,
-                                      float* __restrict__ maxval, int32_t* __restrict__ idx_out) {
+                                      float* __restrict__ maxval, int32_t* __restrict__ idx_out, float* __restrict__ part_val,
+                                      int* __restrict__ part_idx, unsigned* __restrict__ counters) {
   extern __shared__ unsigned char sm_raw[];
+  __shared__ bool s_last;
   const int n = blockIdx.x;
+  const int S = gridDim.y, sl = blockIdx.y;
   const int npos = res_h * res_w;
   const float* base = hm + (long)n * img_stride;
   const int T = blockDim.x;
@@ -526,8 +532,10 @@ __global__ void heatmap_decode_kernel(const float* __restrict__ hm, long img_str
     const int k = threadIdx.x % kslots, l = threadIdx.x / kslots;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
+    const int chunk = (npos + S - 1) / S;
+    const int p0 = sl * chunk, p1 = min(npos, p0 + chunk);
     if (k < K)
-      for (int p = l; p < npos; p += lanes) argmax_merge(bv, bi, base[(long)p * pos_stride + k], p);
+      for (int p = p0 + l; p < p1; p += lanes) argmax_merge(bv, bi, base[(long)p * pos_stride + k], p);
     s_val[threadIdx.x] = bv;
     s_idx[threadIdx.x] = bi;
     __syncthreads();
@@ -558,6 +566,34 @@ __global__ void heatmap_decode_kernel(const float* __restrict__ hm, long img_str
         s_val[k] = bv;
         s_idx[k] = bi;
       }
+    }
+    __syncthreads();
+  }
+  if (S > 1) {
+    // partials -> global, last block of the image merges them (slice order: lowest index wins ties, as in one block)
+    const int kslots_g = 64;
+    if (threadIdx.x < K) {
+      part_val[((long)n * S + sl) * kslots_g + threadIdx.x] = s_val[threadIdx.x];
+      part_idx[((long)n * S + sl) * kslots_g + threadIdx.x] = s_idx[threadIdx.x];
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned old = atomicAdd(counters + n, 1u);
+      s_last = old == (unsigned)S - 1u;
+      if (s_last) counters[n] = 0u;  // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < K) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int q = 0; q < S; ++q)
+        argmax_merge(bv, bi, __ldcg(part_val + ((long)n * S + q) * kslots_g + threadIdx.x),
+                     __ldcg(part_idx + ((long)n * S + q) * kslots_g + threadIdx.x));
+      s_val[threadIdx.x] = bv;
+      s_idx[threadIdx.x] = bi;
     }
     __syncthreads();
   }
@@ -614,9 +650,34 @@ extern "C" int bp_heatmap_decode(bp_engine* e, const float* hm, long img_stride,
   if (k_stride != 1 && pos_stride != 1) return bp_fail(BP_ERR_UNSUPPORTED, "bp_heatmap_decode: need NHWC (k_stride 1) or NCHW (pos_stride 1)");
   const int T = 1024;
   const float r_hw = (float)((double)inp_h / (double)inp_w), r_wh = (float)((double)inp_w / (double)inp_h);
-  heatmap_decode_kernel<<<n, T, T * 8, reinterpret_cast<cudaStream_t>(stream)>>>(hm, img_stride, k_stride, pos_stride, K, res_h,
-                                                                                res_w, r_hw, r_wh, pt1, pt2, preds_hm,
-                                                                                preds_img, maxval, idx);
+  // NHWC maps (the engine's layout): slice every image's positions over S blocks; scratch is grow-only
+  int S = 1;
+  if (k_stride == 1 && K <= 64) {
+    S = (4 * e->num_sms + n - 1) / n;
+    S = std::max(1, std::min(S, std::min(16, res_h * res_w / 256)));
+  }
+  if (S > 1) {
+    const size_t need = (size_t)n * 16 * 64 * 8 + (size_t)n * 4;
+    if (e->hm_scratch_bytes < need) {
+      if (e->hm_scratch) cudaFree(e->hm_scratch);
+      if (cudaMalloc(&e->hm_scratch, need) != cudaSuccess) {
+        e->hm_scratch = nullptr;
+        e->hm_scratch_bytes = 0;
+        return bp_fail(BP_ERR_CUDA, "bp_heatmap_decode: scratch allocation failed");
+      }
+      cudaMemsetAsync(e->hm_scratch, 0, need, reinterpret_cast<cudaStream_t>(stream));  // arrival counters start at zero
+      e->hm_scratch_bytes = need;
+      e->hm_scratch_n = n;
+    }
+  }
+  // layout of the scratch: [n_alloc][16][64] float | [n_alloc][16][64] int | [n_alloc] counters
+  const int na = e->hm_scratch_n;
+  float* pv = reinterpret_cast<float*>(e->hm_scratch);
+  int* pi = reinterpret_cast<int*>(pv + (size_t)na * 16 * 64);
+  unsigned* ctr = reinterpret_cast<unsigned*>(pi + (size_t)na * 16 * 64);
+  heatmap_decode_kernel<<<dim3(n, S), T, T * 8, reinterpret_cast<cudaStream_t>(stream)>>>(hm, img_stride, k_stride, pos_stride, K, res_h,
+                                                                                         res_w, r_hw, r_wh, pt1, pt2, preds_hm,
+                                                                                         preds_img, maxval, idx, pv, pi, ctr);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }
