@@ -331,7 +331,7 @@ pnp_refine_kernel(const float* __restrict__ preds_img, const float* __restrict__
         ok = false;
         break;
       }
-      bp::pnp::lm_refine(ln, R, t, S.pw, S.uv, s_inl, K, fx, fy, cx, cy, 50);
+      bp::pnp::lm_refine(ln, R, t, S.pw, S.uv, s_inl, K, fx, fy, cx, cy, BP_PNP_LM_ITERS);
       if (!ransac) break;
     }
   }

@@ -571,6 +571,8 @@ BP_HD bool within_threshold(const double* R, const double* t, const double* pw, 
 
 // number of consensus re-estimation rounds after the winning hypothesis (classify -> LM refit -> classify ...)
 #define BP_PNP_LO_ROUNDS 4
+// Levenberg-Marquardt iterations per refit (OpenCV's iterative solvePnP, which solvePnPRansac refits with, stops at 20)
+#define BP_PNP_LM_ITERS 20
 
 // score one hypothesis against all candidate points: consensus count and summed squared error of inliers
 BP_HD void score_hypothesis(const double* R, const double* t, const double* pw, const double* uv, const uint8_t* sel,

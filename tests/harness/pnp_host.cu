@@ -56,7 +56,7 @@ extern "C" int bp_host_pnp(const double* pw, const double* uv, const unsigned ch
     }
     if (round > 0 && !changed) break;
     if (cnt < 4) { memset(inl, 0, K); return -1; }
-    lm_refine(ln, bR, bt, pw, uv, inl, K, fx, fy, cx, cy, 50);
+    lm_refine(ln, bR, bt, pw, uv, inl, K, fx, fy, cx, cy, BP_PNP_LM_ITERS);
     if (!ransac) break;
   }
   memcpy(R_out, bR, sizeof bR);
