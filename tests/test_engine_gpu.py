@@ -174,3 +174,63 @@ def test_run_stream_matches_run(engine, frames8):
         assert g.dtype == r.dtype and len(g) == len(r)
         for f in g.dtype.names:
             assert np.array_equal(g[f], r[f]), f
+
+
+def test_engine_batch64_permutation_invariance(yolo_stream, kpd_sd, kp_model):
+    """BASELINE.json configs[2] size (batch 64).  Frames are processed independently, and every output element of the
+    convolutions accumulates in a fixed order whatever tile it lands in, so permuting the batch must permute the
+    records bit for bit (size-independent property; the oracle is too slow for 64 frames)."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine
+
+    e = BetaposeEngine(64, yolo_stream, kpd_sd, kp_model, seed=5)
+    frames = synth.synth_frames(64, seed=21)
+    a = e.run(frames, graph=True).copy()
+    perm = np.random.default_rng(0).permutation(64)
+    b = e.run(frames[perm], graph=True).copy()
+    assert (a["status"] == 1).sum() >= 32  # the synthetic stream is not silently all-rejected
+    for f in a.dtype.names:
+        if f == "image_index":
+            continue
+        assert np.array_equal(a[f][perm], b[f]), f
+    # idempotence: same input, same bytes
+    assert e.run(frames, graph=True).tobytes() == a.tobytes()
+    del e
+    torch.cuda.empty_cache()
+
+
+def test_engine_mixed_objects_and_occlusion(yolo_stream, kpd_sd, kp_model):
+    """configs[3] / configs[4] shape: a batch that mixes two object slots (own detector + key-point net + key-point
+    model each, shared activation buffers) and the Occlusion-LineMod setting left_keypoints = 10.  Every frame must get
+    exactly what a single-object engine of its slot produces; the 10 selected points are the 10 best-scored ones."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine
+
+    ys2, ks2 = synth.cached_yolo_weights(1001), synth.cached_kpd_state_dict(2001)
+    kp2 = synth.synth_kp_model(2, 50)
+    frames = synth.synth_frames(6, seed=33)
+    slots = np.array([0, 1, 1, 0, 1, 0])
+    mixed = BetaposeEngine(6, [yolo_stream, ys2], [kpd_sd, ks2], np.stack([kp_model, kp2]), left_number=10, seed=5)
+    got = mixed.run(frames, obj_slots=slots).copy()
+    sel = mixed.selected.cpu().numpy()
+    score = mixed.kp_score.cpu().numpy()
+    order = np.argsort(slots, kind="stable")  # the engine processes the batch grouped by slot
+    del mixed
+    torch.cuda.empty_cache()
+    for s, (yw, kw, kp) in enumerate([(yolo_stream, kpd_sd, kp_model), (ys2, ks2, kp2)]):
+        single = BetaposeEngine(6, yw, kw, kp, left_number=10, seed=5)
+        idx = np.nonzero(slots == s)[0]
+        ref = single.run(frames[idx]).copy()
+        for f in ref.dtype.names:
+            if f == "image_index":
+                continue
+            assert np.array_equal(got[f][idx], ref[f]), (s, f)
+        del single
+        torch.cuda.empty_cache()
+    assert got["image_index"].tolist() == list(range(6))
+    for j, b in enumerate(order):  # row j of the engine's buffers holds frame order[j]
+        if got["status"][b] == 0:
+            continue
+        assert sel[j].sum() == 10
+        top = np.sort(np.argsort(-score[j], kind="stable")[:10])
+        assert np.array_equal(np.nonzero(sel[j])[0], top)
