@@ -247,3 +247,36 @@ def write_json(all_results, outputpath, for_eval=False):
     with open(os.path.join(outputpath, "Betapose-results.json"), "w") as json_file:
         json_file.write(json.dumps(json_results))
     return json_results
+
+
+# ---------------------------------------------------------------------------------------------- scoring (utils/metrics.py)
+def _pose_batch(pose):
+    p = np.asarray(pose, np.float64)
+    return torch.from_numpy(p[None, :3, :3].copy()), torch.from_numpy(p[None, :3, 3].copy())
+
+
+def _score_one(gt_pose, est_pose, model, cam=None, gt_box=None, est_box=None):
+    dev = _dev()
+    Rg, tg = _pose_batch(gt_pose)
+    Re, te = _pose_batch(est_pose)
+    gb = torch.tensor([gt_box if gt_box is not None else [0, 0, 1, 1]], dtype=torch.float32)
+    eb = torch.tensor([est_box if est_box is not None else [0, 0, 1, 1]], dtype=torch.float32)
+    return stages.score_poses(Re.to(dev), te.to(dev), eb.to(dev), Rg.to(dev), tg.to(dev), gb.to(dev),
+                              torch.from_numpy(np.asarray(model, np.float64)).to(dev),
+                              cam_K=stages.CAM_K if cam is None else cam)
+
+
+def add_err(gt_pose, est_pose, model):
+    """utils/metrics.py:10-22: mean distance of the model vertices under the two 4x4 poses."""
+    return float(_score_one(gt_pose, est_pose, model)["add"][0])
+
+
+def projection_error_2d(gt_pose, est_pose, model, cam):
+    """utils/metrics.py:96-127: mean pixel distance of the projected model vertices."""
+    return float(_score_one(gt_pose, est_pose, model, cam=cam)["proj"][0])
+
+
+def iou(gt_box, est_box):
+    """utils/metrics.py:77-93, boxes as corners (x1, y1, x2, y2)."""
+    I = np.eye(4)
+    return float(_score_one(I, I, np.zeros((1, 3)), gt_box=list(gt_box), est_box=list(est_box))["iou"][0])

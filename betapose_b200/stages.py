@@ -192,3 +192,43 @@ assert RECORD_DTYPE.itemsize == _lib.RECORD_BYTES, (RECORD_DTYPE.itemsize, _lib.
 def records_to_numpy(rec_u8: torch.Tensor) -> np.ndarray:
     """host copy of packed records as a numpy structured array."""
     return rec_u8.detach().cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+
+
+def score_poses(R_est, t_est, box_est, R_gt, t_gt, box_gt, model, cam_K=CAM_K, status=None, model_idx=None):
+    """Scoring stage (betapose_evaluate.py:203-266; utils/metrics.py add_err / projection_error_2d / iou), batched.
+    R_* f64 [n,3,3] or [n,9], t_* f64 [n,3], box_* fp32 [n,4] corners (x1,y1,x2,y2), model f64 [V,3] or [n_models,V,3]
+    (metres), all CUDA tensors.  -> dict(add [n] f64 metres, proj [n] f64 px, iou [n] f32, scored [n] u8)."""
+    dev = R_est.device
+    e = _eng(R_est)
+    n = int(R_est.shape[0])
+    f64 = lambda x: x.to(dev, torch.float64).reshape(n, -1).contiguous()  # noqa: E731
+    Re, te, Rg, tg = f64(R_est), f64(t_est), f64(R_gt), f64(t_gt)
+    be, bg = box_est.to(dev, torch.float32).contiguous(), box_gt.to(dev, torch.float32).contiguous()
+    m = model.to(dev, torch.float64).contiguous()
+    V = int(m.shape[-2])
+    K = np.asarray(cam_K, np.float64)
+    cam = (C.c_double * 4)(K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    add = torch.empty(n, dtype=torch.float64, device=dev)
+    proj = torch.empty(n, dtype=torch.float64, device=dev)
+    iou = torch.empty(n, dtype=torch.float32, device=dev)
+    scored = torch.empty(n, dtype=torch.uint8, device=dev)
+    st = status.to(dev, torch.int32).contiguous() if status is not None else None
+    mi = model_idx.to(dev, torch.int32).contiguous() if model_idx is not None else None
+    _lib.check(_lib.lib().bp_score_poses(e.handle, n, _lib.ptr(Re), _lib.ptr(te), _lib.ptr(st), _lib.ptr(be), _lib.ptr(Rg),
+                                         _lib.ptr(tg), _lib.ptr(bg), _lib.ptr(m), _lib.ptr(mi), V, C.cast(cam, C.c_void_p),
+                                         _lib.ptr(add), _lib.ptr(proj), _lib.ptr(iou), _lib.ptr(scored), _lib.stream_ptr()),
+               "bp_score_poses")
+    return dict(add=add, proj=proj, iou=iou, scored=scored)
+
+
+def summarize_scores(add_m, proj_px, iou, scored, diameter_mm: float, pixel_thresh: float = 5.0) -> dict:
+    """The reference's summary numbers (betapose_evaluate.py:259-266): ADD accuracy at diameter / 10 (errors in mm),
+    2-D reprojection accuracy at 5 px, fraction of frames with IoU > 0.5.  Host arrays / tensors in."""
+    add_mm = np.asarray(torch.as_tensor(add_m).cpu(), np.float64) * 1000.0
+    proj = np.asarray(torch.as_tensor(proj_px).cpu(), np.float64)
+    io = np.asarray(torch.as_tensor(iou).cpu(), np.float64)
+    sc = np.asarray(torch.as_tensor(scored).cpu()).astype(bool)
+    return dict(mean_add_err_mm=float(add_mm[sc].mean()) if sc.any() else float("nan"),
+                add_accuracy=float((add_mm[sc] < diameter_mm / 10.0).mean()) if sc.any() else float("nan"),
+                proj2d_accuracy=float((proj[sc] < pixel_thresh).mean()) if sc.any() else float("nan"),
+                iou_accuracy=float((io > 0.5).mean()) if len(io) else float("nan"), n_scored=int(sc.sum()))

@@ -200,6 +200,18 @@ int bp_pack_records(bp_engine* e, int n, int K, int image_index0, const float* b
                     const float* keypoints, const float* kp_score, const float* proposal, const double* R,
                     const double* t, const int32_t* status, bp_record* out, void* stream);
 
+/* scoring (the evaluation loop after the per-frame path, betapose_evaluate.py:203-266): per image
+ *   add_err[n]  = mean_v |(R_gt v + t_gt) - (R_est v + t_est)|        (utils/metrics.py:10-22, model units: metres)
+ *   proj_err[n] = mean_v |proj(K [R_gt|t_gt] v) - proj(K [R_est|t_est] v)| in pixels (metrics.py:96-127)
+ *   iou[n]      = IoU of box_gt and box_est, both (x1, y1, x2, y2)       (metrics.py:77-93)
+ *   scored[n]   = 1 where the reference would score ADD / reprojection: the frame has a pose (status == 1; NULL = all)
+ *                 and iou >= 0.5.
+ * model: f64 [n_models, n_vertices, 3]; model_idx[n] (NULL = model 0); cam f64[4] = (fx, fy, cx, cy). */
+int bp_score_poses(bp_engine* e, int n, const double* R_est, const double* t_est, const int32_t* status,
+                   const float* box_est, const double* R_gt, const double* t_gt, const float* box_gt, const double* model,
+                   const int32_t* model_idx, int n_vertices, const double* cam, double* add_err, double* proj_err, float* iou,
+                   uint8_t* scored, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

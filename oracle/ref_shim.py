@@ -168,6 +168,15 @@ def load_reference() -> types.SimpleNamespace:
     return ns
 
 
+def load_metrics() -> types.ModuleType:
+    """The reference's scoring functions (3_6Dpose_estimator/utils/metrics.py) unmodified; pyquaternion (only used by
+    rot_error, which the evaluate loop never calls) is stubbed."""
+    _install_stubs()
+    if "pyquaternion" not in sys.modules:
+        _stub("pyquaternion", Quaternion=object)
+    return _load("utils.metrics", "utils/metrics.py")
+
+
 def ref_pnp(points_3D, points_2D, cameraMatrix):
     """The reference's ``pnp`` body (3_6Dpose_estimator/utils/utils.py:17-41) cannot be imported (the module
     pulls renderer/vispy at import); its two live statements are the cv2 calls below."""

@@ -438,3 +438,33 @@ def refine_vertices(v: np.ndarray, n_keep: int) -> np.ndarray:
             i = 0
         v = np.delete(v, i, axis=0)
     return v
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# scoring
+def add_err(gt_pose, est_pose, model):
+    """3_6Dpose_estimator/utils/metrics.py:10-22: mean_v |(R_gt v + t_gt) - (R_est v + t_est)|, 4x4 poses, model [V,3]."""
+    gt_pose, est_pose, model = np.asarray(gt_pose, np.float64), np.asarray(est_pose, np.float64), np.asarray(model, np.float64)
+    a = model @ gt_pose[:3, :3].T + gt_pose[:3, 3]
+    b = model @ est_pose[:3, :3].T + est_pose[:3, 3]
+    return float(np.mean(np.linalg.norm(a - b, axis=1)))
+
+
+def projection_error_2d(gt_pose, est_pose, model, cam):
+    """utils/metrics.py:96-127: mean pixel distance between the vertices projected by cam @ pose[:3]."""
+    model = np.asarray(model, np.float64)
+    h = np.concatenate([model, np.ones((len(model), 1))], 1)
+    g = (np.asarray(cam, np.float64) @ np.asarray(gt_pose, np.float64)[:3]) @ h.T
+    e = (np.asarray(cam, np.float64) @ np.asarray(est_pose, np.float64)[:3]) @ h.T
+    g, e = (g / g[2])[:2].T, (e / e[2])[:2].T
+    return float(np.mean(np.linalg.norm(g - e, axis=1)))
+
+
+def box_iou(gt_box, est_box):
+    """utils/metrics.py:77-93 (corners x1, y1, x2, y2)."""
+    xA, yA = max(gt_box[0], est_box[0]), max(gt_box[1], est_box[1])
+    xB, yB = min(gt_box[2], est_box[2]), min(gt_box[3], est_box[3])
+    if xB <= xA or yB <= yA:
+        return 0.0
+    inter = (xB - xA) * (yB - yA)
+    return float(inter / float((gt_box[2] - gt_box[0]) * (gt_box[3] - gt_box[1]) + (est_box[2] - est_box[0]) * (est_box[3] - est_box[1]) - inter))

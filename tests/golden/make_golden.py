@@ -184,6 +184,7 @@ def versions():
 
 
 def main():
+    make_metrics_golden()
     assert ref_shim.available(), "reference tree not found"
     ref = ref_shim.load_reference()
     rng = np.random.default_rng(2024)
@@ -344,5 +345,41 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def make_metrics_golden():
+    """utils/metrics.py add_err / projection_error_2d / iou of the UNMODIFIED reference on seeded poses."""
+    import cv2
+
+    M = ref_shim.load_metrics()
+    rng = np.random.default_rng(12)
+    model = rng.uniform(-0.06, 0.06, (777, 3))
+    cam = R.CAM_K
+    gt, est, boxes_gt, boxes_est, add, proj, iou = [], [], [], [], [], [], []
+    for i in range(24):
+        rv = rng.standard_normal(3)
+        rv *= rng.uniform(0, np.pi) / np.linalg.norm(rv)
+        Rg = cv2.Rodrigues(rv)[0]
+        tg = np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), rng.uniform(0.6, 1.2)])
+        dr = rng.standard_normal(3) * [0.0, 0.002, 0.02, 0.2][i % 4]
+        Re = cv2.Rodrigues(dr)[0] @ Rg
+        te = tg + rng.standard_normal(3) * [0.0, 0.0005, 0.005, 0.05][i % 4]
+        G, E = np.eye(4), np.eye(4)
+        G[:3, :3], G[:3, 3], E[:3, :3], E[:3, 3] = Rg, tg, Re, te
+        bg = np.array([100 + 10 * i, 80, 260 + 10 * i, 300], np.float64)
+        be = bg + rng.uniform(-60, 60, 4) * (i % 3)
+        if i == 5:
+            be = np.array([500, 400, 560, 470], np.float64)  # disjoint
+        gt.append(G); est.append(E); boxes_gt.append(bg); boxes_est.append(be)
+        add.append(M.add_err(G, E, model))
+        proj.append(M.projection_error_2d(G, E, model, cam))
+        iou.append(M.iou(list(bg), list(be)))
+    np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), model=model, cam=cam, gt=np.array(gt), est=np.array(est),
+                        box_gt=np.array(boxes_gt), box_est=np.array(boxes_est), add=np.array(add), proj=np.array(proj),
+                        iou=np.array(iou), versions=np.array(f"numpy {np.__version__}"))
+    print("metrics_golden.npz", np.array(add)[:4], np.array(iou)[:6])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        make_metrics_golden()
+        sys.exit(0)
     main()

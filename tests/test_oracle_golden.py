@@ -188,3 +188,12 @@ def test_fastpose_vs_reference():
     scale = float(g["hm_absmax"])
     np.testing.assert_allclose(hm[:, :, ::4, ::4], g["hm_sub"], rtol=0, atol=2e-4 * scale)
     assert (hm.reshape(1, 50, -1).argmax(2) == g["hm_argmax"]).mean() >= 0.98
+
+
+def test_scoring_matches_reference_metrics():
+    """oracle add_err / projection_error_2d / box_iou against the UNMODIFIED utils/metrics.py (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(G, "metrics_golden.npz"))
+    for i in range(len(g["gt"])):
+        assert abs(R.add_err(g["gt"][i], g["est"][i], g["model"]) - g["add"][i]) <= 1e-15 + 1e-13 * g["add"][i]
+        assert abs(R.projection_error_2d(g["gt"][i], g["est"][i], g["model"], g["cam"]) - g["proj"][i]) <= 1e-12 + 1e-12 * g["proj"][i]
+        assert R.box_iou(g["box_gt"][i], g["box_est"][i]) == g["iou"][i]

@@ -273,3 +273,50 @@ def test_pack_records_roundtrip(kp_model):
     assert np.array_equal(rec["R"], pose["R"].cpu().numpy()) and np.array_equal(rec["t"], pose["t"].cpu().numpy())
     kp = rec["keypoints"].reshape(n, 50, 3)
     assert np.array_equal(kp[:, :, :2], pose["keypoints"].cpu().numpy()) and np.array_equal(kp[:, :, 2], pose["kp_score"].cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ scoring (8(f) item 1)
+def test_score_poses_matches_reference_goldens():
+    """bp_score_poses against the reference's own metrics.py outputs (golden) and the oracle: fp64, 1e-12 relative."""
+    import os
+
+    from betapose_b200 import compat, stages
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.npz"))
+    n = len(g["gt"])
+    out = stages.score_poses(_cuda(g["est"][:, :3, :3].copy()), _cuda(g["est"][:, :3, 3].copy()), _cuda(g["box_est"].astype(np.float32)),
+                             _cuda(g["gt"][:, :3, :3].copy()), _cuda(g["gt"][:, :3, 3].copy()), _cuda(g["box_gt"].astype(np.float32)),
+                             _cuda(g["model"]), cam_K=g["cam"])
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out["add"].cpu().numpy(), g["add"], rtol=1e-12, atol=1e-16)
+    np.testing.assert_allclose(out["proj"].cpu().numpy(), g["proj"], rtol=1e-11, atol=1e-12)
+    iou32 = np.array([R.box_iou(g["box_gt"][i].astype(np.float32).astype(np.float64), g["box_est"][i].astype(np.float32).astype(np.float64))
+                      for i in range(n)])
+    np.testing.assert_allclose(out["iou"].cpu().numpy(), iou32, rtol=2e-7, atol=0)
+    assert np.array_equal(out["scored"].cpu().numpy().astype(bool), out["iou"].cpu().numpy() >= 0.5)
+    # the drop-in seams
+    assert abs(compat.add_err(g["gt"][3], g["est"][3], g["model"]) - g["add"][3]) <= 1e-12 * g["add"][3]
+    assert abs(compat.projection_error_2d(g["gt"][3], g["est"][3], g["model"], g["cam"]) - g["proj"][3]) <= 1e-11 * g["proj"][3]
+    assert abs(compat.iou(g["box_gt"][1], g["box_est"][1]) - g["iou"][1]) <= 1e-6
+    s = stages.summarize_scores(out["add"], out["proj"], out["iou"], out["scored"], diameter_mm=102.0)
+    sc = g["iou"] >= 0.5
+    assert s["n_scored"] == int(sc.sum()) and abs(s["add_accuracy"] - float((g["add"][sc] * 1000 < 10.2).mean())) < 1e-12
+
+
+def test_score_poses_full_size_properties(kp_model):
+    """BASELINE-size batch (256 poses, a 20k-vertex model): identical poses score exactly 0; a pure translation d scores
+    ADD = |d| for every model (size-independent properties)."""
+    from betapose_b200 import stages
+
+    rng = np.random.default_rng(5)
+    n, V = 256, 20000
+    model = rng.uniform(-0.08, 0.08, (V, 3))
+    Rg = np.stack([np.linalg.qr(rng.standard_normal((3, 3)))[0] for _ in range(n)])
+    Rg[np.linalg.det(Rg) < 0, :, 0] *= -1
+    tg = np.stack([rng.uniform(-0.1, 0.1, n), rng.uniform(-0.1, 0.1, n), rng.uniform(0.6, 1.2, n)], 1)
+    box = np.tile(np.array([[100, 100, 300, 300]], np.float32), (n, 1))
+    same = stages.score_poses(_cuda(Rg), _cuda(tg), _cuda(box), _cuda(Rg), _cuda(tg), _cuda(box), _cuda(model))
+    assert float(same["add"].abs().max()) == 0.0 and float(same["proj"].abs().max()) == 0.0 and float(same["iou"].min()) == 1.0
+    d = rng.standard_normal((n, 3)) * 0.01
+    sh = stages.score_poses(_cuda(Rg), _cuda(tg + d), _cuda(box), _cuda(Rg), _cuda(tg), _cuda(box), _cuda(model))
+    np.testing.assert_allclose(sh["add"].cpu().numpy(), np.linalg.norm(d, axis=1), rtol=1e-9)
