@@ -206,6 +206,89 @@ def per_op_profile(eng, B: int, reps: int = 3):
     return out
 
 
+def add_vs_ref(eng, B):
+    """BASELINE.json's second clause, "ADD(-S)@0.1d vs ref", on synthetic data: B planted poses of the key-point model
+    (|rotation| < pi, t = (+-0.1, +-0.1, 0.6..1.2) m), their projections with 1 px noise and 5 gross
+    outliers (60 px) as key-points -> the engine's PnP stage (bp_pose_pnp) against (i) the CPU oracle and (ii)
+    cv2.solvePnPRansac (the reference's third-party solver) on the same points; ADD over the key-point model scored on
+    the GPU by bp_score_poses, d = model diameter.  (The key-points a randomly initialised network produces fit no pose
+    at all, so the step's own poses cannot be compared between solvers: which local solution wins is arbitrary.)"""
+    import torch
+
+    from betapose_b200 import stages
+    from oracle import pnp as opnp
+    from oracle import restate as R
+
+    try:
+        import cv2
+    except Exception:
+        cv2 = None
+    dev = eng.device
+    rng = np.random.default_rng(2024)
+    kp3d = eng.kp3d[0].cpu().numpy()
+    K = len(kp3d)
+    diam = float(np.max(np.linalg.norm(kp3d[:, None] - kp3d[None], axis=2)))
+    fx, fy, cx, cy = R.CAM_K[0, 0], R.CAM_K[1, 1], R.CAM_K[0, 2], R.CAM_K[1, 2]
+    Rg, tg, uv = [], [], []
+    for _ in range(B):
+        rv = rng.standard_normal(3)
+        rv *= rng.uniform(0, np.pi) / np.linalg.norm(rv)
+        th = np.linalg.norm(rv)
+        k = rv / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        Rm = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t = np.array([rng.choice([-0.1, 0.1]), rng.choice([-0.1, 0.1]), rng.uniform(0.6, 1.2)])
+        pc = kp3d @ Rm.T + t
+        p = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1) + rng.normal(0, 1.0, (K, 2))
+        out = rng.choice(K, 5, replace=False)
+        p[out] += rng.normal(0, 60.0, (5, 2))
+        Rg.append(Rm); tg.append(t); uv.append(p.astype(np.float32))
+    Rg, tg, uv = np.array(Rg), np.array(tg), np.array(uv)
+    pose = stages.pose_pnp(torch.from_numpy(uv).to(dev), None, None, eng.kp3d[0].contiguous(), left_number=K, mode=stages.MODE_RANSAC,
+                           reproj_thr=eng.reproj_thr, n_hyp=eng.n_hyp, seed=eng.seed, flags=1)  # BP_PNP_RAW_POINTS
+    torch.cuda.synchronize()
+    Re, te, st = pose["R"].cpu().numpy().reshape(B, 3, 3), pose["t"].cpu().numpy(), pose["status"].cpu().numpy()
+    Ro, to, Rc, tc = np.zeros_like(Re), np.zeros_like(te), np.zeros_like(Re), np.zeros_like(te)
+    ok_o, ok_c = np.zeros(B, bool), np.zeros(B, bool)
+    for b in range(B):
+        sol = opnp.solve_pnp(kp3d, uv[b], R.CAM_K, mode=0, thr=eng.reproj_thr, n_hyp=eng.n_hyp, seed=eng.seed)
+        ok_o[b] = sol["ok"]
+        Ro[b], to[b] = sol["R"], sol["t"]
+        if cv2 is not None:
+            ok, rvec, tvec, _ = cv2.solvePnPRansac(kp3d, uv[b], R.CAM_K, np.zeros((8, 1), np.float32), reprojectionError=float(eng.reproj_thr))
+            ok_c[b] = bool(ok)
+            if ok:
+                Rc[b], tc[b] = cv2.Rodrigues(rvec)[0], tvec.reshape(3)
+    box = torch.zeros((B, 4), dtype=torch.float32, device=dev)
+    box[:, 2:] = 1
+    model = torch.from_numpy(kp3d).to(dev)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+
+    def add_mm(Ra, ta, Rb, tb):
+        return stages.score_poses(T(Ra), T(ta), box, T(Rb), T(tb), box, model)["add"].cpu().numpy() * 1000.0
+
+    thr = 100.0 * diam  # 0.1 d in mm
+    ours_gt = add_mm(Re, te, Rg, tg)
+    res = {"frames": B, "diameter_mm": diam * 1000.0, "noise_px": 1.0, "outliers": 5, "poses_found": int((st == 1).sum()),
+           "ours_add_pass_at_0.1d_vs_planted": float((ours_gt[st == 1] < thr).mean()),
+           "ours_median_add_mm_vs_planted": float(np.median(ours_gt[st == 1]))}
+    m = (st == 1) & ok_o
+    a = add_mm(Re[m], te[m], Ro[m], to[m])
+    og = add_mm(Ro, to, Rg, tg)
+    res["vs_oracle"] = {"frames": int(m.sum()), "add_pass_at_0.1d": float((a < thr).mean()), "max_add_mm": float(a.max()),
+                        "pass_decisions_agree": float(((ours_gt < thr) == (og < thr))[m].mean()),
+                        "max_abs_dR": float(np.abs(Re[m] - Ro[m]).max()), "max_abs_dt": float(np.abs(te[m] - to[m]).max())}
+    if cv2 is not None:
+        m = (st == 1) & ok_c
+        a = add_mm(Re[m], te[m], Rc[m], tc[m])
+        cg = add_mm(Rc, tc, Rg, tg)
+        res["vs_cv2_solvePnPRansac"] = {"frames": int(m.sum()), "add_pass_at_0.1d": float((a < thr).mean()), "max_add_mm": float(a.max()),
+                                        "pass_decisions_agree": float(((ours_gt < thr) == (cg < thr))[m].mean()),
+                                        "cv2_add_pass_at_0.1d_vs_planted": float((cg[ok_c] < thr).mean()),
+                                        "max_abs_dR": float(np.abs(Re[m] - Rc[m]).max()), "max_abs_dt": float(np.abs(te[m] - tc[m]).max())}
+    return res
+
+
 def ours_arm(args):
     import torch
     import torch.distributed as dist
@@ -372,6 +455,11 @@ def ours_arm(args):
             cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{len(fr) * reps} frames of the same synthetic stream, one at a time: torch-CPU fp32 nets, "
                              f"resize={info['resize']}, numpy decode/crop/heat-map stages, pnp={info['pnp']}"}
+
+            # ---- BASELINE.json's second clause, "ADD(-S)@0.1d vs ref": the engine's poses of one batch against the CPU
+            # oracle's poses (and cv2.solvePnPRansac's, the reference's third-party call, where importable) computed from
+            # the same key-points, scored on the GPU by bp_score_poses (ADD over the key-point model, d = its diameter)
+            extra["add_vs_ref"] = add_vs_ref(eng, B)
 
     if rank == 0:
         st = last_records["status"]
