@@ -1,10 +1,10 @@
 // a9 (single-proposal pose-NMS) + a10 (key-point selection) + a11 (PnP) in two launches:
 //   pnp_hypotheses_kernel : grid (n_hyp / 8, images).  Every CTA redoes the (cheap) pose-NMS + selection of its image,
-//                           then solves 8 five-point EPnP hypotheses, 16 cooperating lanes each: the 12 x 12 M^T M
+//                           then solves 8 five-point EPnP hypotheses, 8 cooperating lanes each: the 12 x 12 M^T M
 //                           eigen-problem -- 80 % of the serial work of a hypothesis -- runs as a parallel-order Jacobi
 //                           (the 6 disjoint rotations of a round at once, 72 column / row updates spread over the
 //                           lanes) on matrices held in shared memory; the rest of EPnP is executed redundantly by the
-//                           16 lanes (identical inputs, identical results, no divergence).  Each hypothesis is scored
+//                           8 lanes (identical inputs, identical results, no divergence).  Each hypothesis is scored
 //                           against all selected points (12 px) and left in a global scratch row.
 //   pnp_refine_kernel     : one warp per image picks the consensus winner (shuffle arg-max) and alternates
 //                           {classify points against the current pose, Levenberg-Marquardt refit, lane-parallel over
@@ -22,7 +22,9 @@ namespace {
 
 constexpr int kMaxK = 64;
 constexpr int kMaxHyp = 128;
-constexpr int kHypPerCta = 8;       // x 16 lanes = 128 threads
+// cooperating lanes per hypothesis: template parameter GW (8 or 16; >= the 6 pairs of a Jacobi round); a CTA is 128
+// threads = 128 / GW hypotheses.  8 lanes is the throughput choice (less redundant fp64 work per hypothesis), 16 the
+// latency choice for small batches (shorter Jacobi phases).
 constexpr int kHypRow = 16;         // doubles per hypothesis in the scratch: count, total, R[9], t[3], pad
 
 // One warp, lanes over points; the 28 sums of an LM step are all-reduced by shuffles (independent chains: they
@@ -50,32 +52,33 @@ struct WarpLanes {
 // Parallel-order cyclic Jacobi: a sweep is 11 rounds of 6 disjoint pairs (circle method); the rotations of a round
 // commute, so A <- J^T A J is applied as "all column updates, then all row updates".  Same rotation formulas as the
 // serial jacobi_eig<12> (pnp_math.cuh), different rotation order.
+template <int kGW>
 struct GroupEig12 {
   double* A;      // [144] shared, this group's
   double* V;      // [144] shared
-  unsigned mask;  // the 16 lanes of this group inside the warp
+  unsigned mask;  // the kGW lanes of this group inside the warp
   int gl;         // lane inside the group
 
   __device__ __forceinline__ double gsum(double x) const {
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, 16);
+    for (int o = kGW / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, kGW);
     return x;
   }
 
   __device__ const double* solve(double* M, double* w) {
-    if (gl < 12) {
+    for (int r = gl; r < 12; r += kGW) {
 #pragma unroll
       for (int c = 0; c < 12; ++c) {
-        A[gl * 12 + c] = M[gl * 12 + c];
-        V[gl * 12 + c] = gl == c ? 1.0 : 0.0;
+        A[r * 12 + c] = M[r * 12 + c];
+        V[r * 12 + c] = r == c ? 1.0 : 0.0;
       }
     }
     __syncwarp(mask);
     for (int sweep = 0; sweep < 60; ++sweep) {
       double off = 0.0, diag = 0.0;
-      if (gl < 12) {
-        diag = A[gl * 13] * A[gl * 13];
-        for (int q = gl + 1; q < 12; ++q) off += A[gl * 12 + q] * A[gl * 12 + q];
+      for (int r = gl; r < 12; r += kGW) {
+        diag += A[r * 13] * A[r * 13];
+        for (int q = r + 1; q < 12; ++q) off += A[r * 12 + q] * A[r * 12 + q];
       }
       off = gsum(off);
       diag = gsum(diag);
@@ -99,14 +102,14 @@ struct GroupEig12 {
           }
         }
         __syncwarp(mask);  // every pair has read its 2 x 2 block before anything is rewritten
-        // columns of A and V: item (pair j, row k), 72 items over 16 lanes
+        // columns of A and V: item (pair j, row k), 72 items over the kGW lanes
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          const int i = gl + 16 * it;
+        for (int it = 0; it < (72 + kGW - 1) / kGW; ++it) {
+          const int i = gl + kGW * it;
           const int j = i < 72 ? i / 12 : 0;
           const int k = i - (i / 12) * 12;
-          const int pj = __shfl_sync(mask, p, j, 16), qj = __shfl_sync(mask, q, j, 16);
-          const double cj = __shfl_sync(mask, c, j, 16), sj = __shfl_sync(mask, s, j, 16);
+          const int pj = __shfl_sync(mask, p, j, kGW), qj = __shfl_sync(mask, q, j, kGW);
+          const double cj = __shfl_sync(mask, c, j, kGW), sj = __shfl_sync(mask, s, j, kGW);
           if (i < 72) {
             const double akp = A[k * 12 + pj], akq = A[k * 12 + qj];
             A[k * 12 + pj] = cj * akp - sj * akq;
@@ -119,12 +122,12 @@ struct GroupEig12 {
         __syncwarp(mask);
         // rows of A
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-          const int i = gl + 16 * it;
+        for (int it = 0; it < (72 + kGW - 1) / kGW; ++it) {
+          const int i = gl + kGW * it;
           const int j = i < 72 ? i / 12 : 0;
           const int k = i - (i / 12) * 12;
-          const int pj = __shfl_sync(mask, p, j, 16), qj = __shfl_sync(mask, q, j, 16);
-          const double cj = __shfl_sync(mask, c, j, 16), sj = __shfl_sync(mask, s, j, 16);
+          const int pj = __shfl_sync(mask, p, j, kGW), qj = __shfl_sync(mask, q, j, kGW);
+          const double cj = __shfl_sync(mask, c, j, kGW), sj = __shfl_sync(mask, s, j, kGW);
           if (i < 72) {
             const double apk = A[pj * 12 + k], aqk = A[qj * 12 + k];
             A[pj * 12 + k] = cj * apk - sj * aqk;
@@ -209,21 +212,23 @@ __device__ __forceinline__ void stage_a(ImageState& S, int i, int K, const float
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kHypPerCta * 16, 4)
+template <int kGW>
+__global__ void __launch_bounds__(128, 4)
 pnp_hypotheses_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
                       const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d,
                       const int32_t* __restrict__ model_idx, double fx, double fy, double cx, double cy, int left_number, int mode,
                       int flags, double thr2, int n_hyp, uint32_t seed, float* __restrict__ keypoints,
                       float* __restrict__ kp_score, float* __restrict__ proposal, uint8_t* __restrict__ selected,
                       double* __restrict__ hyp /* [images][kMaxHyp][kHypRow] */) {
+  constexpr int kHypPerCta = 128 / kGW;
   __shared__ ImageState S;
   __shared__ double s_A[kHypPerCta][144];
   __shared__ double s_V[kHypPerCta][144];
 
   const int i = blockIdx.y;
   const int tid = threadIdx.x;
-  const int g = tid >> 4;                    // hypothesis slot inside the CTA
-  const int gl = tid & 15;
+  const int g = tid / kGW;                   // hypothesis slot inside the CTA
+  const int gl = tid % kGW;
   const int h = blockIdx.x * kHypPerCta + g;  // hypothesis index
   stage_a(S, i, K, preds_img, maxval, det_score, valid, kp3d, model_idx, left_number, flags, blockIdx.x == 0, keypoints, kp_score,
           proposal, selected);
@@ -244,7 +249,7 @@ pnp_hypotheses_kernel(const float* __restrict__ preds_img, const float* __restri
       bp::pnp::sample_subset(pool, m, h, seed, 5);
       m = 5;
     }
-    GroupEig12 eig{s_A[g], s_V[g], 0xFFFFu << (16 * ((tid >> 4) & 1)), gl};
+    GroupEig12<kGW> eig{s_A[g], s_V[g], ((1u << kGW) - 1u) << (kGW * ((tid & 31) / kGW)), gl};
     if (bp::pnp::epnp(eig, S.pw, S.uv, pool, m, fx, fy, cx, cy, R, t)) {
       solved = true;
       cnt = m;
@@ -368,10 +373,17 @@ extern "C" int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* ma
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const double thr2 = (double)reproj_thr * (double)reproj_thr;
-  const int groups = mode == 0 ? (n_hyp + kHypPerCta - 1) / kHypPerCta : 1;
-  pnp_hypotheses_kernel<<<dim3(groups, n), kHypPerCta * 16, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0],
-                                                                   cam[1], cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed,
-                                                                   keypoints, kp_score, proposal, selected, e->pnp_scratch);
+  if (n >= 16) {  // throughput: 8 lanes per hypothesis, 16 hypotheses per CTA
+    const int groups = mode == 0 ? (n_hyp + 15) / 16 : 1;
+    pnp_hypotheses_kernel<8><<<dim3(groups, n), 128, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1],
+                                                              cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints,
+                                                              kp_score, proposal, selected, e->pnp_scratch);
+  } else {        // latency: 16 lanes per hypothesis, 8 hypotheses per CTA
+    const int groups = mode == 0 ? (n_hyp + 7) / 8 : 1;
+    pnp_hypotheses_kernel<16><<<dim3(groups, n), 128, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1],
+                                                               cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints,
+                                                               kp_score, proposal, selected, e->pnp_scratch);
+  }
   pnp_refine_kernel<<<n, 32, 0, st>>>(preds_img, maxval, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode,
                                       flags, thr2, n_hyp, e->pnp_scratch, R, t, inlier, status);
   cudaError_t err = cudaGetLastError();
