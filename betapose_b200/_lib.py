@@ -19,7 +19,7 @@ EXPORTS = (
     "bp_net_copy_channels", "bp_net_add", "bp_net_tensor_info", "bp_net_num_launches", "bp_net_flops_per_image",
     "bp_net_forward", "bp_net_forward_range", "bp_net_num_ops", "bp_net_op_desc", "bp_resize_bicubic",
     "bp_yolo_decode_argmax", "bp_write_results", "bp_crop_resize", "bp_heatmap_decode", "bp_pose_pnp", "bp_pack_records",
-    "bp_score_poses",
+    "bp_score_poses", "bp_pose_nms",
 )
 
 ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.bp_write_results.argtypes = [vp, vp, i, i, i, f, vp, vp, vp, vp]
     L.bp_pose_pnp.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, i, i, i, f, i, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bp_pack_records.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bp_pose_nms.argtypes = [vp, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bp_score_poses.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L

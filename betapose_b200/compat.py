@@ -176,24 +176,18 @@ def getPrediction(hms, pt1, pt2, inpH, inpW, resH, resW):
 
 
 def pose_nms(bboxes, bbox_scores, pose_preds, pose_scores):
-    """pPose_nms.py:24-122 for the evaluate path, where exactly one proposal per image reaches it (yolo/util.py:
-    205-211 keeps the arg-max row): zero scores -> 1e-5 (in place, like the reference), reject if max < 0.3,
-    key-points - 0.3, proposal = mean + bbox score + 1.25 max.  More than one proposal is SURVEY.md 8(f) item 3."""
-    n = int(bboxes.shape[0])
-    if n != 1:
-        raise NotImplementedError("pose_nms with more than one proposal per image is outside the evaluate hot path "
-                                  "(the reference never produces it: yolo/util.py:181,205-211)")
+    """pPose_nms.py:24-122: parametric pose-NMS over the n proposals of one image -> list of dicts
+    {bbox (always bboxes[0], as in the reference :116), keypoints [K,2] (merged - 0.3), kp_score [K,1], proposal_score
+    [1]}.  Zero scores become 1e-5 in place, like the reference.  On the evaluate path n == 1 (yolo/util.py:205-211
+    keeps the arg-max row); n > 1 is SURVEY.md 8(f) item 3."""
     dev = _dev()
-    K = int(pose_preds.shape[1])
+    n, K = int(pose_preds.shape[0]), int(pose_preds.shape[1])
     pose_scores[pose_scores == 0] = 1e-5
-    out = stages.pose_pnp(pose_preds.to(dev, dtype=torch.float32).reshape(1, K, 2), pose_scores.to(dev, dtype=torch.float32).reshape(1, K),
-                          bbox_scores.to(dev, dtype=torch.float32).reshape(1), torch.zeros((K, 3), dtype=torch.float64, device=dev),
-                          left_number=K, flags=stages.PNP_NMS_ONLY)
-    if int(out["status"][0]) != 1:
-        return []
-    return [{"bbox": bboxes[0], "keypoints": out["keypoints"][0].to(pose_preds.device),
-             "kp_score": out["kp_score"][0].reshape(K, 1).to(pose_preds.device),
-             "proposal_score": out["proposal"].reshape(1).to(pose_preds.device)}]
+    out = stages.pose_nms(bboxes.to(dev), bbox_scores.to(dev).reshape(n), pose_preds.to(dev), pose_scores.to(dev).reshape(n, K))
+    cnt = int(out["count"][0])
+    home = pose_preds.device
+    return [{"bbox": bboxes[0], "keypoints": out["keypoints"][j].to(home), "kp_score": out["kp_score"][j].reshape(K, 1).to(home),
+             "proposal_score": out["proposal"][j].reshape(1).to(home)} for j in range(cnt)]
 
 
 def pnp(points_3D, points_2D, cameraMatrix, mode: int = stages.MODE_RANSAC):

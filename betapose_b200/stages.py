@@ -232,3 +232,28 @@ def summarize_scores(add_m, proj_px, iou, scored, diameter_mm: float, pixel_thre
                 add_accuracy=float((add_mm[sc] < diameter_mm / 10.0).mean()) if sc.any() else float("nan"),
                 proj2d_accuracy=float((proj[sc] < pixel_thresh).mean()) if sc.any() else float("nan"),
                 iou_accuracy=float((io > 0.5).mean()) if len(io) else float("nan"), n_scored=int(sc.sum()))
+
+
+def pose_nms(bboxes, bbox_scores, pose_preds, pose_scores, counts=None):
+    """General parametric pose-NMS (pPose_nms.py:24-122) for the proposals of one image (counts=None) or of several
+    images concatenated (counts: list of proposals per image).  CUDA fp32 tensors: bboxes [N,4], bbox_scores [N],
+    pose_preds [N,K,2], pose_scores [N,K].  -> dict(count int32 [n_images], pick int32 [N], keypoints [N,K,2],
+    kp_score [N,K], proposal [N]); image i's results are rows first[i] .. first[i] + count[i] - 1."""
+    e = _eng(pose_preds)
+    dev = pose_preds.device
+    N, K = int(pose_preds.shape[0]), int(pose_preds.shape[1])
+    cl = [N] if counts is None else [int(c) for c in counts]
+    assert sum(cl) == N
+    first = torch.tensor(np.concatenate([[0], np.cumsum(cl)[:-1]]).astype(np.int32), device=dev)
+    cnt = torch.tensor(cl, dtype=torch.int32, device=dev)
+    out = dict(count=torch.zeros(len(cl), dtype=torch.int32, device=dev), pick=torch.zeros(N, dtype=torch.int32, device=dev),
+               keypoints=torch.zeros((N, K, 2), dtype=torch.float32, device=dev),
+               kp_score=torch.zeros((N, K), dtype=torch.float32, device=dev), proposal=torch.zeros(N, dtype=torch.float32, device=dev),
+               first=first)
+    f32 = lambda x, shape: x.to(dev, torch.float32).reshape(shape).contiguous()  # noqa: E731
+    _lib.check(_lib.lib().bp_pose_nms(e.handle, len(cl), _lib.ptr(first), _lib.ptr(cnt), max(cl), K, _lib.ptr(f32(bboxes, (N, 4))),
+                                      _lib.ptr(f32(bbox_scores, (N,))), _lib.ptr(f32(pose_preds, (N, K, 2))),
+                                      _lib.ptr(f32(pose_scores, (N, K))), _lib.ptr(out["count"]), _lib.ptr(out["pick"]),
+                                      _lib.ptr(out["keypoints"]), _lib.ptr(out["kp_score"]), _lib.ptr(out["proposal"]),
+                                      _lib.stream_ptr()), "bp_pose_nms")
+    return out

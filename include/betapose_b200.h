@@ -200,6 +200,17 @@ int bp_pack_records(bp_engine* e, int n, int K, int image_index0, const float* b
                     const float* keypoints, const float* kp_score, const float* proposal, const double* R,
                     const double* t, const int32_t* status, bp_record* out, void* stream);
 
+/* a9 in general: parametric pose-NMS over n >= 1 proposals per image (pPose_nms.py:24-122 with
+ * p_merge_fast :204-240, get_parametric_distance :243-267, PCK_match :270-281).  Proposals of all images are
+ * concatenated: image i owns rows [first[i], first[i] + count[i]) (first == NULL: a single image starting at row 0);
+ * count[i] <= max_count <= 64, K <= 64.  bboxes [N,4] corners, bbox_scores [N], pose_preds [N,K,2], pose_scores [N,K].
+ * Outputs, written at the image's first rows in pick order: out_count[i] surviving poses, out_pick (proposal index
+ * inside the image), out_keypoints [N,K,2] (merged pose - 0.3), out_kp_score [N,K] (merged scores), out_proposal [N]
+ * (mean + bbox score of the pick + 1.25 max).  As in the reference every result carries the image's FIRST box. */
+int bp_pose_nms(bp_engine* e, int n_images, const int32_t* first, const int32_t* count, int max_count, int K, const float* bboxes,
+                const float* bbox_scores, const float* pose_preds, const float* pose_scores, int32_t* out_count, int32_t* out_pick,
+                float* out_keypoints, float* out_kp_score, float* out_proposal, void* stream);
+
 /* scoring (the evaluation loop after the per-frame path, betapose_evaluate.py:203-266): per image
  *   add_err[n]  = mean_v |(R_gt v + t_gt) - (R_est v + t_est)|        (utils/metrics.py:10-22, model units: metres)
  *   proj_err[n] = mean_v |proj(K [R_gt|t_gt] v) - proj(K [R_est|t_est] v)| in pixels (metrics.py:96-127)

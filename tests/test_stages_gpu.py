@@ -320,3 +320,70 @@ def test_score_poses_full_size_properties(kp_model):
     d = rng.standard_normal((n, 3)) * 0.01
     sh = stages.score_poses(_cuda(Rg), _cuda(tg + d), _cuda(box), _cuda(Rg), _cuda(tg), _cuda(box), _cuda(model))
     np.testing.assert_allclose(sh["add"].cpu().numpy(), np.linalg.norm(d, axis=1), rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ general pose-NMS (8(f) item 3)
+def _nms_clusters(rng, n_clusters, per_cluster, K=50):
+    """proposals scattered around `n_clusters` distinct poses: members of a cluster are within a few pixels (they are
+    suppressed and merged), clusters are far apart."""
+    bb, bs, pp, ps = [], [], [], []
+    for c in range(n_clusters):
+        centre = rng.uniform(80, 400, (K, 2)).astype(np.float32)
+        for _ in range(per_cluster):
+            p = centre + rng.normal(0, 1.5, (K, 2)).astype(np.float32)
+            x1, y1, x2, y2 = p[:, 0].min() - 5, p[:, 1].min() - 5, p[:, 0].max() + 5, p[:, 1].max() + 5
+            bb.append([x1, y1, x2, y2]); bs.append(rng.uniform(0.3, 0.99))
+            pp.append(p); ps.append(rng.uniform(0.05, 0.95, (K, 1)).astype(np.float32))
+    return np.float32(bb), np.float32(bs).reshape(-1, 1), np.float32(pp), np.float32(ps)
+
+
+def _check_nms(out, first, ref, K=50):
+    cnt = int(out["count"])
+    assert cnt == len(ref)
+    for j, r in enumerate(ref):
+        np.testing.assert_allclose(out["keypoints"][first + j].cpu().numpy(), r["keypoints"], rtol=0, atol=2e-4)
+        np.testing.assert_allclose(out["kp_score"][first + j].cpu().numpy(), r["kp_score"][:, 0], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(float(out["proposal"][first + j]), float(r["proposal_score"][0]), rtol=2e-5)
+
+
+@pytest.mark.parametrize("n_clusters,per_cluster", [(1, 1), (1, 4), (3, 3), (6, 2), (16, 4)])
+def test_pose_nms_general_matches_oracle(n_clusters, per_cluster):
+    from betapose_b200 import stages
+
+    rng = np.random.default_rng(100 * n_clusters + per_cluster)
+    bb, bs, pp, ps = _nms_clusters(rng, n_clusters, per_cluster)
+    ref = R.pose_nms(bb, bs, pp, ps)
+    out = stages.pose_nms(_cuda(bb), _cuda(bs), _cuda(pp), _cuda(ps[..., 0]))
+    torch.cuda.synchronize()
+    assert len(ref) == n_clusters  # every cluster collapses to one merged pose
+    _check_nms({k: (v[0] if k == "count" else v) for k, v in out.items()}, 0, ref)
+
+
+def test_pose_nms_reference_goldens_and_batched():
+    """The reference's own pose_nms outputs (tests/golden/pose_nms_golden.npz: n = 1, n = 3 with a merge, rejected), all
+    four cases in ONE launch (several images concatenated), and the drop-in seam for n = 3."""
+    import os
+
+    from betapose_b200 import compat, stages
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pose_nms_golden.npz"))
+    nc = int(g["n_cases"])
+    bb = np.concatenate([g[f"c{i}_bb"] for i in range(nc)]).astype(np.float32)
+    bs = np.concatenate([g[f"c{i}_bs"] for i in range(nc)]).astype(np.float32)
+    pp = np.concatenate([g[f"c{i}_pp"] for i in range(nc)]).astype(np.float32)
+    ps = np.concatenate([g[f"c{i}_ps"] for i in range(nc)]).astype(np.float32)
+    counts = [len(g[f"c{i}_bb"]) for i in range(nc)]
+    out = stages.pose_nms(_cuda(bb), _cuda(bs), _cuda(pp), _cuda(ps[..., 0]), counts=counts)
+    torch.cuda.synchronize()
+    first = out["first"].cpu().numpy()
+    for i in range(nc):
+        n_res = int(g[f"c{i}_n"])
+        assert int(out["count"][i]) == n_res
+        for j in range(n_res):
+            np.testing.assert_allclose(out["keypoints"][first[i] + j].cpu().numpy(), g[f"c{i}_r{j}_kp"], rtol=0, atol=2e-4)
+            np.testing.assert_allclose(out["kp_score"][first[i] + j].cpu().numpy(), g[f"c{i}_r{j}_sc"][:, 0], rtol=2e-5, atol=1e-6)
+            np.testing.assert_allclose(float(out["proposal"][first[i] + j]), float(g[f"c{i}_r{j}_prop"][0]), rtol=2e-5)
+    res = compat.pose_nms(torch.from_numpy(g["c2_bb"]), torch.from_numpy(g["c2_bs"]), torch.from_numpy(g["c2_pp"]), torch.from_numpy(g["c2_ps"].copy()))
+    assert len(res) == int(g["c2_n"]) and np.array_equal(res[0]["bbox"].numpy(), g["c2_r0_bbox"])
+    np.testing.assert_allclose(res[1]["keypoints"].numpy(), g["c2_r1_kp"], atol=2e-4)
+    assert res[0]["kp_score"].shape == (50, 1) and res[0]["proposal_score"].shape == (1,)
