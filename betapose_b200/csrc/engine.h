@@ -13,6 +13,7 @@ struct ResizeTables {  // Pillow bicubic coefficient tables for one (in, out) si
   int in_size = 0, out_size = 0, ksize = 0;
   int32_t* bounds = nullptr;  // [out, 2] (first tap, tap count)
   int32_t* coeffs = nullptr;  // [out, ksize] 22-bit fixed point
+  std::vector<int32_t> host_bounds;  // host copy of `bounds` (tile planning of the fused resize kernel)
 };
 
 struct bp_engine {

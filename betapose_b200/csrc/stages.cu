@@ -71,6 +71,7 @@ const ResizeTables* get_tables(bp_engine* e, int in_size, int out_size) {
   cudaMemcpy(t.coeffs, k.data(), k.size() * 4, cudaMemcpyHostToDevice);
   e->owned.push_back(t.bounds);
   e->owned.push_back(t.coeffs);
+  t.host_bounds = b;
   return &(e->resize_tables[key] = t);
 }
 
@@ -140,6 +141,88 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ in, int B, int H, in
   }
 }
 
+// Both passes in one kernel: a block owns TH output rows of one image.  It stages the input rows those need in shared
+// memory (16-byte loads), runs Pillow's horizontal pass on them into a uint8 intermediate -- the rounding to 8 bits
+// between the passes is part of the bit-exact semantics --, then the vertical pass, and writes the network-input
+// layout.  No global intermediate, coalesced traffic only; the horizontal pass is redone for the few rows neighbouring
+// tiles share.
+__global__ void __launch_bounds__(256)
+resize_fused_kernel(const uint8_t* __restrict__ in, int H, int W, int oh, int ow, const int32_t* __restrict__ hb,
+                    const int32_t* __restrict__ hk, int hks, const int32_t* __restrict__ vb, const int32_t* __restrict__ vk, int vks,
+                    int TH, int in_pitch, int mid_pitch, int max_rows, __half* __restrict__ out_net, float* __restrict__ out_f32) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  uint8_t* s_in = rs_smem;                                  // [max_rows][in_pitch]
+  uint8_t* s_mid = rs_smem + (size_t)max_rows * in_pitch;   // [max_rows][mid_pitch]
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * TH, y1 = min(oh, y0 + TH);
+  const int r0 = vb[2 * y0];
+  const int r1 = vb[2 * (y1 - 1)] + vb[2 * (y1 - 1) + 1];
+  const int nrows = r1 - r0;
+  const int row_bytes = W * 3;
+  const uint8_t* src = in + ((long)b * H + r0) * row_bytes;
+  if ((row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
+    const int vec = row_bytes >> 4;
+    for (int e = threadIdx.x; e < nrows * vec; e += blockDim.x) {
+      const int r = e / vec, c = e - r * vec;
+      reinterpret_cast<uint4*>(s_in + (size_t)r * in_pitch)[c] = __ldg(reinterpret_cast<const uint4*>(src + (long)r * row_bytes) + c);
+    }
+  } else {
+    for (int e = threadIdx.x; e < nrows * row_bytes; e += blockDim.x) {
+      const int r = e / row_bytes, c = e - r * row_bytes;
+      s_in[(size_t)r * in_pitch + c] = src[(long)r * row_bytes + c];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nrows * ow; e += blockDim.x) {
+    const int r = e / ow, xx = e - r * ow;
+    const int x0 = hb[2 * xx], n = hb[2 * xx + 1];
+    const int32_t* k = hk + (long)xx * hks;
+    const uint8_t* p = s_in + (size_t)r * in_pitch + x0 * 3;
+    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+    for (int x = 0; x < n; ++x) {
+      const int c = __ldg(k + x);
+      s0 += p[3 * x] * c;
+      s1 += p[3 * x + 1] * c;
+      s2 += p[3 * x + 2] * c;
+    }
+    uint8_t* d = s_mid + (size_t)r * mid_pitch + xx * 3;
+    d[0] = (uint8_t)clip8(s0);
+    d[1] = (uint8_t)clip8(s1);
+    d[2] = (uint8_t)clip8(s2);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < (y1 - y0) * ow; e += blockDim.x) {
+    const int yl = e / ow, xx = e - yl * ow;
+    const int yy = y0 + yl;
+    const int yb = vb[2 * yy] - r0, n = vb[2 * yy + 1];
+    const int32_t* k = vk + (long)yy * vks;
+    const uint8_t* p = s_mid + (size_t)yb * mid_pitch + xx * 3;
+    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+    for (int y = 0; y < n; ++y) {
+      const int c = __ldg(k + y);
+      const uint8_t* q = p + (size_t)y * mid_pitch;
+      s0 += q[0] * c;
+      s1 += q[1] * c;
+      s2 += q[2] * c;
+    }
+    const int r = clip8(s0), g = clip8(s1), bl = clip8(s2);
+    if (out_net) {
+      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+      __half2* h = reinterpret_cast<__half2*>(&pk);
+      h[0] = __floats2half2_rn((float)r, (float)g);
+      h[1] = __floats2half2_rn((float)bl, 0.f);
+      reinterpret_cast<uint4*>(out_net)[((long)b * oh + yy) * (ow + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + xx] = pk;
+    }
+    if (out_f32) {
+      const long plane = (long)oh * ow;
+      float* o = out_f32 + (long)b * 3 * plane + (long)yy * ow + xx;
+      o[0] = __fdiv_rn((float)r, 255.f);
+      o[plane] = __fdiv_rn((float)g, 255.f);
+      o[2 * plane] = __fdiv_rn((float)bl, 255.f);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int H, int W, int oh, int ow,
@@ -149,6 +232,33 @@ extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int
   const ResizeTables* th = get_tables(e, W, ow);
   const ResizeTables* tv = get_tables(e, H, oh);
   if (!th || !tv) return bp_fail(BP_ERR_CUDA, "bp_resize_bicubic: table upload failed");
+  {
+    // fused single-kernel path whenever a row tile fits in shared memory: largest TH (output rows per block) whose
+    // input rows + uint8 intermediate stay below ~100 KB (two blocks per SM)
+    const int in_pitch = (W * 3 + 15) / 16 * 16, mid_pitch = (ow * 3 + 15) / 16 * 16;
+    for (int TH = 32; TH >= 1; TH >>= 1) {
+      int max_rows = 0;
+      for (int y0 = 0; y0 < oh; y0 += TH) {
+        const int yl = std::min(oh, y0 + TH) - 1;
+        max_rows = std::max(max_rows, tv->host_bounds[2 * yl] + tv->host_bounds[2 * yl + 1] - tv->host_bounds[2 * y0]);
+      }
+      const size_t smem = (size_t)max_rows * (in_pitch + mid_pitch);
+      if (smem > 100 * 1024) continue;
+      if (smem > 48 * 1024) {
+        static bool attr_done = false;  // once per process (one device per process)
+        if (!attr_done) {
+          if (cudaFuncSetAttribute(resize_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) break;
+          attr_done = true;
+        }
+      }
+      dim3 grid((oh + TH - 1) / TH, B);
+      resize_fused_kernel<<<grid, 256, smem, st>>>(frames, H, W, oh, ow, th->bounds, th->coeffs, th->ksize, tv->bounds, tv->coeffs,
+                                                  tv->ksize, TH, in_pitch, mid_pitch, max_rows, (__half*)out_net, out_f32_chw);
+      cudaError_t err = cudaGetLastError();
+      return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
+    }
+  }
+  // fall-back for extreme sizes: two passes through a global uint8 intermediate
   const size_t need = (size_t)B * H * ow * 3;
   if (e->resize_tmp_bytes < need) {
     // grow-only scratch; (re)allocation happens at most once per batch size, outside steady state
@@ -418,14 +528,23 @@ __global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, int H, in
                                    const int32_t* __restrict__ img_idx, const uint8_t* __restrict__ valid, int rh, int rw,
                                    __half* __restrict__ out16, float* __restrict__ out32, float* __restrict__ pt1,
                                    float* __restrict__ pt2) {
+  // per block, once: the box geometry and the table (u / 255) - mean[c] of im_to_torch + the mean subtraction
+  // (256 x 3 exact fp32 divisions instead of twelve per output pixel)
+  __shared__ CropGeom s_g;
+  __shared__ float s_lut[3][256];
   const int i = blockIdx.y;
+  const bool ok = !valid || valid[i];
+  if (ok) {
+    if (threadIdx.x == 0) s_g = crop_geometry(box + 4 * i, W, H, rh, rw);
+    const float mean[3] = {0.406f, 0.457f, 0.480f};
+    for (int e = threadIdx.x; e < 768; e += blockDim.x) s_lut[e >> 8][e & 255] = __fadd_rn(__fdiv_rn((float)(e & 255), 255.f), -mean[e >> 8]);
+  }
+  __syncthreads();
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= rh * rw) return;
-  const bool ok = !valid || valid[i];
   float v[3] = {0.f, 0.f, 0.f};
-  CropGeom g;
   if (ok) {
-    g = crop_geometry(box + 4 * i, W, H, rh, rw);
+    const CropGeom g = s_g;
     const int oy = pix / rw, ox = pix - oy * rw;
     const float rhs = rh > 1 ? __fdiv_rn((float)(g.Hp - 1), (float)(rh - 1)) : 0.f;
     const float rws = rw > 1 ? __fdiv_rn((float)(g.Wp - 1), (float)(rw - 1)) : 0.f;
@@ -435,12 +554,10 @@ __global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, int H, in
     const float ly = __fsub_rn(ys, (float)y0), lx = __fsub_rn(xs, (float)x0);
     const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
     const uint8_t* fr = frames + (long)img_idx[i] * H * W * 3;
-    const float mean[3] = {0.406f, 0.457f, 0.480f};
     auto tap = [&](int py, int px, int c) -> float {
       const int sy = py - g.top, sx = px - g.left;  // position inside the source patch
       if (sy < 0 || sy >= g.hS || sx < 0 || sx >= g.wS) return 0.f;
-      const uint8_t u = fr[((long)(g.uly + sy) * W + (g.ulx + sx)) * 3 + c];
-      return __fadd_rn(__fdiv_rn((float)u, 255.f), -mean[c]);
+      return s_lut[c][fr[((long)(g.uly + sy) * W + (g.ulx + sx)) * 3 + c]];
     };
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

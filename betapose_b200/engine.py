@@ -112,9 +112,9 @@ class BetaposeEngine:
         return self.yolo[0].flops_per_image + self.kpd[0].flops_per_image
 
     def count_launches(self, n_slots_in_batch: int = 1) -> int:
-        """kernel launches one step enqueues: per slot 2 resize passes + detector ops + decode + crop + keypoint-net
-        ops + heat-map decode; then pnp (hypotheses + refine) + pack once."""
-        per_slot = 2 + self.yolo[0].num_ops + 1 + 1 + self.kpd[0].num_ops + 1
+        """kernel launches one step enqueues: per slot the (fused two-pass) resize + detector ops + decode + crop +
+        keypoint-net ops + heat-map decode; then pnp (hypotheses + refine) + pack once."""
+        per_slot = 1 + self.yolo[0].num_ops + 1 + 1 + self.kpd[0].num_ops + 1
         return per_slot * n_slots_in_batch + 3
 
     def _enqueue_slot(self, slot: int, b0: int, n: int, st) -> None:
