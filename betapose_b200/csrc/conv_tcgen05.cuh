@@ -372,6 +372,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float bias_next = (cl_id < total_tiles && et < BLOCK_N) ? __ldg(p.bias + (cl_id % p.n_tiles) * BLOCK_N + et) : 0.f;
     const uint32_t tfull_wait0 = smem_u32(&tmem_full_bar[0]);
     const uint32_t tempty_arrive0 = CG == 2 ? leader_addr(smem_u32(&tmem_empty_bar[0])) : smem_u32(&tmem_empty_bar[0]);
+    // Residual tiles arrive by TMA in the ring buffers the results later leave from.  The leader runs a prefetch
+    // cursor NBUF - 1 chunks ahead of the chunk being computed, across tile boundaries: right after the store of chunk
+    // g is committed, `wait_group.read 1` guarantees the store of chunk g - 1 has read its buffer, which is the buffer
+    // of chunk g - 1 + NBUF, and that chunk's residual load is issued -- about three chunk times before it is needed.
+    int pf_tile = cl_id, pf_sub = 0, pf_c = 0, pf_n0 = 0, pf_m0 = 0, pf_live = 0;
+    uint32_t pf_g = 0;  // global index of the next chunk to prefetch
+    auto pf_decode = [&]() {
+      if (pf_tile < total_tiles) {
+        const int pm = fast_div(pf_tile, p.mul_nt);
+        pf_n0 = (pf_tile - pm * p.n_tiles) * BLOCK_N;
+        pf_m0 = (pm * CG + int(rank)) * Cfg::BLOCK_M;
+        pf_live = min(N_CHUNKS, (p.Cout - pf_n0 + CHUNK - 1) / CHUNK);
+      }
+    };
+    auto pf_issue = [&]() {  // leader only: load the residual of chunk pf_g (if there is one) and advance the cursor
+      if (pf_tile >= total_tiles) return;
+      const uint32_t rb = pf_g % Cfg::NBUF;
+      mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
+      tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, pf_n0 + pf_c * CHUNK, pf_m0 + pf_sub * 128);
+      ++pf_g;
+      if (++pf_c == pf_live) {
+        pf_c = 0;
+        if (++pf_sub == MT) {
+          pf_sub = 0;
+          pf_tile += cl_num;
+          pf_decode();
+        }
+      }
+    };
+    if (p.tma_store && use_res && leader) {
+      pf_decode();
+      for (int i = 0; i < Cfg::NBUF - 1; ++i) pf_issue();
+    }
     for (int tile = cl_id; tile < total_tiles; tile += cl_num, ++it) {
       const int pm_tile = fast_div(tile, p.mul_nt);
       const int n_tile = tile - pm_tile * p.n_tiles;
@@ -386,16 +419,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       {  // bias of the next tile: in flight during this tile's epilogue
         const int nt = tile + cl_num;
         if (nt < total_tiles && et < BLOCK_N) bias_next = __ldg(p.bias + (nt - fast_div(nt, p.mul_nt) * p.n_tiles) * BLOCK_N + et);
-      }
-      if (p.tma_store && use_res && leader) {
-        // residual tile -> ring buffers (one TMA load per chunk); the stores that last used them must have read them
-        bulk_wait_group_read<(Cfg::NBUF > MT * N_CHUNKS ? Cfg::NBUF - MT * N_CHUNKS : 0)>();  // (residual layers need NBUF >= MT * N_CHUNKS: planner)
-        for (int sub = 0; sub < MT; ++sub)
-          for (int c = 0; c < live; ++c) {
-            const uint32_t rb = (chunk_ctr + sub * live + c) % Cfg::NBUF;
-            mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
-            tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, n0 + c * CHUNK, m0 + sub * 128);
-          }
       }
       bar_sync_named(1, Cfg::EPI_THREADS);  // bias visible
 
@@ -437,6 +460,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (leader) {
             tma_store_2d(&tmOut, buf, n0 + c * CHUNK, m0 + sub * 128);
             bulk_commit_group();
+            if (use_res) {
+              bulk_wait_group_read<1>();  // every store but the one just committed has read its buffer
+              pf_issue();
+            }
           }
         }
         }
