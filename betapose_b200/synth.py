@@ -188,21 +188,36 @@ def cache_dir() -> str:
     return d
 
 
+def _publish(tmp: str, final: str) -> None:
+    """atomic: several ranks of one node may build the same cache entry at the same time (torchrun on a fresh box)"""
+    os.replace(tmp, final)
+
+
 def cached_yolo_weights(seed: int = 1000) -> np.ndarray:
     p = os.path.join(cache_dir(), f"yolo_synth_{seed}.npy")
     if os.path.exists(p):
-        return np.load(p)
+        try:
+            return np.load(p)
+        except Exception:
+            pass  # unreadable entry: rebuild
     s = synth_yolo_weights(seed)
-    np.save(p, s)
+    tmp = f"{p}.{os.getpid()}.tmp.npy"
+    np.save(tmp, s)
+    _publish(tmp, p)
     return s
 
 
 def cached_kpd_state_dict(seed: int = 2000) -> dict:
     p = os.path.join(cache_dir(), f"kpd_synth_{seed}.pt")
     if os.path.exists(p):
-        return torch.load(p)
+        try:
+            return torch.load(p)
+        except Exception:
+            pass
     sd = synth_kpd_state_dict(seed)
-    torch.save(sd, p)
+    tmp = f"{p}.{os.getpid()}.tmp"
+    torch.save(sd, tmp)
+    _publish(tmp, p)
     return sd
 
 
