@@ -6,14 +6,17 @@
 //
 // Persistent, warp-specialised: one CTA per SM loops over output tiles (n-tile fastest, so the CTAs running at the
 // same time share A rows in L2 and all share the weights).
-//   warp 0    : TMA producer (A + B per k-block, STAGES-deep mbarrier ring)
-//   warp 1    : MMA issuer (one elected lane) + TMEM owner
-//   warps 2-5 : epilogue.  tcgen05.ld -> bias + activation (+ residual) -> fp16 -> swizzled smem staging ->
-//               TMA store (cp.async.bulk.tensor), 64 output channels at a time; the residual tile arrives by TMA
-//               too (prefetched while the main loop of the same tile is still running).  The epilogue of tile i
+//   warp 0    : TMA producer (A + B per k-block into a STAGES-deep mbarrier ring; warp-uniform loop, elect.sync issue)
+//   warp 1    : MMA issuer (warp-uniform loop, elect.sync issue) + TMEM owner
+//   warps 2-9 : epilogue.  tcgen05.ld -> bias + activation (+ residual) -> fp16 -> swizzled smem staging ->
+//               TMA store (cp.async.bulk.tensor), 64 output channels at a time; the residual arrives by TMA in the
+//               same ring buffers, prefetched NBUF - 1 chunks ahead across tile boundaries.  The epilogue of tile i
 //               overlaps the main loop of tile i+1 through the second TMEM accumulator.
 //   Stores that are not a dense [pixels, channels] box (fp32 heads, fused nearest-x2 upsample, fused PixelShuffle)
 //   go out as per-thread 16-byte stores instead.
+// Variants (template parameters): CG = 2 runs CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256, each CTA stages
+// half of B); MT = 2 gives a CTA 256-pixel tiles (two M = 128 MMAs per K step against one B tile) for narrow layers.
+// Launched with programmatic stream serialisation: griddepcontrol.wait sits after the set-up.
 //
 // Replaces, for the reference, every nn.Conv2d+BatchNorm2d+activation (+shortcut) block of
 // 3_6Dpose_estimator/yolo/darknet.py:252-259,333-340 and KPD/src/models/layers/SE_Resnet.py:11-40, DUC.py:12-22.
