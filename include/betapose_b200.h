@@ -6,7 +6,8 @@
  * INTEGRATION.md); each entry point names the reference code it replaces.  Conventions:
  *   - plain pointers and sizes only; device pointers are raw CUDA addresses owned by the CALLER unless stated;
  *   - every call enqueues on the given cudaStream_t (passed as void*) and never synchronises, except
- *     bp_net_conv / bp_net_finalize (load-time: host->device weight upload) and bp_*_create;
+ *     bp_net_conv (load-time: host->device weight upload), bp_*_create and the first use of a new batch size or
+ *     scratch size (descriptor encoding / a one-off cudaMalloc: outside steady state and before CUDA-graph capture);
  *   - int return: 0 = OK, negative = error, message via bp_last_error() (thread-local);
  *   - a handle is bound to one device and is not thread-safe.
  */
