@@ -45,6 +45,16 @@ def main(argv=None):
 
     occlusion = o.mode == "occlusion"
     left = o.left_keypoints if occlusion else o.nClasses  # DataWriter(cam_K, 50, ...) vs (cam_K, args.left_keypoints, ...)
+    bench_info = model_vertices = kp_sixd = None
+    if o.sixd_base:
+        # the reference's evaluation set-up (betapose_evaluate.py:86-98, 203-206): models, key-point model and ground truth
+        # of sequence --obj_id from the benchmark tree; --indir defaults to the sequence's rgb/ folder
+        from . import sixd
+
+        bench_info = sixd.load_sixd(o.sixd_base, seq=o.obj_id, nr_frames=0)
+        model_vertices, kp_sixd, _ = sixd.load_models(o.sixd_base, o.obj_id, o.nClasses)
+        if not o.inputpath and not o.inputlist:
+            o.inputpath = os.path.join(o.sixd_base, "test", f"{o.obj_id:02d}", "rgb")
     if o.synthetic:
         names = [f"synthetic_{i:06d}.png" for i in range(o.synthetic)]
         yolo_stream, kpd_sd, kp3d = synth.cached_yolo_weights(1000), synth.cached_kpd_state_dict(2000), synth.synth_kp_model(1, o.nClasses)
@@ -56,11 +66,21 @@ def main(argv=None):
         names = [os.path.join(o.inputpath, n) for n in names]
         if not names:
             raise SystemExit("no frames found")
-        with open(o.yolo_weights, "rb") as f:
-            f.read(16)
-            yolo_stream = np.fromfile(f, dtype=np.float32)
-        kpd_sd = torch.load(o.kpd_weights, map_location="cpu")
-        kp3d = model3d.load_kp_model(o.kp_model, o.nClasses)
+        if o.synthetic_weights:
+            yolo_stream, kpd_sd = synth.cached_yolo_weights(1000), synth.cached_kpd_state_dict(2000)
+        else:
+            with open(o.yolo_weights, "rb") as f:
+                f.read(16)
+                yolo_stream = np.fromfile(f, dtype=np.float32)
+            kpd_sd = torch.load(o.kpd_weights, map_location="cpu")
+        if o.kp_model:
+            kp3d = model3d.load_kp_model(o.kp_model, o.nClasses)
+        elif kp_sixd is not None:
+            kp3d = kp_sixd
+        elif o.synthetic_weights:
+            kp3d = synth.synth_kp_model(1, o.nClasses)
+        else:
+            raise SystemExit("need --kp_model or --sixd_base for the key-point model")
 
     n_total = len(names)
     lo, hi = bdist.shard_range(n_total, rank, world)
@@ -87,6 +107,10 @@ def main(argv=None):
         results = [compat.result_from_record(allrec[i], names[int(allrec[i]["image_index"])], o.nClasses) for i in range(n_total)]
         out = compat.write_json(results, o.outputpath)
         print(f"{n_total} frames, {len(out)} poses -> {os.path.join(o.outputpath, 'Betapose-results.json')}")
+        if bench_info is not None:
+            from . import sixd
+
+            sixd.evaluate_results(results, bench_info, o.obj_id, model_vertices)
         if o.profile:
             print(f"rank 0: {hi - lo} frames in {dt:.3f} s ({(hi - lo) / dt:.1f} frames/s incl. host frame generation/decoding)")
     if world > 1:

@@ -46,6 +46,11 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--kpd_weights", type=str, default="")
     p.add_argument("--kp_model", type=str, default="")
     p.add_argument("--synthetic", type=int, default=0, help="evaluate N synthetic frames with synthetic weights")
+    p.add_argument("--synthetic_weights", default=False, action="store_true",
+                   help="real frames, synthetic (seeded random) network weights: plumbing tests without checkpoints")
+    p.add_argument("--sixd_base", type=str, default="",
+                   help="SIXD / LineMod benchmark root (the reference hard-codes it, betapose_evaluate.py:91): when given, "
+                        "frames, models and ground truth come from it and the ADD / 2-D / IoU summary is printed")
     return p
 
 

@@ -234,3 +234,83 @@ def test_engine_mixed_objects_and_occlusion(yolo_stream, kpd_sd, kp_model):
         assert sel[j].sum() == 10
         top = np.sort(np.argsort(-score[j], kind="stable")[:10])
         assert np.array_equal(np.nonzero(sel[j])[0], top)
+
+
+def _mini_sixd(base, seq, rng):
+    """a miniature SIXD tree: 5 frames, models/, kpmodels/, models_info.yml, test/<seq>/{rgb,info.yml,gt.yml}"""
+    import yaml
+    from PIL import Image
+
+    from betapose_b200 import synth
+
+    (base / "models").mkdir(parents=True)
+    (base / "kpmodels").mkdir()
+    (base / "test" / f"{seq:02d}" / "rgb").mkdir(parents=True)
+    verts_mm = rng.uniform(-40, 40, (300, 3))
+    kp_mm = synth.synth_kp_model(1, 50) * 1000.0
+
+    def ply(path, v):
+        with open(path, "w") as f:
+            f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nend_header\n" % len(v))
+            for p in v:
+                f.write("%.6f %.6f %.6f\n" % tuple(p))
+
+    ply(base / "models" / f"obj_{seq:02d}.ply", verts_mm)
+    ply(base / "kpmodels" / f"obj_{seq:02d}.ply", kp_mm)
+    yaml.safe_dump({i: {"diameter": 100.0 + i} for i in range(1, 8)}, open(base / "models" / "models_info.yml", "w"))
+    frames = synth.synth_frames(5, seed=77)
+    info, gts = {}, {}
+    for i in range(5):
+        Image.fromarray(frames[i]).save(base / "test" / f"{seq:02d}" / "rgb" / f"{i:04d}.png")
+        info[i] = {"cam_K": [572.4114, 0.0, 325.2611, 0.0, 573.57043, 242.04899, 0.0, 0.0, 1.0], "depth_scale": 1.0}
+        Rm = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        gts[i] = [{"cam_R_m2c": [float(v) for v in Rm.reshape(-1)], "cam_t_m2c": [10.0 * i, -20.0, 800.0 + 10 * i],
+                   "obj_bb": [100, 80, 200, 240], "obj_id": seq if i != 3 else 2}]
+    yaml.safe_dump(info, open(base / "test" / f"{seq:02d}" / "info.yml", "w"))
+    yaml.safe_dump(gts, open(base / "test" / f"{seq:02d}" / "gt.yml", "w"))
+    return verts_mm * 0.001, gts
+
+
+def test_sixd_scoring_loop_and_cli(tmp_path, capsys):
+    """The evaluation that follows the per-frame path (betapose_evaluate.py:203-266) on a miniature SIXD tree: the scoring
+    loop against an independent recomputation with the oracle, then the whole CLI (frames + ground truth from the tree,
+    synthetic weights): Betapose-results.json plus the reference's three summary lines."""
+    from betapose_b200 import evaluate, sixd
+
+    rng = np.random.default_rng(8)
+    base, seq = tmp_path / "sixd", 5
+    verts, gts = _mini_sixd(base, seq, rng)
+    bench = sixd.load_sixd(str(base), seq)
+    mv, kp, diam = sixd.load_models(str(base), seq, 50)
+    assert len(bench.frames) == 5 and bench.diameter[seq] == 105.0 and diam == 105.0 and mv.shape == (300, 3) and kp.shape == (50, 3)
+    np.testing.assert_allclose(mv, verts, atol=1e-9)
+    # hand-made results: frame 0 near-perfect, 1 off by 3 cm, 2 no pose, 3 other object (skipped), 4 good pose but wrong box
+    final, exp_add, exp_proj, exp_iou = [], [], [], []
+    for i in range(5):
+        G = bench.frames[i].gt[0][1]
+        E = G.copy()
+        E[:3, 3] += [0.0005, 0.03, 0.0, 0.0, 0.001][i]
+        box = np.array([100, 80, 300, 320], np.float64) + ([0, 0, 0, 0] if i != 4 else [400, 300, 400, 300])
+        res = [] if i == 2 else [{"bbox": box, "keypoints": np.zeros((50, 2)), "kp_score": np.ones((50, 1)), "proposal_score": 1.0}]
+        final.append({"imgname": f"{i:04d}.png", "result": res, "cam_R": E[:3, :3], "cam_t": E[:3, 3].reshape(3, 1)})
+        if i in (2, 3):
+            continue
+        io = R.box_iou([100, 80, 300, 320], list(box))
+        exp_iou.append(io)
+        if io >= 0.5:
+            exp_add.append(R.add_err(G, E, mv) * 1000.0)
+            exp_proj.append(R.projection_error_2d(G, E, mv, R.CAM_K))
+    out = sixd.evaluate_results(final, bench, seq, mv, log=lambda *_: None)
+    assert out["n_frames"] == 3 and out["n_scored"] == len(exp_add) == 2
+    assert out["add_accuracy"] == float(np.mean(np.array(exp_add) < 10.5)) == 0.5
+    assert out["proj2d_accuracy"] == float(np.mean(np.array(exp_proj) < 5.0))
+    assert out["iou_accuracy"] == float(np.mean(np.array(exp_iou) > 0.5))
+    np.testing.assert_allclose(out["mean_add_err_mm"], np.mean(exp_add), rtol=1e-9)
+    # the CLI end to end
+    out_dir = tmp_path / "out"
+    assert evaluate.main(["--sixd_base", str(base), "--obj_id", str(seq), "--synthetic_weights", "--batch", "4", "--outdir", str(out_dir),
+                          "--nClasses", "50", "--sp"]) == 0
+    printed = capsys.readouterr().out
+    assert (out_dir / "Betapose-results.json").exists()
+    for line in ("Mean add accuracy for seq 05 is:", "2d reprojection accuracy for seq 05 is:", "Mean IoU for seq 05 is:"):
+        assert line in printed
