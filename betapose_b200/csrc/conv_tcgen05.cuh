@@ -77,6 +77,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // shared memory, and each CTA's TMEM receives its own 128 x BLOCK_N accumulator (so the epilogue is unchanged).
 // Per CTA and k-block that is 128*SWZ + BLOCK_N/2*SWZ bytes from L2 instead of 128*SWZ + BLOCK_N*SWZ: the L2->SM
 // fabric (~43 B/clk/SM on B200) is what bounds the single-CTA kernel on every compute-heavy layer.
+// MT = 2 / 4: a CTA tile is 256 / 512 pixels = MT M = 128 MMAs per K step against the same B (MT accumulators); a TMA
+// load stages 256 A rows (two loads for MT = 4).
 // MT = 2: a CTA tile is 256 pixels = two M = 128 MMAs per K step against the same B (two accumulators); one TMA load
 // stages 256 A rows.  Halves the tile count -- and with it the producer / MMA warps' per-tile and per-k-block
 // instruction overhead per pixel -- on the narrow (BLOCK_N <= 64) layers, which are bound by exactly that.
@@ -182,7 +184,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB, MT>;
-  static_assert(MT == 1 || (MT == 2 && CG == 1 && BLOCK_N <= 128 && 2 * (BLOCK_N / (BLOCK_N >= 64 ? 64 : 32)) <= NB), "256-pixel tiles: single-CTA layers up to 128 wide");
+  static_assert(MT == 1 || ((MT == 2 || MT == 4) && CG == 1 && 2 * MT * BLOCK_N <= 512), "256 / 512-pixel tiles: single-CTA layers, 2 x MT accumulators in TMEM");
   static_assert(CG == 1 || (CG == 2 && BLOCK_N >= 64), "pairs need BLOCK_N >= 64");
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32, "BLOCK_K");
@@ -267,6 +269,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           w0 = oq * p.stride - p.pad_w;
           h0 = op * p.stride - p.pad;
         }
+        int w0b = 0, h0b = 0, imgb = 0;  // MT == 4: window origin of the tile's second 256 pixels
+        if constexpr (MT == 4) {
+          if (p.a_im2col == 1) {
+            const int pq = p.P * p.Q, mb = m0 + 256;
+            imgb = fast_div(mb, p.mul_pq);
+            const int rem = mb - imgb * pq;
+            const int op = fast_div(rem, p.mul_q);
+            w0b = (rem - op * p.Q) * p.stride - p.pad_w;
+            h0b = op * p.stride - p.pad;
+          }
+        }
         int cb = 0, fr = 0, fs = 0, kcol = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
@@ -286,8 +299,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx_a(fb, Cfg::STAGE_BYTES);
             if (p.a_im2col == 1) {
               tma_load_im2col_4d_a(&tmA, fb, sa, cb, w0, h0, img, (uint16_t)fs, (uint16_t)fr);
+              if constexpr (MT == 4)
+                tma_load_im2col_4d_a(&tmA, fb, sa + uint32_t(Cfg::A_BYTES / 2), cb, w0b, h0b, imgb, (uint16_t)fs, (uint16_t)fr);
             } else {
               tma_load_2d_a(&tmA, fb, sa, kcol, m0);
+              if constexpr (MT == 4) tma_load_2d_a(&tmA, fb, sa + uint32_t(Cfg::A_BYTES / 2), kcol, m0 + 256);
             }
             tma_load_2d_a(&tmB, fb, sa + uint32_t(Cfg::A_BYTES), kcol, n0);
           }

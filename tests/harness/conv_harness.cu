@@ -235,7 +235,7 @@ static int run_case(const Case& cs) {
 // Stem convolution exactly as betapose_b200/csrc/net.cu builds it: input fp16 [N, H, W + 8, 8] (data from column 3,
 // channels 3..7 and pad columns zero), a k x 1 convolution over "virtual pixels" of Cv channels whose pixel stride
 // (16 B) is smaller than their extent; weights [Cout][r][q*8 + c].  Reference: the naive kernel on a dense C = 8 copy.
-static int run_stem_case(const char* name, int N, int H, int W, int k, int stride, int pad, int Cout, int act, int iters) {
+static int run_stem_case(const char* name, int N, int H, int W, int k, int stride, int pad, int Cout, int act, int iters, int mt = 0) {
   Rng rng(4321);
   const int PADL = 3, PADC = 8, Wp = W + PADC;
   const int Cv = k * 8 <= 32 ? 32 : 64;
@@ -283,7 +283,7 @@ static int run_stem_case(const char* name, int N, int H, int W, int k, int strid
   d.x_row_pitch = (long)Wp * 8; d.x_img_pitch = (long)H * Wp * 8;
   d.R = k; d.S = 1; d.stride = stride; d.pad = pad; d.pad_w = 0; d.real_k = k * k * 3;
   d.w = dw; d.bias = db; d.w_pitch = wp; d.Cout = Cout; d.Cout_pad = Cout_pad; d.act = act;
-  d.out = dout; d.out_pitch = Cout;
+  d.out = dout; d.out_pitch = Cout; d.force_mt = mt;
   ConvPlan pl;
   std::string err;
   if (!conv_plan_build(g_api, &pl, d, &err)) {
@@ -463,6 +463,8 @@ int main(int argc, char** argv) {
     fails += run_stem_case("stem 3x3 s1 3->32 53x47", 2, 53, 47, 3, 1, 1, 32, ACT_LEAKY, 0);
     fails += run_stem_case("stem 3x3 s1 3->32 @416 B64", 64, 416, 416, 3, 1, 1, 32, ACT_LEAKY, 5);
     fails += run_stem_case("stem 7x7 s2 3->64 @320x256 B64", 64, 320, 256, 7, 2, 3, 64, ACT_RELU, 5);
+    fails += run_stem_case("stem 3x3 3->32 53x47 mt4", 2, 53, 47, 3, 1, 1, 32, ACT_LEAKY, 0, 4);
+    fails += run_stem_case("stem 3x3 3->32 @416 B64 mt4", 64, 416, 416, 3, 1, 1, 32, ACT_LEAKY, 5, 4);
   }
 
   std::vector<Case> conv = {
@@ -508,6 +510,12 @@ int main(int argc, char** argv) {
       {"mt2 3x3 s1 C64->64", 2, 80, 64, 64, 64, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
       {"mt2 1x1 C128->64 coff", 2, 52, 52, 128, 64, 1, 1, 1, 0, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 64, 64, 0, 0, 0, 0, 0, 2},
       {"mt2 many tiles C64->32", 40, 33, 31, 64, 32, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2},
+      {"mt4 gemm C64->32 res", 3, 31, 29, 64, 32, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 32, 0, 0, 0, 0, 4},
+      {"mt4 gemm C32->64 bk32 res", 2, 33, 31, 32, 64, 1, 1, 1, 0, ACT_LEAKY, RES_BEFORE_ACT, STORE_PLAIN, 0, 0, 0, 0, 64, 0, 0, 0, 0, 4},
+      {"mt4 3x3 s2 C32->64 bk32", 2, 48, 40, 32, 64, 3, 3, 2, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 64, 0, 0, 0, 0, 4},
+      {"mt4 3x3 s1 C32->64 res", 3, 24, 27, 32, 64, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 64, 0, 0, 0, 0, 4},
+      {"mt4 3x3 s1 C32->32", 5, 24, 27, 32, 32, 3, 3, 1, 1, ACT_LEAKY, RES_NONE, STORE_PLAIN, 0, 0, 0, 0, 32, 0, 0, 0, 0, 4},
+      {"mt4 many tiles C64->32", 40, 33, 31, 64, 32, 1, 1, 1, 0, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 32, 0, 0, 0, 0, 4},
       {"mt2 bn128 3x3 C64->128 res", 3, 52, 50, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, STORE_PLAIN, 0, 0, 0, 0, 128, 0, 0, 0, 1, 2},
       {"mt2 bn128 gemm 256->384", 3, 31, 29, 256, 384, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, STORE_PLAIN, 0, 0, 0, 0, 128, 0, 0, 0, 1, 2},
   };
@@ -516,41 +524,12 @@ int main(int argc, char** argv) {
   if (!quick && fails == 0) {
     printf("---- timing (batch 64 production shapes) ----\n");
     std::vector<Case> perf = {
-        {"Y 3x3 128->256 @52 cg1", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"Y 3x3 128->256 @52 cg2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 3x3 128->256 @52 +res cg2", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 3x3 256->512 @26 cg1", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"Y 3x3 256->512 @26 cg2", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 3x3 512->1024 @13 cg1", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"Y 3x3 512->1024 @13 cg2", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 1x1 256->128 @52 cg1", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1},
-        {"Y 1x1 256->128 @52 cg2", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 2},
-        {"Y 1x1 512->256 @26 cg1", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"Y 1x1 512->256 @26 cg2", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 3x3 64->128 @104 cg1", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1},
-        {"Y 3x3 64->128 @104 mt2", 64, 104, 104, 64, 128, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1, 2},
-        {"Y 3x3/2 64->128 @104 mt1", 64, 208, 208, 64, 128, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1, 1},
-        {"Y 3x3/2 64->128 @104 mt2", 64, 208, 208, 64, 128, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 5, 0, 1, 2},
-        {"Y 1x1 256->128 @52 mt2", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 2},
-        {"K 1x1 512->128 @40x32 mt1", 64, 40, 32, 512, 128, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 1},
-        {"K 1x1 512->128 @40x32 mt2", 64, 40, 32, 512, 128, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 2},
-        {"K 3x3 128->128 @40x32 mt1", 64, 40, 32, 128, 128, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 1},
-        {"K 3x3 128->128 @40x32 mt2", 64, 40, 32, 128, 128, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 128, 0, 10, 0, 1, 2},
-        {"K 3x3 256->256 @20x16 cg1", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"K 3x3 256->256 @20x16 cg2", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"K 1x1 256->1024 +res cg1", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"K 1x1 256->1024 +res cg2", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"K 1x1 1024->256 cg1", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"K 1x1 1024->256 cg2", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"K 3x3 512->1024 ps2 cg1", 64, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 256, 0, 10, 0, 1},
-        {"K 3x3 512->1024 ps2 cg2", 64, 20, 16, 512, 1024, 3, 3, 1, 1, ACT_RELU, RES_NONE, STORE_PIXSHUF2, 0, 0, 0, 0, 256, 0, 10, 0, 2},
-        {"Y 3x3 32->64 s2 @416 bn64", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 5},
-        {"Y 3x3 32->64 s1 @208 +res", 64, 208, 208, 32, 64, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 64, 0, 5},
-        {"K 3x3 64->64 @80x64 bn64", 64, 80, 64, 64, 64, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 64, 0, 10},
-        {"K 1x1 64->256 @80x64 +res", 64, 80, 64, 64, 256, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
-        {"Y 1x1 64->32 @208", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
-        {"Y 1x1 128->64 @104", 64, 104, 104, 128, 64, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 5},
-        {"K 3x3 128->50 f32 head", 64, 80, 64, 128, 50, 3, 3, 1, 1, ACT_NONE, RES_NONE, STORE_PLAIN, 1, 0, 2, 0, 0, 0, 10},
+        {"Y 3x3 32->64 s2 @416 mt2", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 5, 0, 0, 2},
+        {"Y 3x3 32->64 s2 @416 mt4", 64, 416, 416, 32, 64, 3, 3, 2, 1, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 64, 0, 5, 0, 0, 4},
+        {"Y 3x3 32->64 s1 @208 +res mt2", 64, 208, 208, 32, 64, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 64, 0, 5, 0, 0, 2},
+        {"Y 3x3 32->64 s1 @208 +res mt4", 64, 208, 208, 32, 64, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 64, 0, 5, 0, 0, 4},
+        {"Y 1x1 64->32 @208 mt2", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 32, 0, 5, 0, 0, 2},
+        {"Y 1x1 64->32 @208 mt4", 64, 208, 208, 64, 32, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 32, 0, 5, 0, 0, 4},
     };
     for (auto& c : perf) fails += run_case(c);
   }
