@@ -144,3 +144,42 @@ def test_model3d_ply_roundtrip(tmp_path):
     with pytest.raises(ValueError):
         model3d.load_kp_model(str(q), 50)   # the shipped obj-10 model has 17 points
     assert np.array_equal(model3d.CAM_K, R.CAM_K)
+
+
+def test_sixd_loader_and_score_summary(tmp_path):
+    """Host side of the evaluation loop: the SIXD tree loader (utils/sixd.py:60-111 semantics: millimetres -> metres, diameters
+    indexed by object id, first ground-truth entry per frame) and the reference's summary arithmetic
+    (betapose_evaluate.py:259-266) on hand-made per-frame errors."""
+    import yaml
+
+    from betapose_b200 import sixd, stages
+
+    base = tmp_path / "sixd"
+    (base / "models").mkdir(parents=True)
+    (base / "kpmodels").mkdir()
+    (base / "test" / "02").mkdir(parents=True)
+    yaml.safe_dump({1: {"diameter": 102.1}, 2: {"diameter": 247.5}}, open(base / "models" / "models_info.yml", "w"))
+    yaml.safe_dump({"fx": 500.0, "fy": 501.0, "cx": 320.0, "cy": 240.0}, open(base / "camera.yml", "w"))
+    yaml.safe_dump({0: {"cam_K": [1, 0, 2, 0, 3, 4, 0, 0, 1]}, 1: {"cam_K": [1, 0, 2, 0, 3, 4, 0, 0, 1]}}, open(base / "test" / "02" / "info.yml", "w"))
+    yaml.safe_dump({0: [{"cam_R_m2c": [1, 0, 0, 0, 1, 0, 0, 0, 1], "cam_t_m2c": [10.0, 20.0, 900.0], "obj_bb": [5, 6, 70, 80], "obj_id": 2}],
+                    1: [{"cam_R_m2c": [0, 1, 0, -1, 0, 0, 0, 0, 1], "cam_t_m2c": [0.0, 0.0, 1000.0], "obj_bb": [1, 2, 3, 4], "obj_id": 9},
+                        {"cam_R_m2c": [1, 0, 0, 0, 1, 0, 0, 0, 1], "cam_t_m2c": [1.0, 1.0, 1.0], "obj_bb": [0, 0, 1, 1], "obj_id": 2}]},
+                   open(base / "test" / "02" / "gt.yml", "w"))
+    with open(base / "models" / "obj_02.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nend_header\n1 2 3\n4 5 6\n7 8 10\n")
+    kp = np.random.default_rng(0).uniform(-50, 50, (50, 3))
+    with open(base / "kpmodels" / "obj_02.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 50\nproperty float x\nproperty float y\nproperty float z\nend_header\n")
+        f.write("\n".join("%.5f %.5f %.5f" % tuple(p) for p in kp) + "\n")
+    b = sixd.load_sixd(str(base), 2)
+    assert b.diameter == [10000.0, 102.1, 247.5] and b.cam[0, 0] == 500.0 and b.cam[1, 2] == 240.0 and len(b.frames) == 2
+    oid, pose, bb = b.frames[0].gt[0]
+    assert oid == 2 and bb == [5.0, 6.0, 70.0, 80.0] and np.allclose(pose[:3, 3], [0.01, 0.02, 0.9]) and np.array_equal(pose[:3, :3], np.eye(3))
+    assert b.frames[1].gt[0][0] == 9 and len(b.frames[1].gt) == 2 and b.frames[1].path.endswith("0001.png")
+    assert len(sixd.load_sixd(str(base), None).frames) == 0
+    verts, kpm, diam = sixd.load_models(str(base), 2, 50)
+    assert diam == 247.5 and np.allclose(verts, np.array([[1, 2, 3], [4, 5, 6], [7, 8, 10]]) * 0.001) and np.allclose(kpm, kp * 0.001, atol=1e-8)
+    s = stages.summarize_scores(np.array([0.001, 0.030, 0.005, 0.5]), np.array([1.0, 9.0, 4.9, 100.0]), np.array([0.9, 0.7, 0.51, 0.2]),
+                                np.array([1, 1, 1, 0], np.uint8), diameter_mm=100.0)
+    assert s["n_scored"] == 3 and s["add_accuracy"] == 2 / 3 and s["proj2d_accuracy"] == 2 / 3 and s["iou_accuracy"] == 0.75
+    assert abs(s["mean_add_err_mm"] - 12.0) < 1e-9
