@@ -29,7 +29,7 @@ class BetaposeEngine:
     def __init__(self, max_batch: int, yolo_streams, kpd_state_dicts, kp3d, cfg_blocks=None, frame_h: int = 480,
                  frame_w: int = 640, reso: int = 416, inp_h: int = 320, inp_w: int = 256, n_kp: int = 50,
                  left_number: int = 50, conf: float = 0.01, pnp_mode: int = stages.MODE_RANSAC, reproj_thr: float = 12.0,
-                 n_hyp: int = 64, seed: int = 0, cam_K=stages.CAM_K, device=None):
+                 n_hyp: int = 64, seed: int = 0, cam_K=stages.CAM_K, device=None, concurrent_slots: bool | None = None):
         """yolo_streams: fp32 darknet weight stream (or list, one per object slot); kpd_state_dicts: FastPose
         state_dict (or list); kp3d: float64 [K,3] (or [n_slots,K,3]) key-point model in metres."""
         _lib.require_cuda()
@@ -45,6 +45,11 @@ class BetaposeEngine:
             kpd_state_dicts = [kpd_state_dicts]
         assert len(yolo_streams) == len(kpd_state_dicts)
         self.n_slots = len(yolo_streams)
+        # Mixed-object batches (BASELINE configs[3]): every slot (object) sees only a few frames, so its convolutions fill a
+        # fraction of the machine.  With concurrent_slots the slots get their own activation buffers and run on their
+        # own CUDA streams (forked from / joined into the caller's stream, also inside graph capture), so their small
+        # grids overlap.  Costs (max_batch x 133 MB) of activations per extra slot; default: on for up to 16 slots.
+        self.concurrent_slots = (1 < self.n_slots <= 16) if concurrent_slots is None else bool(concurrent_slots and self.n_slots > 1)
         blocks = cfg_blocks if cfg_blocks is not None else yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
         self.blocks = blocks
 
@@ -54,11 +59,13 @@ class BetaposeEngine:
         self.hm_id: list[int] = []
         with torch.cuda.device(self.device):
             for s in range(self.n_slots):
-                y = _net.Net(self.B, reso, reso, _lib.IN_RAW255, share=self.yolo[0] if s else None, device=self.device.index)
+                shared = None if self.concurrent_slots else (self.yolo[0] if s else None)
+                y = _net.Net(self.B, reso, reso, _lib.IN_RAW255, share=shared, device=self.device.index)
                 params, used = _net.split_darknet_stream(blocks, np.asarray(yolo_streams[s], np.float32))
                 self.heads.append(_net.build_darknet(y, blocks, params))
                 self.yolo.append(y)
-                k = _net.Net(self.B, inp_h, inp_w, _lib.IN_F16, share=self.kpd[0] if s else None, device=self.device.index)
+                k = _net.Net(self.B, inp_h, inp_w, _lib.IN_F16, share=None if self.concurrent_slots else (self.kpd[0] if s else None),
+                             device=self.device.index)
                 self.hm_id.append(_net.build_fastpose(k, kpd_state_dicts[s], self.K))
                 self.kpd.append(k)
             kp3d = np.asarray(kp3d, np.float64)
@@ -135,6 +142,13 @@ class BetaposeEngine:
                                     off(self.valid), n, self.inp_h, self.inp_w, C.c_void_p(kpd.tensor_info(0)["ptr"]), None,
                                     off(self.pt1), off(self.pt2), st), "bp_crop_resize")
         _lib.check(L.bp_net_forward(kpd.handle, n, st), "bp_net_forward(kpd)")
+
+    def _enqueue_decode(self, slot: int, b0: int, n: int, st) -> None:
+        """a8 for the images of one slot (kept on the caller's stream: the engine-level scratch of the sliced arg-max is
+        shared between calls)."""
+        L, e = _lib.lib(), self.yolo[slot].engine.handle
+        kpd = self.kpd[slot]
+        off = lambda t: C.c_void_p(t.data_ptr() + b0 * t.stride(0) * t.element_size())  # noqa: E731
         hi = kpd.tensor_info(self.hm_id[slot])
         _lib.check(L.bp_heatmap_decode(e, C.c_void_p(hi["ptr"]), hi["H"] * hi["W"] * hi["pitch"], 1, hi["pitch"], n, self.K,
                                        hi["H"], hi["W"], self.inp_h, self.inp_w, off(self.pt1), off(self.pt2),
@@ -156,8 +170,23 @@ class BetaposeEngine:
 
     def _enqueue(self, n: int, groups, image_index0: int) -> None:
         st = _lib.stream_ptr()
-        for slot, b0, cnt in groups:
-            self._enqueue_slot(slot, b0, cnt, st)
+        if self.concurrent_slots and len(groups) > 1:
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_slot_streams"):
+                self._slot_streams = [torch.cuda.Stream() for _ in range(self.n_slots)]
+            for slot, b0, cnt in groups:
+                side = self._slot_streams[slot]
+                side.wait_stream(main)  # fork (also valid under CUDA-graph capture)
+                with torch.cuda.stream(side):
+                    self._enqueue_slot(slot, b0, cnt, _lib.stream_ptr())
+            for slot, _, _ in groups:
+                main.wait_stream(self._slot_streams[slot])  # join
+            for slot, b0, cnt in groups:
+                self._enqueue_decode(slot, b0, cnt, st)
+        else:
+            for slot, b0, cnt in groups:  # slots share activation buffers: decode a slot's heat-maps before the next slot runs
+                self._enqueue_slot(slot, b0, cnt, st)
+                self._enqueue_decode(slot, b0, cnt, st)
         self._enqueue_tail(n, image_index0, st)
 
     # ------------------------------------------------------------------------------------------------

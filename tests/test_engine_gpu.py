@@ -199,10 +199,13 @@ def test_engine_batch64_permutation_invariance(yolo_stream, kpd_sd, kp_model):
     torch.cuda.empty_cache()
 
 
-def test_engine_mixed_objects_and_occlusion(yolo_stream, kpd_sd, kp_model):
+@pytest.mark.parametrize("concurrent", [True, False])
+def test_engine_mixed_objects_and_occlusion(yolo_stream, kpd_sd, kp_model, concurrent):
     """configs[3] / configs[4] shape: a batch that mixes two object slots (own detector + key-point net + key-point
     model each, shared activation buffers) and the Occlusion-LineMod setting left_keypoints = 10.  Every frame must get
-    exactly what a single-object engine of its slot produces; the 10 selected points are the 10 best-scored ones."""
+    exactly what a single-object engine of its slot produces; the 10 selected points are the 10 best-scored ones.  Both
+    schedules: slots concurrently on side streams with their own activation buffers, and one after the other on shared
+    buffers."""
     from betapose_b200 import synth
     from betapose_b200.engine import BetaposeEngine
 
@@ -210,8 +213,9 @@ def test_engine_mixed_objects_and_occlusion(yolo_stream, kpd_sd, kp_model):
     kp2 = synth.synth_kp_model(2, 50)
     frames = synth.synth_frames(6, seed=33)
     slots = np.array([0, 1, 1, 0, 1, 0])
-    mixed = BetaposeEngine(6, [yolo_stream, ys2], [kpd_sd, ks2], np.stack([kp_model, kp2]), left_number=10, seed=5)
-    got = mixed.run(frames, obj_slots=slots).copy()
+    mixed = BetaposeEngine(6, [yolo_stream, ys2], [kpd_sd, ks2], np.stack([kp_model, kp2]), left_number=10, seed=5,
+                           concurrent_slots=concurrent)
+    got = mixed.run(frames, obj_slots=slots, graph=concurrent).copy()
     sel = mixed.selected.cpu().numpy()
     score = mixed.kp_score.cpu().numpy()
     order = np.argsort(slots, kind="stable")  # the engine processes the batch grouped by slot
