@@ -18,7 +18,7 @@ import time
 import numpy as np
 import torch
 
-from . import compat, dist as bdist, model3d, stages, synth
+from . import yolo_cfg, compat, dist as bdist, model3d, stages, synth
 from .engine import BetaposeEngine
 from .opt import parse_args
 
@@ -69,10 +69,13 @@ def main(argv=None):
         if o.synthetic_weights:
             yolo_stream, kpd_sd = synth.cached_yolo_weights(1000), synth.cached_kpd_state_dict(2000)
         else:
-            with open(o.yolo_weights, "rb") as f:
-                f.read(16)
-                yolo_stream = np.fromfile(f, dtype=np.float32)
+            from . import weights
+
+            _, yolo_stream = weights.read_darknet_weights(o.yolo_weights)
+            weights.check_darknet_stream(yolo_cfg.parse_cfg_text(open(o.yolo_cfg).read() if o.yolo_cfg else yolo_cfg.default_cfg_text()),
+                                         yolo_stream)
             kpd_sd = torch.load(o.kpd_weights, map_location="cpu")
+            weights.check_fastpose_state_dict(kpd_sd, o.nClasses)
         if o.kp_model:
             kp3d = model3d.load_kp_model(o.kp_model, o.nClasses)
         elif kp_sixd is not None:

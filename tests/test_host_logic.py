@@ -183,3 +183,42 @@ def test_sixd_loader_and_score_summary(tmp_path):
                                 np.array([1, 1, 1, 0], np.uint8), diameter_mm=100.0)
     assert s["n_scored"] == 3 and s["add_accuracy"] == 2 / 3 and s["proj2d_accuracy"] == 2 / 3 and s["iou_accuracy"] == 0.75
     assert abs(s["mean_add_err_mm"] - 12.0) < 1e-9
+
+
+def test_weight_format_tooling(tmp_path):
+    """darknet .weights round trip (header, stream, per-block split and its inverse, size / truncation checks) and the
+    FastPose state_dict schema (the 654 reference keys; missing / mis-shaped / unexpected keys are named)."""
+    import torch
+
+    from betapose_b200 import net as bnet, synth, weights, yolo_cfg
+
+    blocks = yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+    assert weights.darknet_stream_size(blocks) == 61523734 + 2 * sum(int(b["filters"]) for b in blocks if b["type"] == "convolutional" and int(b.get("batch_normalize", 0)))
+    stream = synth.cached_yolo_weights(1000)
+    weights.check_darknet_stream(blocks, stream)
+    p = tmp_path / "x.weights"
+    weights.write_darknet_weights(str(p), stream, seen=1234)
+    hdr, back = weights.read_darknet_weights(str(p))
+    assert hdr.tolist() == [0, 1, 0, 1234] and np.array_equal(back, stream)
+    params, used = bnet.split_darknet_stream(blocks, stream)
+    assert used == stream.size and np.array_equal(weights.darknet_stream_from_params(blocks, params), stream)
+    with pytest.raises(ValueError, match="truncated"):
+        weights.check_darknet_stream(blocks, stream[:-5])
+    with pytest.raises(ValueError, match="left over"):
+        weights.check_darknet_stream(blocks, np.concatenate([stream, np.zeros(3, np.float32)]))
+    sd = synth.cached_kpd_state_dict(2000)
+    exp = weights.fastpose_expected_shapes(50)
+    assert len(exp) + sum(1 for k in sd if k.endswith("num_batches_tracked")) == 654 == len(sd)
+    weights.check_fastpose_state_dict(sd)
+    bad = dict(sd)
+    del bad["preact.layer3.7.bn2.running_var"]
+    with pytest.raises(ValueError, match="missing 'preact.layer3.7.bn2.running_var'"):
+        weights.check_fastpose_state_dict(bad)
+    bad = dict(sd)
+    bad["duc1.conv.weight"] = torch.zeros(1024, 256, 3, 3)
+    with pytest.raises(ValueError, match="duc1.conv.weight"):
+        weights.check_fastpose_state_dict(bad)
+    bad = dict(sd)
+    bad["module.extra"] = torch.zeros(1)
+    with pytest.raises(ValueError, match="unexpected key"):
+        weights.check_fastpose_state_dict(bad)
