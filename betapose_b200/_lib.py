@@ -19,8 +19,11 @@ EXPORTS = (
     "bp_net_copy_channels", "bp_net_add", "bp_net_tensor_info", "bp_net_num_launches", "bp_net_flops_per_image",
     "bp_net_forward", "bp_net_forward_range", "bp_net_num_ops", "bp_net_op_desc", "bp_resize_bicubic",
     "bp_yolo_decode_argmax", "bp_write_results", "bp_crop_resize", "bp_heatmap_decode", "bp_pose_pnp", "bp_pack_records",
-    "bp_score_poses", "bp_pose_nms",
+    "bp_score_poses", "bp_pose_nms", "bp_ingest_create", "bp_ingest_destroy", "bp_ingest_num_threads", "bp_png_info",
+    "bp_png_decode", "bp_ingest_submit", "bp_ingest_wait", "bp_zlib_inflate",
 )
+ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO = -1, -2, -3, -4
+ORDER_RGB, ORDER_BGR = 0, 1  # frame ingest channel orders
 
 ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 RES_NONE, RES_AFTER_ACT, RES_BEFORE_ACT = 0, 1, 2
@@ -104,6 +107,16 @@ def lib() -> C.CDLL:
     L.bp_pack_records.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bp_pose_nms.argtypes = [vp, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bp_score_poses.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
+    L.bp_ingest_create.argtypes = [i, C.POINTER(vp)]
+    L.bp_ingest_destroy.argtypes = [vp]
+    L.bp_ingest_destroy.restype = None
+    L.bp_ingest_num_threads.argtypes = [vp]
+    L.bp_png_info.argtypes = [vp, C.c_size_t, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    L.bp_png_decode.argtypes = [vp, C.c_size_t, i, i, i, vp, C.c_size_t]
+    L.bp_ingest_submit.argtypes = [vp, C.POINTER(C.c_char_p), i, i, i, i, vp, C.c_size_t, vp]
+    L.bp_ingest_submit.restype = C.c_int64
+    L.bp_ingest_wait.argtypes = [vp, C.c_int64]
+    L.bp_zlib_inflate.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = L
     return L
 

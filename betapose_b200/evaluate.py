@@ -23,17 +23,6 @@ from .engine import BetaposeEngine
 from .opt import parse_args
 
 
-def _load_frames(paths):
-    from PIL import Image  # frame decode is outside the hot path
-
-    out = np.empty((len(paths), 480, 640, 3), np.uint8)
-    for i, p in enumerate(paths):
-        im = np.asarray(Image.open(p).convert("RGB"))
-        assert im.shape == (480, 640, 3), f"{p}: expected a 640x480 frame, got {im.shape}"
-        out[i] = im
-    return out
-
-
 def main(argv=None):
     o = parse_args(argv)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -94,13 +83,22 @@ def main(argv=None):
     recs = []
     t0 = time.time()
 
-    def batches():  # frame decoding / generation of batch i+1 overlaps the GPU work of batch i (BetaposeEngine.run_stream)
-        for b0 in range(lo, hi, B):
-            b1 = min(hi, b0 + B)
-            yield synth.synth_frames(b1 - b0, seed=b0) if o.synthetic else _load_frames(names[b0:b1])
+    ingest = None
+    if o.synthetic:
+        def batches():  # generation of batch i+1 overlaps the GPU work of batch i (BetaposeEngine.run_stream)
+            for b0 in range(lo, hi, B):
+                yield synth.synth_frames(min(hi, b0 + B) - b0, seed=b0)
+        stream = batches()
+    else:
+        # the native decoder pool fills pinned batch buffers `ingest_depth` batches ahead of the GPU
+        from .ingest import FrameIngest
 
-    for rec in eng.run_stream(batches(), graph=True, image_index0=lo):
+        ingest = FrameIngest(o.ingest_threads)
+        stream = ingest.batches(names[lo:hi], B, depth=o.ingest_depth)
+    for rec in eng.run_stream(stream, graph=True, image_index0=lo):
         recs.append(rec)
+    if ingest is not None:
+        ingest.close()
     torch.cuda.synchronize()
     dt = time.time() - t0
     mine = np.concatenate(recs) if recs else np.zeros(0, stages.RECORD_DTYPE)
@@ -115,7 +113,7 @@ def main(argv=None):
 
             sixd.evaluate_results(results, bench_info, o.obj_id, model_vertices)
         if o.profile:
-            print(f"rank 0: {hi - lo} frames in {dt:.3f} s ({(hi - lo) / dt:.1f} frames/s incl. host frame generation/decoding)")
+            print(f"rank 0: {hi - lo} frames in {dt:.3f} s ({(hi - lo) / dt:.1f} frames/s incl. host frame generation / decoding)")
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -1,0 +1,139 @@
+"""Frame ingest: image files -> uint8 [n, H, W, 3] RGB frames in pinned host memory, decoded by
+the native thread pool of libbetapose_b200.so (csrc/ingest.cu) ahead of the GPU.
+
+The reference decodes every frame twice (cv2.imread for `orig_img`, PIL.Image.open for the detector input) on the one
+Python thread of `ImageLoader.getitem_yolo` (dataloader.py:150-179; yolo/preprocess.py:34-46).  Here one decode per frame
+lands directly in the buffer `BetaposeEngine.run_stream` uploads from; `FrameIngest.batches` keeps `depth` batches in
+flight so decoding, the host->device copy and the GPU step of three different batches overlap.
+
+Files the native decoder does not handle (JPEG, Adam7-interlaced PNG) are decoded with Pillow on the calling thread --
+host-side image decoding is outside the CUDA path either way; corrupt files raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _Ticket:
+    __slots__ = ("id", "paths", "c_paths", "status", "out", "n")
+
+
+class FrameIngest:
+    def __init__(self, n_threads: int = 0, frame_h: int = 480, frame_w: int = 640, order: str = "rgb"):
+        self.H, self.W = int(frame_h), int(frame_w)
+        self.order = {"rgb": _lib.ORDER_RGB, "bgr": _lib.ORDER_BGR}[order]
+        h = C.c_void_p()
+        _lib.check(_lib.lib().bp_ingest_create(int(n_threads), C.byref(h)), "bp_ingest_create")
+        self.handle = h
+        self.n_threads = _lib.lib().bp_ingest_num_threads(h)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().bp_ingest_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ single in-memory stream (calling thread)
+    @staticmethod
+    def png_info(data: bytes) -> dict:
+        vals = [C.c_int() for _ in range(4)]
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        _lib.check(_lib.lib().bp_png_info(buf, len(data), *[C.byref(v) for v in vals]), "bp_png_info")
+        return dict(zip(("H", "W", "channels", "depth"), (v.value for v in vals)))
+
+    def decode_bytes(self, data: bytes, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.H, self.W, 3), np.uint8)
+        assert out.dtype == np.uint8 and out.shape == (self.H, self.W, 3) and out.strides[1:] == (3, 1)
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        _lib.check(_lib.lib().bp_png_decode(buf, len(data), self.H, self.W, self.order, C.c_void_p(out.ctypes.data), out.strides[0]),
+                   "bp_png_decode")
+        return out
+
+    # ------------------------------------------------------------------ files, through the pool
+    def _frame_buffer(self, n: int) -> torch.Tensor:
+        t = torch.empty((n, self.H, self.W, 3), dtype=torch.uint8)
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    def submit(self, paths, out: torch.Tensor | np.ndarray) -> _Ticket:
+        """Queue `paths` for decoding into out[:len(paths)] (uint8 [>=n, H, W, 3], C-contiguous).  Returns at once."""
+        n = len(paths)
+        assert n > 0 and tuple(out.shape[1:]) == (self.H, self.W, 3) and out.shape[0] >= n
+        if isinstance(out, torch.Tensor):
+            assert out.dtype == torch.uint8 and out.is_contiguous() and not out.is_cuda
+            addr = out.data_ptr()
+        else:
+            assert out.dtype == np.uint8 and out.flags.c_contiguous
+            addr = out.ctypes.data
+        t = _Ticket()
+        t.paths, t.n, t.out = list(paths), n, out  # keep the buffers alive until wait()
+        t.c_paths = (C.c_char_p * n)(*[str(p).encode() for p in paths])
+        t.status = np.zeros(n, np.int32)
+        t.id = _lib.lib().bp_ingest_submit(self.handle, t.c_paths, n, self.H, self.W, self.order, C.c_void_p(addr), 0,
+                                           C.c_void_p(t.status.ctypes.data))
+        _lib.check(int(t.id), "bp_ingest_submit")
+        return t
+
+    def wait(self, t: _Ticket):
+        """Block until the ticket's files are decoded; returns out[:n]."""
+        rc = _lib.lib().bp_ingest_wait(self.handle, t.id)
+        if rc != 0:
+            msg = _lib.lib().bp_last_error().decode("utf-8", "replace")
+            hard = np.flatnonzero((t.status != 0) & (t.status != _lib.ERR_UNSUPPORTED))
+            if hard.size:
+                raise _lib.BetaposeError(f"frame ingest: {hard.size} file(s) failed, first: {msg} (code {rc})")
+            for i in np.flatnonzero(t.status == _lib.ERR_UNSUPPORTED):
+                self._decode_with_pillow(t.paths[i], t.out[i])
+        return t.out[: t.n]
+
+    def _decode_with_pillow(self, path, dst):
+        from PIL import Image
+
+        im = np.asarray(Image.open(path).convert("RGB"))
+        if im.shape != (self.H, self.W, 3):
+            raise _lib.BetaposeError(f"{path}: expected a {self.W}x{self.H} frame, got {im.shape[1]}x{im.shape[0]}")
+        if self.order == _lib.ORDER_BGR:
+            im = im[:, :, ::-1]
+        if isinstance(dst, torch.Tensor):
+            dst.copy_(torch.from_numpy(np.ascontiguousarray(im)))
+        else:
+            dst[...] = im
+
+    def decode_files(self, paths, out=None):
+        if out is None:
+            out = np.empty((len(paths), self.H, self.W, 3), np.uint8)
+        return self.wait(self.submit(paths, out))
+
+    def batches(self, paths, batch: int, depth: int = 2):
+        """Yield uint8 [n <= batch, H, W, 3] host tensors (pinned when CUDA is present) for consecutive slices of `paths`,
+        with up to `depth` later batches decoding in the pool meanwhile.  A yielded tensor stays valid until two more
+        batches have been requested -- what BetaposeEngine.run_stream needs: it may still be uploading batch k+1 when it
+        asks for batch k+2, and has finished with batch k by then."""
+        paths = list(paths)
+        starts = list(range(0, len(paths), batch))
+        ring = [self._frame_buffer(batch) for _ in range(min(len(starts), depth + 3))]
+        tickets = {}
+
+        def submit(j):
+            tickets[j] = self.submit(paths[starts[j]: starts[j] + batch], ring[j % len(ring)])
+
+        for j in range(min(depth + 1, len(starts))):
+            submit(j)
+        for j in range(len(starts)):
+            fr = self.wait(tickets.pop(j))
+            nxt = j + depth + 1
+            if nxt < len(starts):
+                submit(nxt)  # reuses the buffer of batch nxt - (depth + 3) = j - 2: the caller is done with it (see above)
+            yield fr

@@ -25,6 +25,7 @@ extern "C" {
 #define BP_ERR_INVALID (-1)
 #define BP_ERR_CUDA (-2)
 #define BP_ERR_UNSUPPORTED (-3)
+#define BP_ERR_IO (-4)
 
 /* activation / residual / store selectors of a fused conv block */
 #define BP_ACT_NONE 0
@@ -223,6 +224,35 @@ int bp_score_poses(bp_engine* e, int n, const double* R_est, const double* t_est
                    const float* box_est, const double* R_gt, const double* t_gt, const float* box_gt, const double* model,
                    const int32_t* model_idx, int n_vertices, const double* cam, double* add_err, double* proj_err, float* iou,
                    uint8_t* scored, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- frame ingest
+ * what stands before a1 -- cv2.imread / PIL.Image.open per frame, twice, on one Python thread
+ * (ImageLoader.getitem_yolo, dataloader.py:150-179; prep_image, yolo/preprocess.py:34-46).  Host-only (no CUDA call, no
+ * bp_engine): a pool of threads decodes PNG files straight into caller memory, normally the pinned buffers the engine
+ * uploads from, so decoding of batch i+1.. overlaps the GPU work of batch i.  The result is the 8-bit 3-channel image
+ * both reference decoders produce: alpha dropped, grey replicated, palette expanded, 16-bit samples reduced to the high
+ * byte.  Non-PNG streams and Adam7-interlaced files return BP_ERR_UNSUPPORTED (the caller decodes those elsewhere). */
+#define BP_ORDER_RGB 0 /* PIL.Image.open: the detector branch and this engine's frame layout */
+#define BP_ORDER_BGR 1 /* cv2.imread: the reference's orig_img */
+typedef struct bp_ingest bp_ingest;
+/* n_threads <= 0: one per hardware thread */
+int bp_ingest_create(int n_threads, bp_ingest** out);
+/* waits for queued files (their output buffers must stay valid until this returns) */
+void bp_ingest_destroy(bp_ingest* g);
+int bp_ingest_num_threads(bp_ingest* g);
+/* header fields of an in-memory PNG; channels counts the stored samples per pixel (palette = 3) */
+int bp_png_info(const uint8_t* png, size_t len, int* H, int* W, int* channels, int* depth);
+/* decode one in-memory PNG on the calling thread into out[H][row_pitch] (row_pitch 0 = 3*W); the file must be HxW */
+int bp_png_decode(const uint8_t* png, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch);
+/* the ingest's inflate on its own: one whole zlib stream (RFC 1950) -> out[0..out_cap); *out_len = bytes produced.
+ * BP_ERR_INVALID for corrupt / truncated streams and for streams that hold more than out_cap bytes. */
+int bp_zlib_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len);
+/* queue n files; file i is decoded into out + i*frame_pitch (frame_pitch 0 = H*W*3) and status[i] (may be NULL) gets
+ * its return code.  Returns a ticket > 0, or a negative error.  May be called again before earlier tickets finished. */
+int64_t bp_ingest_submit(bp_ingest* g, const char* const* paths, int n, int H, int W, int order, uint8_t* out, size_t frame_pitch,
+                         int32_t* status);
+/* blocks until every file of the ticket is done; 0, or the first failing file's code with its path in bp_last_error() */
+int bp_ingest_wait(bp_ingest* g, int64_t ticket);
 
 #ifdef __cplusplus
 }

@@ -176,6 +176,29 @@ def test_run_stream_matches_run(engine, frames8):
             assert np.array_equal(g[f], r[f]), f
 
 
+def test_run_stream_from_png_files_through_the_native_ingest(engine, frames8, tmp_path):
+    """frames on disk -> decoder pool -> pinned ring -> run_stream.  Same records as feeding the arrays,
+    over enough batches that every ring buffer is reused while uploads of earlier batches are still in flight."""
+    from PIL import Image
+
+    from betapose_b200.ingest import FrameIngest
+
+    order = [(3 * i) % 8 for i in range(19)]
+    paths = []
+    for j, i in enumerate(order):
+        p = str(tmp_path / f"{j:03d}.png")
+        Image.fromarray(frames8[i]).save(p, compress_level=1)
+        paths.append(p)
+    arrays = [frames8[order[b0: b0 + 2]] for b0 in range(0, len(order), 2)]
+    ref = np.concatenate(list(engine.run_stream(iter(arrays), graph=True, image_index0=5)))
+    for depth in (0, 2):
+        with FrameIngest(3) as ing:
+            got = np.concatenate(list(engine.run_stream(ing.batches(paths, 2, depth=depth), graph=True, image_index0=5)))
+        assert len(got) == len(ref) == 19
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], ref[f]), (depth, f)
+
+
 def test_engine_batch64_permutation_invariance(yolo_stream, kpd_sd, kp_model):
     """BASELINE.json configs[2] size (batch 64).  Frames are processed independently, and every output element of the
     convolutions accumulates in a fixed order whatever tile it lands in, so permuting the batch must permute the
