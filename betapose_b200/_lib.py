@@ -21,6 +21,7 @@ EXPORTS = (
     "bp_yolo_decode_argmax", "bp_write_results", "bp_crop_resize", "bp_heatmap_decode", "bp_pose_pnp", "bp_pack_records",
     "bp_score_poses", "bp_pose_nms", "bp_ingest_create", "bp_ingest_destroy", "bp_ingest_num_threads", "bp_png_info",
     "bp_png_decode", "bp_ingest_submit", "bp_ingest_wait", "bp_zlib_inflate",
+    "bp_write_results_nms",
 )
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO = -1, -2, -3, -4
 ORDER_RGB, ORDER_BGR = 0, 1  # frame ingest channel orders
@@ -103,6 +104,7 @@ def lib() -> C.CDLL:
     L.bp_crop_resize.argtypes = [vp, vp, i, i, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp]
     L.bp_heatmap_decode.argtypes = [vp, vp, C.c_long, C.c_long, C.c_long, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.bp_write_results.argtypes = [vp, vp, i, i, i, f, vp, vp, vp, vp]
+    L.bp_write_results_nms.argtypes = [vp, vp, i, i, i, f, f, i, vp, vp, vp, vp, vp]
     L.bp_pose_pnp.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, i, i, i, f, i, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bp_pack_records.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bp_pose_nms.argtypes = [vp, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -88,10 +88,29 @@ class Darknet:
     forward = __call__
 
 
-def dynamic_write_results(prediction, confidence, num_classes, nms=True, nms_conf=0.4):
+def dynamic_write_results(prediction, confidence, num_classes, nms=True, nms_conf=0.4, box_nms: bool = False):
     """yolo/util.py:104-223: one row (img_idx, x1, y1, x2, y2, obj, cls_conf, cls_idx) per image that has a candidate
-    (NMS is hard-coded off there: arg-max objectness), or the int 0 when no image has one."""
+    (NMS is hard-coded off there, whatever `nms` says: arg-max objectness), or the int 0 when no image has one.
+
+    box_nms=True (not a reference argument) switches the reference's shipped-but-disabled IoU-NMS branch on, for scenes
+    with several instances: every surviving box per image, image-major, best first, with dynamic_write_results' own
+    retry -- more than 100 detections in the batch => once more with nms_conf - 0.05 (util.py:111-113)."""
     dev = _dev()
+    if box_nms:
+        pred = prediction.to(dev, dtype=torch.float32)
+
+        def run(thr):
+            r = stages.write_results_nms(pred, float(confidence), float(thr), max_det=int(pred.shape[1]))
+            cnt = r["count"].cpu()
+            keep = torch.arange(r["det"].shape[1])[None, :] < cnt[:, None]
+            return r["det"][keep.to(dev)], int(cnt.sum())
+
+        dets, n = run(nms_conf)
+        if n == 0:
+            return 0
+        if n > 100:
+            dets, n = run(nms_conf - 0.05)
+        return dets.to(prediction.device)
     res = stages.write_results(prediction.to(dev, dtype=torch.float32), float(confidence))
     valid = res["valid"].bool()
     if not bool(valid.any()):

@@ -89,6 +89,23 @@ def write_results(pred: torch.Tensor, conf: float = 0.01):
     return dict(det=det, row=row, valid=valid)
 
 
+def write_results_nms(pred: torch.Tensor, conf: float = 0.01, nms_thr: float = 0.6, max_det: int = 100):
+    """write_results with the IoU-NMS branch on (yolo/util.py:182-196, shipped disabled by `nms = False` at :181).
+    pred fp32 [B,R,n_attr] decoded rows (cuda) -> dict(det [B,max_det,8], row int32 [B,max_det], count int32 [B] =
+    min(kept, max_det), total int32 [B] = kept before the cap), detections best first."""
+    e = _eng(pred)
+    pred = pred.contiguous()
+    B, R, A = pred.shape
+    dev = pred.device
+    det = torch.zeros((B, max_det, 8), dtype=torch.float32, device=dev)
+    row = torch.full((B, max_det), -1, dtype=torch.int32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    total = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().bp_write_results_nms(e.handle, _lib.ptr(pred), B, R, A, float(conf), float(nms_thr), int(max_det), _lib.ptr(det),
+                                               _lib.ptr(row), _lib.ptr(count), _lib.ptr(total), _lib.stream_ptr()), "bp_write_results_nms")
+    return dict(det=det, row=row, count=count, total=total)
+
+
 def crop_resize(frames_u8: torch.Tensor, box: torch.Tensor, img_idx: torch.Tensor, valid: torch.Tensor | None = None,
                 res_h: int = 320, res_w: int = 256, out_net: torch.Tensor | None = None, want_f16: bool = True,
                 want_f32: bool = False):

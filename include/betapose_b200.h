@@ -154,6 +154,15 @@ int bp_yolo_decode_argmax(bp_engine* e, const float* const* heads, const int* gr
 int bp_write_results(bp_engine* e, const float* pred, int B, int R, int n_attr, float conf, float* det, int32_t* row,
                      uint8_t* valid, void* stream);
 
+/* a4 with the IoU-NMS branch the reference ships switched off (yolo/util.py:182-196 behind `nms = False` at :181; bbox_iou,
+ * yolo/bbox.py:51-77) -- SURVEY 8(f) item 3, scenes with several instances.  pred[B,R,n_attr] decoded rows as above
+ * (R <= 16384).  Per image: candidates (objectness > conf, class arg-max 0) sorted by objectness, descending (ties: lower
+ * row first); keep the best remaining box, drop every later one whose IoU with it ("+1 pixel" convention, fp32) is not
+ * < nms_thr; repeat.  out_det[B,max_det,8] rows as bp_write_results, best first; out_row[B,max_det]; out_count[B] =
+ * min(kept, max_det); out_total[B] = kept before the cap (what dynamic_write_results' "> 100 detections" retry reads). */
+int bp_write_results_nms(bp_engine* e, const float* pred, int B, int R, int n_attr, float conf, float nms_thr, int max_det,
+                         float* out_det, int32_t* out_row, int32_t* out_count, int32_t* out_total, void* stream);
+
 /* a6: im_to_torch + crop_from_dets + cropBox (KPD/src/utils/img.py:13-18,242-262; dataloader.py:794-835).
  * frames uint8 [F,H,W,3] RGB; box[n,4]; img_idx[n] (frame of each box); valid[n] (may be NULL).
  * Outputs: out_net = a BP_IN_F16 network input buffer (fp16 [n,rh,rw+BP_IN_PAD_COLS,8]) and/or out_f32_chw fp32

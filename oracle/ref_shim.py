@@ -168,6 +168,22 @@ def load_reference() -> types.SimpleNamespace:
     return ns
 
 
+def load_box_nms():
+    """`write_results` of yolo/util.py with its shipped IoU-NMS branch switched back on: the two statements that disable
+    it (`nms = False`, :181) and that afterwards keep only the arg-max row (:210-211) are neutralised IN MEMORY; every other
+    line, `bbox_iou` included, runs as written.  Used only to pin oracle/restate.py:write_results_nms."""
+    load_reference()
+    root = ref_root()
+    src = open(os.path.join(root, _E, "yolo/util.py")).read().replace(".cuda()", "")
+    a = "            nms = False\n"
+    b = "            best_idx = np.argmax(out[:,5])\n            out = out[best_idx].view(1,-1)\n"
+    assert src.count(a) == 1 and src.count(b) == 1, "reference yolo/util.py changed"
+    src = src.replace(a, "").replace(b, "")
+    mod = types.ModuleType("yolo.util_box_nms")
+    exec(compile(src, "yolo/util.py<box-nms on>", "exec"), mod.__dict__)
+    return mod.write_results
+
+
 def load_metrics() -> types.ModuleType:
     """The reference's scoring functions (3_6Dpose_estimator/utils/metrics.py) unmodified; pyquaternion (only used by
     rot_error, which the evaluate loop never calls) is stubbed."""

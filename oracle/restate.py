@@ -173,6 +173,49 @@ def write_results(pred: np.ndarray, confidence: float = 0.01):
     return np.array(out, F32), np.array(rows, np.int64)
 
 
+def bbox_iou_plus1(box: np.ndarray, others: np.ndarray) -> np.ndarray:
+    """yolo/bbox.py:51-77 `bbox_iou`: corner boxes, the "+1 pixel" convention, fp32, one rounding per operation."""
+    ix1 = np.maximum(box[0], others[:, 0])
+    iy1 = np.maximum(box[1], others[:, 1])
+    ix2 = np.minimum(box[2], others[:, 2])
+    iy2 = np.minimum(box[3], others[:, 3])
+    one, zero = F32(1), F32(0)
+    inter = np.maximum(ix2 - ix1 + one, zero) * np.maximum(iy2 - iy1 + one, zero)
+    a1 = (box[2] - box[0] + one) * (box[3] - box[1] + one)
+    a2 = (others[:, 2] - others[:, 0] + one) * (others[:, 3] - others[:, 1] + one)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (inter / (a1 + a2 - inter)).astype(F32)
+
+
+def write_results_nms(pred: np.ndarray, confidence: float = 0.01, nms_conf: float = 0.6):
+    """The IoU-NMS branch the reference ships switched off (yolo/util.py:182-196, `nms = False` at :181), restated for
+    multi-instance scenes.  pred [B,R,6] -> (dets [D,8] fp32, rows int64 [D], counts int64 [B]):
+    per image the candidates (obj > confidence) sorted by objectness, descending, then greedily: keep the first, drop
+    every later box whose IoU with it is not < nms_conf, repeat.  Detections are image-major, best first.
+    Tie-break of the sort: lower flat row first (torch.sort is unstable there; parity inputs are tie-free)."""
+    out, rows, counts = [], [], []
+    half = F32(2)
+    for b in range(pred.shape[0]):
+        p = pred[b].astype(F32)
+        cand = np.flatnonzero(p[:, 4] > F32(confidence))
+        order = cand[np.argsort(-p[cand, 4].astype(np.float64), kind="stable")]
+        q = p[order]
+        boxes = np.stack([q[:, 0] - q[:, 2] / half, q[:, 1] - q[:, 3] / half, q[:, 0] + q[:, 2] / half, q[:, 1] + q[:, 3] / half], 1).astype(F32)
+        alive = np.ones(len(order), bool)
+        n = 0
+        for i in range(len(order)):
+            if not alive[i]:
+                continue
+            out.append([F32(b), *boxes[i], q[i, 4], q[i, 5], F32(0)])
+            rows.append(int(order[i]))
+            n += 1
+            if i + 1 < len(order):
+                iou = bbox_iou_plus1(boxes[i], boxes[i + 1:])
+                alive[i + 1:] &= iou < F32(nms_conf)  # NaN compares false: dropped, as `image_pred_class[1:][ious < nms_conf]`
+        counts.append(n)
+    return np.array(out, F32).reshape(-1, 8), np.array(rows, np.int64), np.array(counts, np.int64)
+
+
 def rescale_boxes(dets: np.ndarray, im_w: int, im_h: int, reso: int = 416):
     """-> boxes [D,4] fp32 in frame pixels, scores [D,1]."""
     wr = F32(im_w) / F32(reso)

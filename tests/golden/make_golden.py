@@ -345,6 +345,47 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def box_nms_cases():
+    """Decoded prediction tensors [B,R,6] with clusters of overlapping boxes around a few objects + low-score clutter."""
+    rng = np.random.default_rng(21)
+    cases = []
+    for B, Rn, n_obj, conf, thr in ((3, 300, 3, 0.01, 0.6), (2, 1200, 6, 0.3, 0.4), (1, 10647, 9, 0.01, 0.6), (2, 64, 0, 0.5, 0.6)):
+        pred = np.zeros((B, Rn, 6), np.float32)
+        for b in range(B):
+            pred[b, :, 0] = rng.uniform(0, 416, Rn)
+            pred[b, :, 1] = rng.uniform(0, 416, Rn)
+            pred[b, :, 2] = rng.uniform(4, 120, Rn)
+            pred[b, :, 3] = rng.uniform(4, 120, Rn)
+            pred[b, :, 4] = rng.uniform(0, 0.35, Rn) ** 2          # clutter: mostly below the confidence cut
+            pred[b, :, 5] = rng.uniform(0.5, 1.0, Rn)
+            for o in range(n_obj):
+                c = rng.uniform(60, 356, 2)
+                wh = rng.uniform(40, 140, 2)
+                idx = rng.choice(Rn, size=min(Rn // 8, 24), replace=False)
+                pred[b, idx, 0:2] = c + rng.normal(0, 5, (len(idx), 2))
+                pred[b, idx, 2:4] = wh * rng.uniform(0.85, 1.15, (len(idx), 2))
+                pred[b, idx, 4] = rng.uniform(0.4, 0.999, len(idx))
+        if B == 2 and Rn == 64:
+            pred[1, :, 4] = 0.2   # an image without any candidate between images with some
+            pred[0, :5, 4] = [0.9, 0.8, 0.7, 0.6, 0.55]
+        cases.append((pred, conf, thr))
+    return cases
+
+
+def make_box_nms_golden():
+    """write_results of the reference with its disabled IoU-NMS branch re-enabled (ref_shim.load_box_nms) on box_nms_cases()."""
+    import torch
+
+    wr = ref_shim.load_box_nms()
+    out = {}
+    for i, (pred, conf, thr) in enumerate(box_nms_cases()):
+        dets = wr(torch.from_numpy(pred.copy()), conf, 80, True, thr)
+        dets = np.zeros((0, 8), np.float32) if isinstance(dets, int) else dets.numpy().astype(np.float32)
+        out[f"pred{i}"], out[f"conf{i}"], out[f"thr{i}"], out[f"dets{i}"] = pred, np.float32(conf), np.float32(thr), dets
+        print("box-nms case", i, pred.shape, "->", dets.shape, np.bincount(dets[:, 0].astype(int), minlength=pred.shape[0]))
+    np.savez_compressed(os.path.join(HERE, "box_nms_golden.npz"), n_cases=len(box_nms_cases()), versions=np.array(f"torch {torch.__version__}"), **out)
+
+
 def make_metrics_golden():
     """utils/metrics.py add_err / projection_error_2d / iou of the UNMODIFIED reference on seeded poses."""
     import cv2
@@ -381,5 +422,8 @@ def make_metrics_golden():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         make_metrics_golden()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "box_nms":
+        make_box_nms_golden()
         sys.exit(0)
     main()

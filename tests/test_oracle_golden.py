@@ -197,3 +197,17 @@ def test_scoring_matches_reference_metrics():
         assert abs(R.add_err(g["gt"][i], g["est"][i], g["model"]) - g["add"][i]) <= 1e-15 + 1e-13 * g["add"][i]
         assert abs(R.projection_error_2d(g["gt"][i], g["est"][i], g["model"], g["cam"]) - g["proj"][i]) <= 1e-12 + 1e-12 * g["proj"][i]
         assert R.box_iou(g["box_gt"][i], g["box_est"][i]) == g["iou"][i]
+
+
+def test_box_nms_oracle_matches_reference_branch():
+    """oracle/restate.py:write_results_nms against the reference's own (shipped but disabled) IoU-NMS branch, re-enabled by
+    the generator (tests/golden/make_golden.py box_nms).  Bit-exact: same detections, same order, same fp32 values."""
+    g = np.load(os.path.join(G, "box_nms_golden.npz"))
+    for i in range(int(g["n_cases"])):
+        pred, want = g[f"pred{i}"], g[f"dets{i}"]
+        dets, rows, counts = R.write_results_nms(pred, float(g[f"conf{i}"]), float(g[f"thr{i}"]))
+        assert dets.shape == want.shape, i
+        assert np.array_equal(dets, want), i
+        assert counts.sum() == len(want) and np.array_equal(np.bincount(want[:, 0].astype(int), minlength=len(pred)), counts)
+        for d, r in zip(dets, rows):  # rows index the prediction tensor
+            assert pred[int(d[0]), r, 4] == d[5]

@@ -103,6 +103,63 @@ def test_yolo_decode_no_candidate_and_ties():
     assert rr.tolist() == rows[1:]
 
 
+# ------------------------------------------------------------------------------------------------ a4 with box NMS (8f-3)
+def _flat_nms(res):
+    det, row, cnt = res["det"].cpu().numpy(), res["row"].cpu().numpy(), res["count"].cpu().numpy()
+    return (np.concatenate([det[b, : cnt[b]] for b in range(len(cnt))]).reshape(-1, 8),
+            np.concatenate([row[b, : cnt[b]] for b in range(len(cnt))]), cnt)
+
+
+def test_box_nms_bit_exact_against_reference_branch_goldens():
+    """bp_write_results_nms against what the reference's own (shipped, disabled) IoU-NMS branch produces
+    (tests/golden/box_nms_golden.npz), including the full 10647-row case (16384-key shared-memory sort, 1024 threads)."""
+    import os
+
+    from betapose_b200 import stages
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "box_nms_golden.npz"))
+    for i in range(int(g["n_cases"])):
+        pred, want = g[f"pred{i}"], g[f"dets{i}"]
+        res = stages.write_results_nms(_cuda(pred), float(g[f"conf{i}"]), float(g[f"thr{i}"]), max_det=pred.shape[1])
+        d, r, cnt = _flat_nms(res)
+        assert np.array_equal(d, want), i
+        assert np.array_equal(res["total"].cpu().numpy(), cnt)
+        _, rows, counts = R.write_results_nms(pred, float(g[f"conf{i}"]), float(g[f"thr{i}"]))
+        assert np.array_equal(r, rows) and np.array_equal(cnt, counts)
+
+
+def test_box_nms_on_decoded_heads_cap_and_seam():
+    """decode (bp_yolo_decode_argmax, decoded tensor) -> bp_write_results_nms on real head shapes; max_det caps the
+    output but not the count; the dynamic_write_results seam with its > 100 detections retry."""
+    from betapose_b200 import compat, stages
+
+    rng = np.random.default_rng(11)
+    B = 3
+    heads = _rand_heads(rng, B, obj_shift=-4.0)
+    out = _run_decode(heads, B, want_decoded=True)
+    pred_dev = out["decoded"]
+    pred = pred_dev.cpu().numpy()
+    res = stages.write_results_nms(pred_dev, 0.05, 0.45, max_det=4096)
+    d, r, cnt = _flat_nms(res)
+    d2, r2, c2 = R.write_results_nms(pred, 0.05, 0.45)
+    assert cnt.min() > 20
+    assert np.array_equal(cnt, c2) and np.array_equal(r, r2) and np.array_equal(d, d2)
+    capped = stages.write_results_nms(pred_dev, 0.05, 0.45, max_det=7)
+    assert np.array_equal(capped["count"].cpu().numpy(), np.minimum(c2, 7)) and np.array_equal(capped["total"].cpu().numpy(), c2)
+    assert np.array_equal(capped["det"].cpu().numpy()[1, :7], res["det"].cpu().numpy()[1, :7])
+    # seam: more than 100 detections in the batch -> one retry with nms_conf - 0.05 (yolo/util.py:111-113)
+    dets = compat.dynamic_write_results(pred_dev, 0.05, 80, True, 0.45, box_nms=True)
+    want = d2 if len(d2) <= 100 else R.write_results_nms(pred, 0.05, 0.45 - 0.05)[0]  # the retry subtracts in double, as the reference does
+    assert len(d2) > 100 and np.array_equal(dets.cpu().numpy(), want)
+    few = compat.dynamic_write_results(pred_dev, 0.9999, 80, True, 0.45, box_nms=True)
+    w2 = R.write_results_nms(pred, 0.9999, 0.45)[0]
+    assert (isinstance(few, int) and few == 0 and len(w2) == 0) or np.array_equal(few.cpu().numpy(), w2)
+    assert compat.dynamic_write_results(pred_dev, 2.0, 80, True, 0.45, box_nms=True) == 0
+    # default behaviour of the seam is untouched: one arg-max row per image
+    one = compat.dynamic_write_results(pred_dev, 0.05, 80, True, 0.45)
+    assert one.shape == (B, 8)
+
+
 # ------------------------------------------------------------------------------------------------ a6
 BOXES = np.array([
     [200.3, 120.7, 330.9, 300.2],    # ordinary, w > 100
