@@ -21,7 +21,7 @@ EXPORTS = (
     "bp_yolo_decode_argmax", "bp_write_results", "bp_crop_resize", "bp_heatmap_decode", "bp_pose_pnp", "bp_pack_records",
     "bp_score_poses", "bp_pose_nms", "bp_ingest_create", "bp_ingest_destroy", "bp_ingest_num_threads", "bp_png_info",
     "bp_png_decode", "bp_ingest_submit", "bp_ingest_wait", "bp_zlib_inflate",
-    "bp_write_results_nms",
+    "bp_write_results_nms", "bp_pack_conv_weights",
 )
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO = -1, -2, -3, -4
 ORDER_RGB, ORDER_BGR = 0, 1  # frame ingest channel orders
@@ -40,6 +40,7 @@ class ConvSpec(C.Structure):
         ("store_mode", C.c_int), ("out_f32", C.c_int),
         ("weight", C.c_void_p), ("bias", C.c_void_p), ("bn_gamma", C.c_void_p), ("bn_beta", C.c_void_p),
         ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p), ("bn_eps", C.c_float),
+        ("packed_w", C.c_void_p), ("packed_b", C.c_void_p), ("packed_w_elems", C.c_size_t), ("packed_b_elems", C.c_size_t),
     ]
 
 
@@ -81,6 +82,7 @@ def lib() -> C.CDLL:
     L.bp_net_input_ptr.argtypes = [vp]
     L.bp_net_input_ptr.restype = vp
     L.bp_net_conv.argtypes = [vp, C.POINTER(ConvSpec)]
+    L.bp_pack_conv_weights.argtypes = [C.POINTER(ConvSpec), i, i, vp, vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.bp_net_alloc_tensor.argtypes = [vp, i, i, i]
     L.bp_net_view.argtypes = [vp, i, i, i]
     L.bp_net_maxpool3x3s2.argtypes = [vp, i]

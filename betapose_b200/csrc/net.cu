@@ -149,8 +149,71 @@ int bp_net_view(bp_net* n, int tensor, int coff, int c) {
   return (int)n->tensors.size() - 1;
 }
 
+// Fold BN (fp64) into the weights and pack them for the implicit-GEMM kernel: [Cout_pad][K] fp16 rows + fp32 bias.
+// Host code (no CUDA call): shared by bp_net_conv and bp_pack_conv_weights (the packed-weight cache).
+//   ordinary conv: K = k*k*Cin ordered (r, q, ci) -- NHWC im2col order;
+//   stem (3-channel network input, stored [N, H, W + 8, 8] fp16 with zero pad columns): one filter ROW of k pixels x 8
+//   channels is contiguous in memory, so the convolution is run as a k x 1 convolution over "virtual pixels" of
+//   Cv = 32 (k <= 4) or 64 (k <= 8) channels = 4 or 8 neighbouring real pixels, whose pixel stride (16 B) is smaller than
+//   their extent (overlapping TMA im2col map).  K = k * Cv, ordered (row, pixel-in-row, 8 channels); entries beyond the
+//   k real pixels / 3 real channels are zero weights.  For RAW255 inputs ToTensor's 1/255 (dataloader.py:94-99) is
+//   folded into the weights, so the 0..255 pixel values are exact in fp16.
+struct PackedDims {
+  int Cv, K, wpitch, Cout_pad;
+};
+static PackedDims packed_dims(int Cin, int k, int Cout, bool stem) {
+  PackedDims d;
+  d.Cv = stem ? (k * 8 <= 32 ? 32 : 64) : 0;
+  d.K = stem ? k * d.Cv : k * k * Cin;
+  d.wpitch = (d.K + 7) / 8 * 8;
+  d.Cout_pad = (Cout + 255) / 256 * 256;
+  return d;
+}
+static void pack_conv_weights(const bp_conv_spec* s, int Cin, int in_kind /* -1: not a stem */, __half* hw, float* hb) {
+  const bool stem = in_kind >= 0;
+  const int k = s->ksize, Cout = s->cout;
+  const PackedDims pd = packed_dims(Cin, k, Cout, stem);
+  for (size_t i = 0; i < (size_t)pd.Cout_pad * pd.wpitch; ++i) hw[i] = __float2half(0.f);
+  for (int i = 0; i < pd.Cout_pad; ++i) hb[i] = 0.f;
+  const int c4 = Cout / 4;
+  const double in_scale = (stem && in_kind == BP_IN_RAW255) ? 1.0 / 255.0 : 1.0;
+  for (int o = 0; o < Cout; ++o) {
+    double scale = 1.0, shift = s->bias ? (double)s->bias[o] : 0.0;
+    if (s->bn_gamma) {
+      const double inv = (double)s->bn_gamma[o] / std::sqrt((double)s->bn_var[o] + (double)s->bn_eps);
+      scale = inv;
+      shift = (double)s->bn_beta[o] - (double)s->bn_mean[o] * inv + shift * inv;
+    }
+    // PixelShuffle(2) fused store: kernel row o' = sub*(Cout/4) + c holds PyTorch channel o = 4c + sub
+    const int row = s->store_mode == BP_STORE_PIXSHUF2 ? (o % 4) * c4 + o / 4 : o;
+    hb[row] = (float)shift;
+    const float* wsrc = s->weight + (size_t)o * Cin * k * k;
+    __half* wdst = hw + (size_t)row * pd.wpitch;
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int r = 0; r < k; ++r)
+        for (int q = 0; q < k; ++q) {
+          const size_t kidx = stem ? (size_t)r * pd.Cv + q * 8 + ci : (size_t)(r * k + q) * Cin + ci;
+          wdst[kidx] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale * in_scale));
+        }
+  }
+}
+
+int bp_pack_conv_weights(const bp_conv_spec* s, int cin, int in_kind, void* w_out, float* b_out, size_t* w_elems, size_t* b_elems) {
+  if (!s || cin <= 0 || s->cout <= 0 || s->ksize <= 0 || in_kind > BP_IN_F16) return bp_fail(BP_ERR_INVALID, "bp_pack_conv_weights: bad arguments");
+  const bool stem = in_kind >= 0;
+  if (stem && (s->ksize > 8 || cin > 8)) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pack_conv_weights: stem convolution geometry (k <= 8, cin <= 8)");
+  if (!stem && cin % 32 != 0) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pack_conv_weights: Cin must be a multiple of 32");
+  const PackedDims pd = packed_dims(cin, s->ksize, s->cout, stem);
+  if (w_elems) *w_elems = (size_t)pd.Cout_pad * pd.wpitch;
+  if (b_elems) *b_elems = (size_t)pd.Cout_pad;
+  if (!w_out && !b_out) return BP_OK;  // size query
+  if (!w_out || !b_out || !s->weight) return bp_fail(BP_ERR_INVALID, "bp_pack_conv_weights: null buffer");
+  pack_conv_weights(s, cin, in_kind, reinterpret_cast<__half*>(w_out), b_out);
+  return BP_OK;
+}
+
 int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
-  if (!n || !s || !s->weight) return bp_fail(BP_ERR_INVALID, "bp_net_conv: null argument");
+  if (!n || !s || (!s->weight && !s->packed_w)) return bp_fail(BP_ERR_INVALID, "bp_net_conv: null argument");
   if (s->src < 0 || s->src >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_conv: src id");
   cudaSetDevice(n->eng->device);
   const Tensor src = n->tensors[s->src];
@@ -163,47 +226,31 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (s->store_mode != BP_STORE_PLAIN && s->out_f32) return bp_fail(BP_ERR_UNSUPPORTED, "fp32 output supports plain stores only");
   if (s->store_mode != BP_STORE_PLAIN && Cout % 8) return bp_fail(BP_ERR_UNSUPPORTED, "fused stores need Cout % 8 == 0");
 
-  // ---- fold BN (fp64) and pack weights [Cout_pad][R][S][Cin] fp16
-  // Stem (3-channel network input, stored [N, H, W + 8, 8] fp16 with zero pad columns): one filter ROW of k pixels x 8
-  // channels is contiguous in memory, so the convolution is run as a k x 1 convolution over "virtual pixels" of
-  // Cv = 32 (k <= 4) or 64 (k <= 8) channels = 4 or 8 neighbouring real pixels, whose pixel stride (16 B) is smaller than
-  // their extent (overlapping TMA im2col map).  K = k * Cv, ordered (row, pixel-in-row, 8 channels); entries beyond the
-  // k real pixels / 3 real channels are zero weights.  For RAW255 inputs ToTensor's 1/255 (dataloader.py:94-99) is
-  // folded into the weights, so the 0..255 pixel values are exact in fp16.
-  const int Cv = stem ? (k * 8 <= 32 ? 32 : 64) : 0;
+  // ---- packed weights: folded + packed here (pack_conv_weights above), or taken as they are from a packed-weight cache
+  const PackedDims pd = packed_dims(Cin, k, Cout, stem);
+  const int Cv = pd.Cv, K = pd.K, wpitch = pd.wpitch, Cout_pad = pd.Cout_pad;
   if (stem && (k > 8 || s->pad > BP_IN_PAD_LEFT || (Q - 1) * s->stride + Cv / 8 > src.row_px - (BP_IN_PAD_LEFT - s->pad)))
     return bp_fail(BP_ERR_UNSUPPORTED, "bp_net_conv: stem convolution geometry (k <= 8, pad <= 3)");
-  const int K = stem ? k * Cv : k * k * Cin;
-  const int wpitch = (K + 7) / 8 * 8;
-  const int Cout_pad = (Cout + 255) / 256 * 256;
-  std::vector<__half> hw((size_t)Cout_pad * wpitch, __float2half(0.f));
-  std::vector<float> hb(Cout_pad, 0.f);
-  const int c4 = Cout / 4;
-  const double in_scale = (stem && src.in_kind == BP_IN_RAW255) ? 1.0 / 255.0 : 1.0;
-  for (int o = 0; o < Cout; ++o) {
-    double scale = 1.0, shift = s->bias ? (double)s->bias[o] : 0.0;
-    if (s->bn_gamma) {
-      const double inv = (double)s->bn_gamma[o] / std::sqrt((double)s->bn_var[o] + (double)s->bn_eps);
-      scale = inv;
-      shift = (double)s->bn_beta[o] - (double)s->bn_mean[o] * inv + shift * inv;
-    }
-    // PixelShuffle(2) fused store: kernel row o' = sub*(Cout/4) + c holds PyTorch channel o = 4c + sub
-    const int row = s->store_mode == BP_STORE_PIXSHUF2 ? (o % 4) * c4 + o / 4 : o;
-    hb[row] = (float)shift;
-    const float* wsrc = s->weight + (size_t)o * Cin * k * k;
-    __half* wdst = hw.data() + (size_t)row * wpitch;
-    for (int ci = 0; ci < Cin; ++ci)
-      for (int r = 0; r < k; ++r)
-        for (int q = 0; q < k; ++q) {
-          const size_t kidx = stem ? (size_t)r * Cv + q * 8 + ci : (size_t)(r * k + q) * Cin + ci;
-          wdst[kidx] = __float2half_rn((float)((double)wsrc[(ci * k + r) * k + q] * scale * in_scale));
-        }
+  const size_t n_w = (size_t)Cout_pad * wpitch, n_b = (size_t)Cout_pad;
+  std::vector<__half> hw;
+  std::vector<float> hb;
+  const void* w_host = s->packed_w;
+  const float* b_host = s->packed_b;
+  if (s->packed_w) {
+    if (!s->packed_b || s->packed_w_elems != n_w || s->packed_b_elems != n_b)
+      return bp_fail(BP_ERR_INVALID, "bp_net_conv: packed weights do not have this convolution's packed size (stale cache?)");
+  } else {
+    hw.resize(n_w);
+    hb.resize(n_b);
+    pack_conv_weights(s, Cin, stem ? src.in_kind : -1, hw.data(), hb.data());
+    w_host = hw.data();
+    b_host = hb.data();
   }
-  __half* dw = (__half*)net_alloc_weights(n, hw.size() * 2);
-  float* db = (float*)net_alloc_weights(n, hb.size() * 4);
+  __half* dw = (__half*)net_alloc_weights(n, n_w * 2);
+  float* db = (float*)net_alloc_weights(n, n_b * 4);
   if (!dw || !db) return bp_fail(BP_ERR_CUDA, "bp_net_conv: cudaMalloc (weights) failed");
-  if (cudaMemcpy(dw, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(db, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+  if (cudaMemcpy(dw, w_host, n_w * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(db, b_host, n_b * 4, cudaMemcpyHostToDevice) != cudaSuccess)
     return bp_fail(BP_ERR_CUDA, "bp_net_conv: weight upload failed");
 
   // ---- destination tensor

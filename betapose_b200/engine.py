@@ -22,7 +22,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, net as _net, stages, yolo_cfg
+from . import _lib, net as _net, stages, weights as _weights, yolo_cfg
 
 
 class BetaposeEngine:
@@ -31,7 +31,8 @@ class BetaposeEngine:
                  left_number: int = 50, conf: float = 0.01, pnp_mode: int = stages.MODE_RANSAC, reproj_thr: float = 12.0,
                  n_hyp: int = 64, seed: int = 0, cam_K=stages.CAM_K, device=None, concurrent_slots: bool | None = None):
         """yolo_streams: fp32 darknet weight stream (or list, one per object slot); kpd_state_dicts: FastPose
-        state_dict (or list); kp3d: float64 [K,3] (or [n_slots,K,3]) key-point model in metres."""
+        state_dict (or list); either may be a weights.PackedWeights (packed-weight cache) instead; kp3d: float64 [K,3]
+        (or [n_slots,K,3]) key-point model in metres."""
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.B = int(max_batch)
@@ -61,12 +62,24 @@ class BetaposeEngine:
             for s in range(self.n_slots):
                 shared = None if self.concurrent_slots else (self.yolo[0] if s else None)
                 y = _net.Net(self.B, reso, reso, _lib.IN_RAW255, share=shared, device=self.device.index)
-                params, used = _net.split_darknet_stream(blocks, np.asarray(yolo_streams[s], np.float32))
+                if isinstance(yolo_streams[s], _weights.PackedWeights):  # packed-weight cache: shapes from the cfg, data as packed
+                    assert yolo_streams[s].kind == "darknet" and yolo_streams[s].meta.get("reso") == reso
+                    params, y.packed = _weights.darknet_placeholder_params(blocks), iter(yolo_streams[s])
+                else:
+                    params, used = _net.split_darknet_stream(blocks, np.asarray(yolo_streams[s], np.float32))
                 self.heads.append(_net.build_darknet(y, blocks, params))
+                if getattr(y, "packed", None) is not None:
+                    _net.packed_exhausted(y.packed)
                 self.yolo.append(y)
                 k = _net.Net(self.B, inp_h, inp_w, _lib.IN_F16, share=None if self.concurrent_slots else (self.kpd[0] if s else None),
                              device=self.device.index)
-                self.hm_id.append(_net.build_fastpose(k, kpd_state_dicts[s], self.K))
+                sd = kpd_state_dicts[s]
+                if isinstance(sd, _weights.PackedWeights):
+                    assert sd.kind == "fastpose" and sd.meta.get("n_maps") == self.K
+                    sd, k.packed = _weights.fastpose_placeholder_state_dict(self.K), iter(sd)
+                self.hm_id.append(_net.build_fastpose(k, sd, self.K))
+                if getattr(k, "packed", None) is not None:
+                    _net.packed_exhausted(k.packed)
                 self.kpd.append(k)
             kp3d = np.asarray(kp3d, np.float64)
             if kp3d.ndim == 2:

@@ -34,7 +34,7 @@ def main(argv=None):
 
     occlusion = o.mode == "occlusion"
     left = o.left_keypoints if occlusion else o.nClasses  # DataWriter(cam_K, 50, ...) vs (cam_K, args.left_keypoints, ...)
-    bench_info = model_vertices = kp_sixd = None
+    bench_info = model_vertices = kp_sixd = blocks = None
     if o.sixd_base:
         # the reference's evaluation set-up (betapose_evaluate.py:86-98, 203-206): models, key-point model and ground truth
         # of sequence --obj_id from the benchmark tree; --indir defaults to the sequence's rgb/ folder
@@ -60,11 +60,28 @@ def main(argv=None):
         else:
             from . import weights
 
-            _, yolo_stream = weights.read_darknet_weights(o.yolo_weights)
-            weights.check_darknet_stream(yolo_cfg.parse_cfg_text(open(o.yolo_cfg).read() if o.yolo_cfg else yolo_cfg.default_cfg_text()),
-                                         yolo_stream)
-            kpd_sd = torch.load(o.kpd_weights, map_location="cpu")
-            weights.check_fastpose_state_dict(kpd_sd, o.nClasses)
+            blocks = yolo_cfg.parse_cfg_text(open(o.yolo_cfg).read() if o.yolo_cfg else yolo_cfg.default_cfg_text())
+
+            def pack_yolo():
+                _, st = weights.read_darknet_weights(o.yolo_weights)
+                return weights.pack_darknet(blocks, st, int(o.inp_dim))  # validates the stream against the cfg
+
+            def pack_kpd():
+                return weights.pack_fastpose(torch.load(o.kpd_weights, map_location="cpu"), o.nClasses, o.inputResH, o.inputResW)
+
+            if o.packed_cache:  # folded + packed weights, memory-mapped; re-packed when the source changes
+                tag = f"{int(o.inp_dim)}_{o.nClasses}"
+                yolo_stream, hit_y = weights.load_or_pack(os.path.join(o.packed_cache, os.path.basename(o.yolo_weights) + f".{tag}.bppw"),
+                                                          o.yolo_weights, pack_yolo)
+                kpd_sd, hit_k = weights.load_or_pack(os.path.join(o.packed_cache, os.path.basename(o.kpd_weights) + f".{tag}.bppw"),
+                                                     o.kpd_weights, pack_kpd)
+                if rank == 0 and o.profile:
+                    print(f"packed-weight cache: detector {'hit' if hit_y else 'packed'}, key-point net {'hit' if hit_k else 'packed'}")
+            else:
+                _, yolo_stream = weights.read_darknet_weights(o.yolo_weights)
+                weights.check_darknet_stream(blocks, yolo_stream)
+                kpd_sd = torch.load(o.kpd_weights, map_location="cpu")
+                weights.check_fastpose_state_dict(kpd_sd, o.nClasses)
         if o.kp_model:
             kp3d = model3d.load_kp_model(o.kp_model, o.nClasses)
         elif kp_sixd is not None:
@@ -79,7 +96,7 @@ def main(argv=None):
     B = min(o.batch, max(1, hi - lo))
     mode = stages.MODE_RANSAC if o.pnp_mode == "ransac" else stages.MODE_ALLPTS
     eng = BetaposeEngine(B, yolo_stream, kpd_sd, kp3d, reso=int(o.inp_dim), inp_h=o.inputResH, inp_w=o.inputResW, n_kp=o.nClasses,
-                         left_number=left, conf=o.confidence, pnp_mode=mode)
+                         left_number=left, conf=o.confidence, pnp_mode=mode, cfg_blocks=blocks)
     recs = []
     t0 = time.time()
 

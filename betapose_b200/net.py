@@ -25,6 +25,55 @@ def _f32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _shape4(weight):
+    sh = tuple(weight.shape)
+    return sh + (1, 1) if len(sh) == 2 else sh
+
+
+def conv_spec(src, weight, bias, bn, stride, pad, act, res, res_mode, dst, dst_coff, store, out_f32, shapes_only=False):
+    """-> (ConvSpec, arrays to keep alive while it is used).  shapes_only: do not touch parameter data (placeholders)."""
+    sh = _shape4(weight)
+    s = _lib.ConvSpec()
+    s.src, s.cout, s.ksize, s.stride, s.pad = int(src), int(sh[0]), int(sh[2]), int(stride), int(pad)
+    s.act, s.res, s.res_mode, s.dst, s.dst_coff = int(act), int(res), int(res_mode), int(dst), int(dst_coff)
+    s.store_mode, s.out_f32 = int(store), int(bool(out_f32))
+    keep = []
+    if shapes_only:
+        return s, keep
+    w = _f32(weight).reshape(sh)
+    keep.append(w)
+    s.weight = w.ctypes.data_as(C.c_void_p)
+    if bias is not None:
+        b = _f32(bias)
+        keep.append(b)
+        s.bias = b.ctypes.data_as(C.c_void_p)
+    if bn is not None:
+        g, be, m, v = (_f32(x) for x in bn[:4])
+        keep += [g, be, m, v]
+        s.bn_gamma, s.bn_beta = g.ctypes.data_as(C.c_void_p), be.ctypes.data_as(C.c_void_p)
+        s.bn_mean, s.bn_var = m.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)
+        s.bn_eps = float(bn[4]) if len(bn) > 4 else 1e-5
+    return s, keep
+
+
+def take_packed(packed, weight, store, in_kind):
+    """next entry of a PackedWeights iterator, checked against what the builder is about to emit"""
+    ent = next(packed, None)
+    want = tuple(int(v) for v in _shape4(weight))
+    if ent is None:
+        raise _lib.BetaposeError(f"packed weights end before the network does (next conv: {want})")
+    if tuple(ent["shape"]) != want or ent["store"] != int(store) or ent["in_kind"] != int(in_kind):
+        raise _lib.BetaposeError(f"packed weights do not match the network: conv {ent['index']} was packed for {tuple(ent['shape'])} "
+                                 f"(store {ent['store']}, input kind {ent['in_kind']}), the builder asks for {want} "
+                                 f"(store {int(store)}, input kind {int(in_kind)})")
+    return ent["w"], ent["b"]
+
+
+def packed_exhausted(packed) -> None:
+    if next(packed, None) is not None:
+        raise _lib.BetaposeError("packed weights hold more convolutions than the network (wrong cfg / n_maps?)")
+
+
 class _DevArray:
     """Minimal __cuda_array_interface__ carrier so torch can alias engine-owned device memory without a copy."""
 
@@ -55,25 +104,16 @@ class Net:
     # ---- builders -------------------------------------------------------------------------------------
     def conv(self, src, weight, bias=None, bn=None, stride=1, pad=0, act=ACT_NONE, res=-1, res_mode=RES_NONE, dst=-1,
              dst_coff=0, store=STORE_PLAIN, out_f32=False) -> int:
-        w = _f32(weight)
-        if w.ndim == 2:
-            w = w[:, :, None, None]
-        keep = [w]
-        s = _lib.ConvSpec()
-        s.src, s.cout, s.ksize, s.stride, s.pad = int(src), int(w.shape[0]), int(w.shape[2]), int(stride), int(pad)
-        s.act, s.res, s.res_mode, s.dst, s.dst_coff = int(act), int(res), int(res_mode), int(dst), int(dst_coff)
-        s.store_mode, s.out_f32 = int(store), int(bool(out_f32))
-        s.weight = w.ctypes.data_as(C.c_void_p)
-        if bias is not None:
-            b = _f32(bias)
-            keep.append(b)
-            s.bias = b.ctypes.data_as(C.c_void_p)
-        if bn is not None:
-            g, be, m, v = (_f32(x) for x in bn[:4])
-            keep += [g, be, m, v]
-            s.bn_gamma, s.bn_beta = g.ctypes.data_as(C.c_void_p), be.ctypes.data_as(C.c_void_p)
-            s.bn_mean, s.bn_var = m.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p)
-            s.bn_eps = float(bn[4]) if len(bn) > 4 else 1e-5
+        """`self.packed` (an iterator over a weights.PackedWeights' entries, set by the caller before building) makes
+        every conv take its folded + packed weights from there; `weight` / `bias` / `bn` then only provide shapes."""
+        packed = getattr(self, "packed", None)
+        s, keep = conv_spec(src, weight, bias, bn, stride, pad, act, res, res_mode, dst, dst_coff, store, out_f32,
+                            shapes_only=packed is not None)
+        if packed is not None:
+            w, b = take_packed(packed, weight, store, self.in_kind if int(src) == 0 else -1)
+            keep += [w, b]
+            s.packed_w, s.packed_b = w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)
+            s.packed_w_elems, s.packed_b_elems = w.size, b.size
         return _lib.check(_lib.lib().bp_net_conv(self.handle, C.byref(s)), "bp_net_conv")
 
     def alloc_tensor(self, h, w, c) -> int:

@@ -92,11 +92,24 @@ typedef struct bp_conv_spec {
   const float* bn_mean;
   const float* bn_var;
   float bn_eps;
+  /* optional: this convolution's weights already folded and packed (bp_pack_conv_weights, e.g. read from a packed-weight
+   * cache).  When packed_w != NULL it is uploaded as it is and weight / bias / bn_* are ignored (may be NULL). */
+  const void* packed_w;  /* fp16 [packed_w_elems] */
+  const float* packed_b; /* fp32 [packed_b_elems] */
+  size_t packed_w_elems;
+  size_t packed_b_elems;
 } bp_conv_spec;
 
 /* conv (+folded BN) + bias + activation (+ residual) (+ fused upsample / pixel-shuffle store). Returns the
  * output tensor id (>= 0) or a negative error. */
 int bp_net_conv(bp_net* n, const bp_conv_spec* spec);
+/* SURVEY 8(f) item 4 -- the packed form bp_net_conv uploads, computed on the HOST (no CUDA call, no bp_net): BN folded in
+ * fp64, fp16 rows [cout_pad][K] in the kernel's K order (NHWC im2col; for a stem the "virtual pixel" row order), fp32 bias
+ * [cout_pad], PixelShuffle row permutation applied.  cin = input channels; in_kind = BP_IN_RAW255 / BP_IN_F16 when the
+ * convolution reads the network input (stem), -1 otherwise.  Only cout, ksize, store_mode and the parameter pointers of
+ * `spec` are read.  *w_elems / *b_elems receive the sizes; with w_out == b_out == NULL the call is a size query. */
+int bp_pack_conv_weights(const bp_conv_spec* spec, int cin, int in_kind, void* w_out, float* b_out, size_t* w_elems,
+                         size_t* b_elems);
 /* pre-allocate a tensor several producers write into (darknet [route] with two layers = channel concat) */
 int bp_net_alloc_tensor(bp_net* n, int h, int w, int c);
 /* channel window [coff, coff+c) of an existing tensor as a tensor of its own (no copy) */

@@ -199,6 +199,24 @@ def test_run_stream_from_png_files_through_the_native_ingest(engine, frames8, tm
             assert np.array_equal(got[f], ref[f]), (depth, f)
 
 
+def test_engine_from_packed_weight_cache_is_bit_identical(engine, yolo_stream, kpd_sd, kp_model, frames8, tmp_path):
+    """both networks packed on the host, saved, memory-mapped back and uploaded as they are
+    (bp_conv_spec.packed_w) -- the engine built that way returns the records of the engine built from fp32 weights."""
+    from betapose_b200 import weights, yolo_cfg
+    from betapose_b200.engine import BetaposeEngine
+
+    blocks = yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+    weights.pack_darknet(blocks, yolo_stream).save(str(tmp_path / "y.bppw"))
+    weights.pack_fastpose(kpd_sd, 50).save(str(tmp_path / "k.bppw"))
+    py, pk = weights.PackedWeights.load(str(tmp_path / "y.bppw")), weights.PackedWeights.load(str(tmp_path / "k.bppw"))
+    e2 = BetaposeEngine(8, py, pk, kp_model, seed=5)
+    ref = engine.run(frames8).copy()
+    got = e2.run(frames8)
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], ref[f]), f
+    assert (ref["status"] == 1).any()
+
+
 def test_engine_batch64_permutation_invariance(yolo_stream, kpd_sd, kp_model):
     """BASELINE.json configs[2] size (batch 64).  Frames are processed independently, and every output element of the
     convolutions accumulates in a fixed order whatever tile it lands in, so permuting the batch must permute the

@@ -24,7 +24,7 @@ def test_library_exports_every_header_symbol():
     assert L.bp_version() == 100
     # struct layouts shared across the boundary
     assert C.sizeof(_lib.Record) == 4 + 4 + 16 + 4 + 4 + 600 + 72 + 24
-    assert C.sizeof(_lib.ConvSpec) == 12 * 4 + 6 * 8 + 8
+    assert C.sizeof(_lib.ConvSpec) == 12 * 4 + 6 * 8 + 8 + 4 * 8  # ... bn_eps (+pad), packed_w, packed_b, packed_w_elems, packed_b_elems
 
 
 def test_engine_create_fails_loudly_without_gpu():
@@ -222,3 +222,147 @@ def test_weight_format_tooling(tmp_path):
     bad["module.extra"] = torch.zeros(1)
     with pytest.raises(ValueError, match="unexpected key"):
         weights.check_fastpose_state_dict(bad)
+
+
+# ---------------------------------------------------------------------------------------------- packed-weight cache (8f-4)
+def _fold_reference(w, bias, bn, in_scale=1.0):
+    """independent numpy statement of what csrc/net.cu:pack_conv_weights computes, before the re-ordering"""
+    cout = w.shape[0]
+    scale, shift = np.ones(cout), (np.zeros(cout) if bias is None else bias.astype(np.float64))
+    if bn is not None:
+        g, be, m, v, eps = bn
+        inv = g.astype(np.float64) / np.sqrt(v.astype(np.float64) + np.float64(np.float32(eps)))
+        scale, shift = inv, be.astype(np.float64) - m.astype(np.float64) * inv + shift * inv
+    wf = (w.astype(np.float64) * scale[:, None, None, None] * in_scale).astype(np.float32).astype(np.float16)
+    return wf, shift.astype(np.float32)
+
+
+def test_pack_conv_weights_layouts_bit_exact():
+    """bp_pack_conv_weights (host entry point; the same function bp_net_conv packs with) against a numpy statement of the
+    layout: ordinary conv (NHWC im2col K order), pixel-shuffle row permutation, both stem kinds, zero padding."""
+    from betapose_b200 import _lib, weights
+
+    rng = np.random.default_rng(0)
+
+    def bn_of(c):
+        return (rng.uniform(0.5, 1.5, c).astype(np.float32), rng.normal(0, 0.2, c).astype(np.float32),
+                rng.normal(0, 0.2, c).astype(np.float32), rng.uniform(0.5, 1.5, c).astype(np.float32), 1e-5)
+
+    cases = [dict(cout=48, cin=32, k=3, store=_lib.STORE_PLAIN, bn=True, bias=False, in_kind=-1),
+             dict(cout=18, cin=64, k=1, store=_lib.STORE_PLAIN, bn=False, bias=True, in_kind=-1),
+             dict(cout=64, cin=32, k=3, store=_lib.STORE_PIXSHUF2, bn=True, bias=False, in_kind=-1),
+             dict(cout=32, cin=3, k=3, store=_lib.STORE_PLAIN, bn=True, bias=False, in_kind=_lib.IN_RAW255),
+             dict(cout=64, cin=3, k=7, store=_lib.STORE_PLAIN, bn=True, bias=False, in_kind=_lib.IN_F16)]
+    for c in cases:
+        w = rng.normal(0, 0.1, (c["cout"], c["cin"], c["k"], c["k"])).astype(np.float32)
+        bias = rng.normal(0, 0.5, c["cout"]).astype(np.float32) if c["bias"] else None
+        bn = bn_of(c["cout"]) if c["bn"] else None
+        rec = weights.PackRecorder(64, 64, c["in_kind"] if c["in_kind"] >= 0 else _lib.IN_F16)
+        src = 0 if c["in_kind"] >= 0 else 5
+        rec.conv(src, w, bias=bias, bn=bn, store=c["store"])
+        e = rec.entries[0]
+        stem = c["in_kind"] >= 0
+        wf, shift = _fold_reference(w, bias, bn, 1.0 / 255.0 if c["in_kind"] == _lib.IN_RAW255 else 1.0)
+        cout, cin, k = c["cout"], c["cin"], c["k"]
+        cv = (32 if k * 8 <= 32 else 64) if stem else 0
+        K = k * cv if stem else k * k * cin
+        wpitch, cout_pad = (K + 7) // 8 * 8, (cout + 255) // 256 * 256
+        want_w = np.zeros((cout_pad, wpitch), np.float16)
+        want_b = np.zeros(cout_pad, np.float32)
+        rows = np.arange(cout) if c["store"] != _lib.STORE_PIXSHUF2 else (np.arange(cout) % 4) * (cout // 4) + np.arange(cout) // 4
+        if stem:
+            blk = np.zeros((cout, k, cv // 8, 8), np.float16)
+            blk[:, :, :k, :cin] = wf.transpose(0, 2, 3, 1)
+            want_w[rows, :K] = blk.reshape(cout, K)
+        else:
+            want_w[rows, :K] = wf.transpose(0, 2, 3, 1).reshape(cout, K)
+        want_b[rows] = shift
+        assert e["w"].size == want_w.size and e["b"].size == cout_pad
+        assert np.array_equal(e["w"].view(np.uint16), want_w.reshape(-1).view(np.uint16)), c
+        assert np.array_equal(e["b"], want_b), c
+        # and back: the folded fp32 tensors (fp16-rounded), PyTorch layout
+        uw, ub = weights.unpack_conv(e)
+        scale_back = 255.0 if c["in_kind"] == _lib.IN_RAW255 else 1.0
+        assert np.array_equal(uw, wf.astype(np.float32) * np.float32(scale_back)) and np.array_equal(ub, shift)
+    # geometry the kernels do not support is refused here too
+    with pytest.raises(_lib.BetaposeError):
+        weights.PackRecorder(64, 64, _lib.IN_F16).conv(3, np.zeros((8, 20, 1, 1), np.float32))
+
+
+def test_packed_weights_file_roundtrip_and_replay(tmp_path):
+    """pack a small darknet + a FastPose-shaped state_dict through the real builders, save / mmap-load, and replay: the
+    builders driven by shape-only placeholders consume exactly the packed entries, in order; mismatches are named."""
+    from betapose_b200 import _lib, net as bnet, weights, yolo_cfg
+
+    blocks = yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+    rng = np.random.default_rng(1)
+    stream = rng.normal(0, 0.05, weights.darknet_stream_size(blocks)).astype(np.float32)
+    # BN variances must be positive (the per-block arrays are views into the stream)
+    params, _ = bnet.split_darknet_stream(blocks, stream)
+    for p in params:
+        if p and "bn_var" in p:
+            p["bn_var"][:] = np.abs(p["bn_var"]) + 0.5
+    pw = weights.pack_darknet(blocks, stream, 416, meta=dict(note="test"))
+    assert pw.kind == "darknet" and len(pw) == 75 and pw.meta["reso"] == 416 and pw.entries[0]["in_kind"] == _lib.IN_RAW255
+    assert all(e["in_kind"] == -1 for e in pw.entries[1:])
+    path = str(tmp_path / "yolo.bppw")
+    pw.save(path)
+    back = weights.PackedWeights.load(path)
+    assert back.kind == "darknet" and back.meta["note"] == "test" and len(back) == 75
+    for a, b in zip(pw, back):
+        assert a["shape"] == b["shape"] and a["store"] == b["store"] and a["in_kind"] == b["in_kind"]
+        assert np.array_equal(a["w"].view(np.uint16), np.asarray(b["w"]).view(np.uint16)) and np.array_equal(a["b"], b["b"])
+        assert b["w"].ctypes.data % 64 == 0 and b["b"].ctypes.data % 64 == 0
+
+    class Replay(weights.PackRecorder):  # what Net.conv does with `packed`, without CUDA behind it
+        def __init__(self, packed, *a):
+            super().__init__(*a)
+            self.packed, self.taken = iter(packed), 0
+
+        def conv(self, src, weight, bias=None, bn=None, stride=1, pad=0, act=0, res=-1, res_mode=0, dst=-1, dst_coff=0, store=0,
+                 out_f32=False):
+            bnet.conv_spec(src, weight, bias, bn, stride, pad, act, res, res_mode, dst, dst_coff, store, out_f32, shapes_only=True)
+            bnet.take_packed(self.packed, weight, store, self.in_kind if int(src) == 0 else -1)
+            self.taken += 1
+            return self._new()
+
+    r = Replay(back, 416, 416, _lib.IN_RAW255)
+    bnet.build_darknet(r, blocks, weights.darknet_placeholder_params(blocks))
+    bnet.packed_exhausted(r.packed)
+    assert r.taken == 75
+    # a cache packed for another network is refused with the conv named
+    other = [b.copy() for b in blocks]
+    other[2] = dict(other[2], filters="48")
+    with pytest.raises(_lib.BetaposeError, match="do not match the network"):
+        bnet.build_darknet(Replay(back, 416, 416, _lib.IN_RAW255), other, weights.darknet_placeholder_params(other))
+    with pytest.raises(_lib.BetaposeError, match="end before"):
+        bnet.build_darknet(Replay(back.entries[:10], 416, 416, _lib.IN_RAW255), blocks, weights.darknet_placeholder_params(blocks))
+    # FastPose: 115 convolutions (SE Linear layers run as 1x1 convs), head sliced to n_maps
+    sd = {k: (np.abs(rng.normal(0, 0.05, sh)) + 0.3).astype(np.float32) for k, sh in weights.fastpose_expected_shapes(60).items()}
+    pk = weights.pack_fastpose(sd, 50)
+    assert len(pk) == 115 and pk.entries[0]["in_kind"] == _lib.IN_F16 and pk.entries[-1]["shape"] == (50, 128, 3, 3)
+    assert sum(e["store"] == _lib.STORE_PIXSHUF2 for e in pk) == 2
+    r = Replay(pk, 320, 256, _lib.IN_F16)
+    bnet.build_fastpose(r, weights.fastpose_placeholder_state_dict(50), 50)
+    bnet.packed_exhausted(r.packed)
+    # load_or_pack: second call hits the cache; touching the source invalidates it
+    src = str(tmp_path / "a.weights")
+    weights.write_darknet_weights(src, stream)
+    calls = []
+
+    def pack():
+        calls.append(1)
+        return weights.pack_darknet(blocks, weights.read_darknet_weights(src)[1])
+
+    c = str(tmp_path / "cache" / "a.bppw")
+    p1, hit1 = weights.load_or_pack(c, src, pack)
+    p2, hit2 = weights.load_or_pack(c, src, pack)
+    assert (hit1, hit2, len(calls)) == (False, True, 1)
+    assert all(np.array_equal(a["w"].view(np.uint16), np.asarray(b["w"]).view(np.uint16)) for a, b in zip(p1, p2))
+    import os
+    os.utime(src, ns=(1, 1))
+    _, hit3 = weights.load_or_pack(c, src, pack)
+    assert not hit3 and len(calls) == 2
+    open(str(tmp_path / "junk.bppw"), "wb").write(b"not a cache")
+    with pytest.raises(ValueError):
+        weights.PackedWeights.load(str(tmp_path / "junk.bppw"))
