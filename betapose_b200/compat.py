@@ -213,6 +213,9 @@ def pnp(points_3D, points_2D, cameraMatrix, mode: int = stages.MODE_RANSAC):
     """utils/utils.py:17-41 -> (R [3,3] f64, t [3,1] f64).  mode RANSAC mirrors the cv2.solvePnPRansac(12 px) variant,
     MODE_ALLPTS the active cv2.solvePnP call where that converges."""
     assert points_3D.shape[0] == points_2D.shape[0], "points 3D and points 2D must have same number of vertices"
+    dist = getattr(pnp, "distCoeffs", None)  # optional function attribute of the reference's pnp (utils.py:18-21); default zeros
+    if dist is not None and np.any(np.asarray(dist, np.float64) != 0):
+        raise _lib.BetaposeError("pnp: non-zero lens distortion (pnp.distCoeffs) is not supported by the PnP kernel; undistort the points first")
     dev = _dev()
     K = int(points_3D.shape[0])
     p2 = torch.as_tensor(np.ascontiguousarray(np.asarray(points_2D, np.float32)[:, :2])).to(dev).reshape(1, K, 2)

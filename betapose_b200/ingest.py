@@ -37,7 +37,11 @@ class FrameIngest:
             _lib.lib().bp_ingest_destroy(self.handle)
             self.handle = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def __enter__(self):
         return self

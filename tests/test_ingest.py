@@ -325,3 +325,16 @@ def test_inflate_rejects_bad_streams_without_touching_memory_outside_its_buffers
             want = None
         assert (rc == 0 and got == want) if (want is not None and len(want) <= 4096) else rc == _lib.ERR_INVALID
     assert agree == 3000
+
+
+def test_paeth_and_average_rows_on_noise(ing):
+    """The branch-free pixel-wise Paeth / Average paths (3- and 4-byte pixels) on incompressible data, where every tie and
+    sign case of the predictor occurs; first row (no row above) and every later row."""
+    rng = np.random.default_rng(9)
+    for ctype, ch in ((2, 3), (6, 4)):
+        rows = rng.integers(0, 256, (H, W * ch), dtype=np.uint8)
+        rows[5] = rows[4]          # predictor ties: a == b == c along a repeated row
+        rows[7, :] = 0
+        for filters in ([4], [3], [4, 3]):
+            png = write_png(rows, ctype, 8, filters)
+            assert np.array_equal(ing.decode_bytes(png), rows.reshape(H, W, ch)[:, :, :3])
