@@ -21,7 +21,7 @@ EXPORTS = (
     "bp_yolo_decode_argmax", "bp_write_results", "bp_crop_resize", "bp_heatmap_decode", "bp_pose_pnp", "bp_pack_records",
     "bp_score_poses", "bp_pose_nms", "bp_ingest_create", "bp_ingest_destroy", "bp_ingest_num_threads", "bp_png_info",
     "bp_png_decode", "bp_ingest_submit", "bp_ingest_wait", "bp_zlib_inflate",
-    "bp_write_results_nms", "bp_pack_conv_weights",
+    "bp_write_results_nms", "bp_pack_conv_weights", "bp_frame_decode",
 )
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO = -1, -2, -3, -4
 ORDER_RGB, ORDER_BGR = 0, 1  # frame ingest channel orders
@@ -117,6 +117,7 @@ def lib() -> C.CDLL:
     L.bp_ingest_num_threads.argtypes = [vp]
     L.bp_png_info.argtypes = [vp, C.c_size_t, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.bp_png_decode.argtypes = [vp, C.c_size_t, i, i, i, vp, C.c_size_t]
+    L.bp_frame_decode.argtypes = [vp, C.c_size_t, i, i, i, vp, C.c_size_t]
     L.bp_ingest_submit.argtypes = [vp, C.POINTER(C.c_char_p), i, i, i, i, vp, C.c_size_t, vp]
     L.bp_ingest_submit.restype = C.c_int64
     L.bp_ingest_wait.argtypes = [vp, C.c_int64]

@@ -1,4 +1,4 @@
-// Frame ingest: PNG files -> uint8 [n, H, W, 3] frames in caller memory (normally the pinned
+// Frame ingest: PNG (or pre-decoded PPM / PGM / .npy) files -> uint8 [n, H, W, 3] frames in caller memory (normally the pinned
 // host buffers BetaposeEngine.run_stream uploads from), decoded by a pool of host threads while the GPU works on the
 // previous batch.  Stands in for cv2.imread / PIL.Image.open in ImageLoader.getitem_yolo (dataloader.py:150-179) and
 // prep_image (yolo/preprocess.py:34-46), which decode every frame twice on one Python thread.
@@ -341,6 +341,110 @@ int decode_png(const uint8_t* png, size_t len, int H, int W, int order, uint8_t*
   return BP_OK;
 }
 
+// ---- containers without entropy coding: a decoded-once copy of a sequence that the pool can deliver at memory speed.
+// Binary PPM / PGM ("P6" / "P5", maxval 255) and NumPy .npy files holding uint8 [H, W, 3] (C order).
+inline void copy_rgb_rows(const uint8_t* src, int H, int W, int channels, int bgr, uint8_t* out, size_t row_pitch) {
+  for (int y = 0; y < H; ++y) {
+    const uint8_t* s = src + size_t(y) * W * channels;
+    uint8_t* d = out + size_t(y) * row_pitch;
+    if (channels == 3 && !bgr) {
+      memcpy(d, s, size_t(W) * 3);
+    } else if (channels == 3) {
+      for (int x = 0; x < W; ++x) {
+        d[3 * x] = s[3 * x + 2];
+        d[3 * x + 1] = s[3 * x + 1];
+        d[3 * x + 2] = s[3 * x];
+      }
+    } else {
+      for (int x = 0; x < W; ++x) d[3 * x] = d[3 * x + 1] = d[3 * x + 2] = s[x];
+    }
+  }
+}
+
+int decode_pnm(const uint8_t* p, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch, std::string* err) {
+  const int channels = p[1] == '6' ? 3 : 1;
+  size_t pos = 2;
+  long vals[3];
+  for (int k = 0; k < 3; ++k) {  // width, height, maxval: decimal numbers separated by white space, '#' starts a comment
+    for (;;) {
+      while (pos < len && (p[pos] == ' ' || p[pos] == '\t' || p[pos] == '\n' || p[pos] == '\r')) ++pos;
+      if (pos < len && p[pos] == '#') {
+        while (pos < len && p[pos] != '\n') ++pos;
+        continue;
+      }
+      break;
+    }
+    if (pos >= len || p[pos] < '0' || p[pos] > '9') {
+      *err = "PNM: bad header";
+      return BP_ERR_INVALID;
+    }
+    long v = 0;
+    while (pos < len && p[pos] >= '0' && p[pos] <= '9' && v < (1L << 24)) v = v * 10 + (p[pos++] - '0');
+    vals[k] = v;
+  }
+  if (pos >= len || !(p[pos] == ' ' || p[pos] == '\t' || p[pos] == '\n' || p[pos] == '\r')) {
+    *err = "PNM: bad header";
+    return BP_ERR_INVALID;
+  }
+  ++pos;  // exactly one white-space byte before the samples
+  if (vals[2] != 255) {
+    *err = "PNM: only maxval 255 is read by the native ingest";
+    return BP_ERR_UNSUPPORTED;
+  }
+  if (vals[0] != W || vals[1] != H) {
+    *err = "PNM: frame is " + std::to_string(vals[0]) + "x" + std::to_string(vals[1]) + ", expected " + std::to_string(W) + "x" + std::to_string(H);
+    return BP_ERR_INVALID;
+  }
+  if (len - pos < size_t(H) * W * channels) {
+    *err = "PNM: sample data ends early (truncated file?)";
+    return BP_ERR_INVALID;
+  }
+  copy_rgb_rows(p + pos, H, W, channels, order == BP_ORDER_BGR, out, row_pitch);
+  return BP_OK;
+}
+
+int decode_npy(const uint8_t* p, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch, std::string* err) {
+  if (len < 12) {
+    *err = "NPY: truncated header";
+    return BP_ERR_INVALID;
+  }
+  const int major = p[6];
+  const size_t hlen = major == 1 ? size_t(p[8] | (p[9] << 8)) : size_t(p[8]) | (size_t(p[9]) << 8) | (size_t(p[10]) << 16) | (size_t(p[11]) << 24);
+  const size_t hoff = major == 1 ? 10 : 12;
+  if (major < 1 || major > 3 || hoff + hlen > len) {
+    *err = "NPY: bad header";
+    return BP_ERR_INVALID;
+  }
+  const std::string head(reinterpret_cast<const char*>(p + hoff), hlen);
+  const std::string shape3 = "(" + std::to_string(H) + ", " + std::to_string(W) + ", 3)";
+  const std::string shape1 = "(" + std::to_string(H) + ", " + std::to_string(W) + ")";
+  const bool u1 = head.find("'|u1'") != std::string::npos || head.find("'<u1'") != std::string::npos || head.find("'u1'") != std::string::npos;
+  const bool c_order = head.find("'fortran_order': False") != std::string::npos;
+  const bool rgb = head.find("'shape': " + shape3) != std::string::npos, grey = head.find("'shape': " + shape1) != std::string::npos;
+  if (!u1 || !c_order) {
+    *err = "NPY: only C-ordered uint8 arrays are read by the native ingest";
+    return BP_ERR_UNSUPPORTED;
+  }
+  if (!rgb && !grey) {
+    *err = "NPY: array shape is not " + shape3 + " or " + shape1;
+    return BP_ERR_INVALID;
+  }
+  const int channels = rgb ? 3 : 1;
+  if (len - (hoff + hlen) < size_t(H) * W * channels) {
+    *err = "NPY: array data ends early (truncated file?)";
+    return BP_ERR_INVALID;
+  }
+  copy_rgb_rows(p + hoff + hlen, H, W, channels, order == BP_ORDER_BGR, out, row_pitch);
+  return BP_OK;
+}
+
+// PNG, binary PPM / PGM or .npy, told apart by their magic bytes; anything else is BP_ERR_UNSUPPORTED
+int decode_frame(const uint8_t* p, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch, Scratch* sc, std::string* err) {
+  if (len >= 3 && p[0] == 'P' && (p[1] == '6' || p[1] == '5')) return decode_pnm(p, len, H, W, order, out, row_pitch, err);
+  if (len >= 6 && memcmp(p, "\x93NUMPY", 6) == 0) return decode_npy(p, len, H, W, order, out, row_pitch, err);
+  return decode_png(p, len, H, W, order, out, row_pitch, sc, err);
+}
+
 int read_file(const char* path, std::vector<uint8_t>* buf, std::string* err) {
   const int fd = open(path, O_RDONLY | O_CLOEXEC);
   if (fd < 0) {
@@ -406,7 +510,7 @@ struct bp_ingest {
       }
       std::string err;
       int rc = read_file(j.path.c_str(), &sc.file, &err);
-      if (rc == BP_OK) rc = decode_png(sc.file.data(), sc.file.size(), j.H, j.W, j.order, j.out, size_t(j.W) * 3, &sc, &err);
+      if (rc == BP_OK) rc = decode_frame(sc.file.data(), sc.file.size(), j.H, j.W, j.order, j.out, size_t(j.W) * 3, &sc, &err);
       if (j.status) *j.status = rc;
       {
         std::lock_guard<std::mutex> lk(mu);
@@ -442,6 +546,16 @@ int bp_png_decode(const uint8_t* png, size_t len, int H, int W, int order, uint8
   static thread_local Scratch sc;
   std::string err;
   const int rc = decode_png(png, len, H, W, order, out, row_pitch ? row_pitch : size_t(W) * 3, &sc, &err);
+  return rc == BP_OK ? BP_OK : bp_fail(rc, err.c_str());
+}
+
+int bp_frame_decode(const uint8_t* data, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch) {
+  if (!data || !out || H <= 0 || W <= 0 || (order != BP_ORDER_RGB && order != BP_ORDER_BGR))
+    return bp_fail(BP_ERR_INVALID, "bp_frame_decode: bad arguments");
+  if (row_pitch && row_pitch < size_t(W) * 3) return bp_fail(BP_ERR_INVALID, "bp_frame_decode: row pitch smaller than a row");
+  static thread_local Scratch sc;
+  std::string err;
+  const int rc = decode_frame(data, len, H, W, order, out, row_pitch ? row_pitch : size_t(W) * 3, &sc, &err);
   return rc == BP_OK ? BP_OK : bp_fail(rc, err.c_str());
 }
 

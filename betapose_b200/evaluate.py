@@ -51,7 +51,7 @@ def main(argv=None):
         if o.inputlist:
             names = [ln.strip() for ln in open(o.inputlist) if ln.strip()]
         else:
-            names = sorted(f for f in os.listdir(o.inputpath) if f.lower().endswith((".png", ".jpg", ".jpeg")))
+            names = sorted(f for f in os.listdir(o.inputpath) if f.lower().endswith((".png", ".jpg", ".jpeg", ".ppm", ".pgm", ".npy")))
         names = [os.path.join(o.inputpath, n) for n in names]
         if not names:
             raise SystemExit("no frames found")

@@ -62,8 +62,8 @@ class FrameIngest:
             out = np.empty((self.H, self.W, 3), np.uint8)
         assert out.dtype == np.uint8 and out.shape == (self.H, self.W, 3) and out.strides[1:] == (3, 1)
         buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
-        _lib.check(_lib.lib().bp_png_decode(buf, len(data), self.H, self.W, self.order, C.c_void_p(out.ctypes.data), out.strides[0]),
-                   "bp_png_decode")
+        _lib.check(_lib.lib().bp_frame_decode(buf, len(data), self.H, self.W, self.order, C.c_void_p(out.ctypes.data), out.strides[0]),
+                   "bp_frame_decode")
         return out
 
     # ------------------------------------------------------------------ files, through the pool
@@ -105,7 +105,13 @@ class FrameIngest:
     def _decode_with_pillow(self, path, dst):
         from PIL import Image
 
-        im = np.asarray(Image.open(path).convert("RGB"))
+        if str(path).lower().endswith(".npy"):
+            im = np.load(path)
+            if im.dtype != np.uint8:
+                raise _lib.BetaposeError(f"{path}: frames must be uint8, got {im.dtype}")
+            im = np.ascontiguousarray(im if im.ndim == 3 else np.repeat(im[..., None], 3, -1))
+        else:
+            im = np.asarray(Image.open(path).convert("RGB"))
         if im.shape != (self.H, self.W, 3):
             raise _lib.BetaposeError(f"{path}: expected a {self.W}x{self.H} frame, got {im.shape[1]}x{im.shape[0]}")
         if self.order == _lib.ORDER_BGR:
@@ -141,3 +147,30 @@ class FrameIngest:
             if nxt < len(starts):
                 submit(nxt)  # reuses the buffer of batch nxt - (depth + 3) = j - 2: the caller is done with it (see above)
             yield fr
+
+
+def convert_sequence(paths, out_dir: str, fmt: str = "ppm", frame_h: int = 480, frame_w: int = 640, n_threads: int = 0, chunk: int = 64):
+    """Decode a sequence once and write it as binary PPM (or .npy) frames, which the pool then delivers at memory speed
+    (no entropy decoding): the way to keep a B200 fed from disk when the host has fewer than ~20 cores per GPU.
+    Returns the new paths, same order."""
+    import os
+
+    assert fmt in ("ppm", "npy")
+    os.makedirs(out_dir, exist_ok=True)
+    paths, out_paths = list(paths), []
+    head = f"P6\n{frame_w} {frame_h}\n255\n".encode()
+    with FrameIngest(n_threads, frame_h, frame_w) as ing:
+        buf = np.empty((chunk, frame_h, frame_w, 3), np.uint8)
+        for c0 in range(0, len(paths), chunk):
+            part = paths[c0: c0 + chunk]
+            frames = ing.decode_files(part, buf)
+            for p, fr in zip(part, frames):
+                q = os.path.join(out_dir, os.path.splitext(os.path.basename(p))[0] + "." + fmt)
+                if fmt == "ppm":
+                    with open(q, "wb") as f:
+                        f.write(head)
+                        f.write(fr.tobytes())
+                else:
+                    np.save(q, fr)
+                out_paths.append(q)
+    return out_paths

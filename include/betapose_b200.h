@@ -253,7 +253,8 @@ int bp_score_poses(bp_engine* e, int n, const double* R_est, const double* t_est
  * bp_engine): a pool of threads decodes PNG files straight into caller memory, normally the pinned buffers the engine
  * uploads from, so decoding of batch i+1.. overlaps the GPU work of batch i.  The result is the 8-bit 3-channel image
  * both reference decoders produce: alpha dropped, grey replicated, palette expanded, 16-bit samples reduced to the high
- * byte.  Non-PNG streams and Adam7-interlaced files return BP_ERR_UNSUPPORTED (the caller decodes those elsewhere). */
+ * byte.  Adam7-interlaced PNGs and formats other than PNG / PPM / PGM / .npy return BP_ERR_UNSUPPORTED (the caller decodes
+ * those elsewhere). */
 #define BP_ORDER_RGB 0 /* PIL.Image.open: the detector branch and this engine's frame layout */
 #define BP_ORDER_BGR 1 /* cv2.imread: the reference's orig_img */
 typedef struct bp_ingest bp_ingest;
@@ -266,6 +267,10 @@ int bp_ingest_num_threads(bp_ingest* g);
 int bp_png_info(const uint8_t* png, size_t len, int* H, int* W, int* channels, int* depth);
 /* decode one in-memory PNG on the calling thread into out[H][row_pitch] (row_pitch 0 = 3*W); the file must be HxW */
 int bp_png_decode(const uint8_t* png, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch);
+/* what the pool runs per file, on the calling thread: PNG as above, or a container without entropy coding -- binary
+ * PPM / PGM ("P6" / "P5", maxval 255) or a NumPy .npy file holding C-ordered uint8 [H,W,3] (or [H,W]) -- told apart by
+ * their magic bytes.  A sequence converted once to one of those is delivered at memory speed. */
+int bp_frame_decode(const uint8_t* data, size_t len, int H, int W, int order, uint8_t* out, size_t row_pitch);
 /* the ingest's inflate on its own: one whole zlib stream (RFC 1950) -> out[0..out_cap); *out_len = bytes produced.
  * BP_ERR_INVALID for corrupt / truncated streams and for streams that hold more than out_cap bytes. */
 int bp_zlib_inflate(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len);

@@ -338,3 +338,44 @@ def test_paeth_and_average_rows_on_noise(ing):
         for filters in ([4], [3], [4, 3]):
             png = write_png(rows, ctype, 8, filters)
             assert np.array_equal(ing.decode_bytes(png), rows.reshape(H, W, ch)[:, :, :3])
+
+
+def test_pre_decoded_containers_ppm_pgm_npy(ing, ing_bgr, tmp_path):
+    """Binary PPM / PGM and .npy frames: no entropy coding, delivered by the same pool; convert_sequence writes them."""
+    from betapose_b200.ingest import convert_sequence
+
+    rng = np.random.default_rng(10)
+    im = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    grey = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    ppm = f"P6\n# a comment line\n{W} {H}\n255\n".encode() + im.tobytes()
+    pgm = f"P5 {W}\t{H} 255\n".encode() + grey.tobytes()
+    assert np.array_equal(ing.decode_bytes(ppm), im) and np.array_equal(ing_bgr.decode_bytes(ppm), im[:, :, ::-1])
+    assert np.array_equal(ing.decode_bytes(pgm), np.repeat(grey[..., None], 3, -1))
+    assert np.array_equal(ing.decode_bytes(ppm), np.asarray(Image.open(io.BytesIO(ppm)).convert("RGB")))
+    p_npy, p_npy_g, p_f = str(tmp_path / "a.npy"), str(tmp_path / "g.npy"), str(tmp_path / "f.npy")
+    np.save(p_npy, im)
+    np.save(p_npy_g, grey)
+    np.save(p_f, np.asfortranarray(im))
+    got = ing.decode_files([p_npy, p_npy_g, p_f])      # the Fortran-ordered one goes through the Python fallback
+    assert np.array_equal(got[0], im) and np.array_equal(got[1], np.repeat(grey[..., None], 3, -1)) and np.array_equal(got[2], im)
+    assert np.array_equal(ing_bgr.decode_files([p_npy])[0], im[:, :, ::-1])
+    for bad in (ppm[:-5], f"P6\n{W} {H + 1}\n255\n".encode() + im.tobytes(), b"P6\n64 x\n255\n", f"P6\n{W} {H}\n255".encode()):
+        with pytest.raises(_lib.BetaposeError):
+            ing.decode_bytes(bad)
+    rc = _lib.lib().bp_frame_decode(f"P6\n{W} {H}\n65535\n".encode() + bytes(2 * im.size), 15 + 2 * im.size, H, W, 0,
+                                    np.empty((H, W, 3), np.uint8).ctypes.data, 0)
+    assert rc == _lib.ERR_UNSUPPORTED
+    np.save(str(tmp_path / "u16.npy"), im.astype(np.uint16))
+    with pytest.raises(_lib.BetaposeError, match="uint8"):
+        ing.decode_files([str(tmp_path / "u16.npy")])
+    # convert a PNG sequence once, read it back through the pool
+    pngs = []
+    ims = rng.integers(0, 256, (5, H, W, 3), dtype=np.uint8)
+    for i in range(5):
+        p = str(tmp_path / f"s{i}.png")
+        Image.fromarray(ims[i]).save(p)
+        pngs.append(p)
+    for fmt in ("ppm", "npy"):
+        out = convert_sequence(pngs, str(tmp_path / fmt), fmt=fmt, frame_h=H, frame_w=W, n_threads=2, chunk=2)
+        assert [os.path.basename(q) for q in out] == [f"s{i}.{fmt}" for i in range(5)]
+        assert np.array_equal(ing.decode_files(out), ims)
