@@ -217,6 +217,43 @@ def test_engine_from_packed_weight_cache_is_bit_identical(engine, yolo_stream, k
     assert (ref["status"] == 1).any()
 
 
+def test_multi_instance_path(engine, frames8):
+    """SURVEY 8(f) item 3 end to end (betapose_b200/multi.py): box NMS -> crop per detection -> key-point net -> general
+    pose-NMS -> PnP per pose.  With max_det = 1 it is the reference's behaviour (arg-max detection, identity merge) and must
+    return the poses of BetaposeEngine.run; with more detections every frame yields between 1 and max_det poses."""
+    from betapose_b200.multi import MultiInstance
+
+    n = 4
+    ref = engine.run(frames8[:n]).copy()
+    one = MultiInstance(engine, nms_thr=0.6, max_det=1).run(frames8[:n])
+    assert (ref["status"] == 1).any()
+    for b in range(n):
+        if ref["status"][b] == 0:
+            assert one[b] == []
+            continue
+        assert len(one[b]) == 1
+        p = one[b][0]
+        kp = ref["keypoints"][b].reshape(50, 3)
+        assert p["status"] == ref["status"][b]
+        assert np.array_equal(p["bbox"], ref["box"][b]) and np.array_equal(p["bbox_pick"], ref["box"][b])
+        assert p["det_score"] == ref["det_score"][b]
+        assert np.array_equal(p["keypoints"], kp[:, :2]) and np.array_equal(p["kp_score"][:, 0], kp[:, 2])
+        assert abs(p["proposal_score"] - ref["proposal_score"][b]) < 1e-5
+        if p["status"] == 1:
+            np.testing.assert_allclose(p["cam_R"].reshape(-1), ref["R"][b], atol=1e-9)
+            np.testing.assert_allclose(p["cam_t"].reshape(-1), ref["t"][b], atol=1e-9)
+    many = MultiInstance(engine, nms_thr=0.45, max_det=5).run(frames8[:n])
+    assert sum(len(m) for m in many) >= 1
+    for b in range(n):
+        assert len(many[b]) <= 5
+        for p in many[b]:
+            assert np.isfinite(p["keypoints"]).all() and np.isfinite(p["kp_score"]).all() and p["kp_score"].max() >= 0.3
+            assert np.array_equal(p["bbox"], ref["box"][b])  # pose_nms reports the frame's first (= best) box for every pose
+            if p["status"] == 1:
+                R3 = p["cam_R"]
+                assert np.isfinite(R3).all() and np.allclose(R3 @ R3.T, np.eye(3), atol=1e-6) and abs(np.linalg.det(R3) - 1) < 1e-6
+
+
 def test_engine_batch64_permutation_invariance(yolo_stream, kpd_sd, kp_model):
     """BASELINE.json configs[2] size (batch 64).  Frames are processed independently, and every output element of the
     convolutions accumulates in a fixed order whatever tile it lands in, so permuting the batch must permute the
