@@ -133,20 +133,34 @@ class FrameIngest:
         asks for batch k+2, and has finished with batch k by then."""
         paths = list(paths)
         starts = list(range(0, len(paths), batch))
-        ring = [self._frame_buffer(batch) for _ in range(min(len(starts), depth + 3))]
+        n_buf = min(len(starts), depth + 3)
+        # the pinned ring is kept between calls (pinning ~60 MB buffers costs tens of ms each): one stream at a time
+        if getattr(self, "_streaming", False):
+            raise _lib.BetaposeError("FrameIngest.batches: a previous stream of this FrameIngest is still being consumed")
+        ring = getattr(self, "_ring", [])
+        if len(ring) < n_buf or (ring and ring[0].shape[0] != batch):
+            ring = [self._frame_buffer(batch) for _ in range(n_buf)]
+            self._ring = ring
+        ring = ring[:max(n_buf, 1)]
         tickets = {}
 
         def submit(j):
             tickets[j] = self.submit(paths[starts[j]: starts[j] + batch], ring[j % len(ring)])
 
-        for j in range(min(depth + 1, len(starts))):
-            submit(j)
-        for j in range(len(starts)):
-            fr = self.wait(tickets.pop(j))
-            nxt = j + depth + 1
-            if nxt < len(starts):
-                submit(nxt)  # reuses the buffer of batch nxt - (depth + 3) = j - 2: the caller is done with it (see above)
-            yield fr
+        self._streaming = True
+        try:
+            for j in range(min(depth + 1, len(starts))):
+                submit(j)
+            for j in range(len(starts)):
+                fr = self.wait(tickets.pop(j))
+                nxt = j + depth + 1
+                if nxt < len(starts):
+                    submit(nxt)  # reuses the buffer of batch nxt - (depth + 3) = j - 2: the caller is done with it (see above)
+                yield fr
+        finally:
+            for t in tickets.values():  # abandoned early: let queued decodes finish before their buffers can be reused
+                _lib.lib().bp_ingest_wait(self.handle, t.id)
+            self._streaming = False
 
 
 def convert_sequence(paths, out_dir: str, fmt: str = "ppm", frame_h: int = 480, frame_w: int = 640, n_threads: int = 0, chunk: int = 64):

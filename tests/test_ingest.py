@@ -379,3 +379,26 @@ def test_pre_decoded_containers_ppm_pgm_npy(ing, ing_bgr, tmp_path):
         out = convert_sequence(pngs, str(tmp_path / fmt), fmt=fmt, frame_h=H, frame_w=W, n_threads=2, chunk=2)
         assert [os.path.basename(q) for q in out] == [f"s{i}.{fmt}" for i in range(5)]
         assert np.array_equal(ing.decode_files(out), ims)
+
+
+def test_batches_reuses_its_ring_and_refuses_two_streams_at_once(tmp_path):
+    rng = np.random.default_rng(12)
+    ims = rng.integers(0, 256, (9, H, W, 3), dtype=np.uint8)
+    paths = []
+    for i in range(9):
+        p = str(tmp_path / f"{i}.ppm")
+        open(p, "wb").write(f"P6\n{W} {H}\n255\n".encode() + ims[i].tobytes())
+        paths.append(p)
+    with FrameIngest(2, H, W) as g:
+        a = [fr.numpy().copy() for fr in g.batches(paths, 2, depth=1)]
+        ring = [t.data_ptr() for t in g._ring]
+        b = [fr.numpy().copy() for fr in g.batches(paths[::-1], 2, depth=1)]
+        assert [t.data_ptr() for t in g._ring] == ring          # second stream: same (pinned) buffers
+        assert np.array_equal(np.concatenate(a), ims) and np.array_equal(np.concatenate(b), ims[::-1])
+        it = g.batches(paths, 2, depth=1)
+        next(it)
+        with pytest.raises(_lib.BetaposeError, match="still being consumed"):
+            next(g.batches(paths, 2, depth=1))
+        it.close()                                              # abandoning a stream waits for its queued decodes
+        assert np.array_equal(np.concatenate([fr.numpy().copy() for fr in g.batches(paths, 4, depth=0)]), ims)
+        assert g._ring[0].shape[0] == 4                         # other batch size: new ring
