@@ -96,7 +96,7 @@ def main(argv=None):
     B = min(o.batch, max(1, hi - lo))
     mode = stages.MODE_RANSAC if o.pnp_mode == "ransac" else stages.MODE_ALLPTS
     eng = BetaposeEngine(B, yolo_stream, kpd_sd, kp3d, reso=int(o.inp_dim), inp_h=o.inputResH, inp_w=o.inputResW, n_kp=o.nClasses,
-                         left_number=left, conf=o.confidence, pnp_mode=mode, cfg_blocks=blocks)
+                         left_number=left, conf=o.confidence, pnp_mode=mode, cfg_blocks=blocks, frame_h=o.frame_h, frame_w=o.frame_w)
     recs = []
     t0 = time.time()
 
@@ -104,13 +104,13 @@ def main(argv=None):
     if o.synthetic:
         def batches():  # generation of batch i+1 overlaps the GPU work of batch i (BetaposeEngine.run_stream)
             for b0 in range(lo, hi, B):
-                yield synth.synth_frames(min(hi, b0 + B) - b0, seed=b0)
+                yield synth.synth_frames(min(hi, b0 + B) - b0, seed=b0, h=o.frame_h, w=o.frame_w)
         stream = batches()
     else:
         # the native decoder pool fills pinned batch buffers `ingest_depth` batches ahead of the GPU
         from .ingest import FrameIngest
 
-        ingest = FrameIngest(o.ingest_threads)
+        ingest = FrameIngest(o.ingest_threads, o.frame_h, o.frame_w)
         stream = ingest.batches(names[lo:hi], B, depth=o.ingest_depth)
     for rec in eng.run_stream(stream, graph=True, image_index0=lo):
         recs.append(rec)

@@ -51,6 +51,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--sixd_base", type=str, default="",
                    help="SIXD / LineMod benchmark root (the reference hard-codes it, betapose_evaluate.py:91): when given, "
                         "frames, models and ground truth come from it and the ADD / 2-D / IoU summary is printed")
+    p.add_argument("--frame_h", type=int, default=480, help="frame height (the LineMod sequences are 640x480)")
+    p.add_argument("--frame_w", type=int, default=640)
     p.add_argument("--packed_cache", type=str, default="",
                    help="directory for packed-weight files (BN folded, fp16, kernel order): packed once, memory-mapped afterwards")
     p.add_argument("--ingest_threads", type=int, default=0, help="frame decoder threads (0 = one per hardware thread)")
