@@ -110,3 +110,23 @@ def test_host_iou_is_the_reference_formula(host):
         got = host.bp_box_iou_host(a.ctypes.data, b.ctypes.data)
         want = R.bbox_iou_plus1(a, b[None])[0]
         assert got == want or (np.isnan(got) and np.isnan(want))
+
+
+def test_host_build_random_sweep_against_oracle(host):
+    """Many small random scenes (heavy overlap, coarse coordinates so that IoUs land exactly on the threshold, duplicated
+    objectness values): detections, order and counts equal the oracle's every time."""
+    rng = np.random.default_rng(6)
+    for trial in range(120):
+        Rn = int(rng.integers(1, 90))
+        p = np.zeros((2, Rn, 6), np.float32)
+        p[..., 0:2] = rng.integers(0, 12, (2, Rn, 2)) * 8.0
+        p[..., 2:4] = rng.integers(1, 6, (2, Rn, 2)) * 8.0 - 1.0      # (w+1)(h+1) areas are multiples of 64: exact IoU fractions
+        p[..., 4] = rng.integers(1, 20, (2, Rn)) / 20.0 if trial % 2 else rng.uniform(0, 1, (2, Rn))
+        p[..., 5] = rng.uniform(0, 1, (2, Rn))
+        conf = float(rng.choice([0.0, 0.1, 0.5]))
+        thr = float(rng.choice([0.25, 0.5, 0.6, 1.0 / 3.0]))
+        det, row, cnt, tot = run(host, p, conf, thr, Rn)
+        d2, r2, c2 = R.write_results_nms(p, conf, thr)
+        d, r = flat(det, row, cnt)
+        assert np.array_equal(cnt, c2) and np.array_equal(tot, c2), trial
+        assert np.array_equal(r, r2) and np.array_equal(d, d2), trial
