@@ -40,10 +40,11 @@ def main(argv=None):
         # of sequence --obj_id from the benchmark tree; --indir defaults to the sequence's rgb/ folder
         from . import sixd
 
-        bench_info = sixd.load_sixd(o.sixd_base, seq=o.obj_id, nr_frames=0)
+        # the Occlusion annotations live in sequence 02 whatever the object (occlusion_betapose_evaluate.py:204)
+        bench_info = sixd.load_sixd(o.sixd_base, seq=2 if occlusion else o.obj_id, nr_frames=0)
         model_vertices, kp_sixd, _ = sixd.load_models(o.sixd_base, o.obj_id, o.nClasses)
         if not o.inputpath and not o.inputlist:
-            o.inputpath = os.path.join(o.sixd_base, "test", f"{o.obj_id:02d}", "rgb")
+            o.inputpath = os.path.join(o.sixd_base, "test", f"{2 if occlusion else o.obj_id:02d}", "rgb")
     if o.synthetic:
         names = [f"synthetic_{i:06d}.png" for i in range(o.synthetic)]
         yolo_stream, kpd_sd, kp3d = synth.cached_yolo_weights(1000), synth.cached_kpd_state_dict(2000), synth.synth_kp_model(1, o.nClasses)
@@ -128,7 +129,7 @@ def main(argv=None):
         if bench_info is not None:
             from . import sixd
 
-            sixd.evaluate_results(results, bench_info, o.obj_id, model_vertices)
+            sixd.evaluate_results(results, bench_info, o.obj_id, model_vertices, occlusion=occlusion, left_keypoints=o.left_keypoints)
         if o.profile:
             print(f"rank 0: {hi - lo} frames in {dt:.3f} s ({(hi - lo) / dt:.1f} frames/s incl. host frame generation / decoding)")
     if world > 1:

@@ -72,25 +72,39 @@ def load_models(base_path: str, obj_id: int, n_kp: int = 50):
     return verts, kp, diam
 
 
-def evaluate_results(final_result, bench: Benchmark, obj_id: int, model_vertices: np.ndarray, cam=model3d.CAM_K,
-                     pixel_thresh: float = 5.0, device=None, log=print) -> dict:
-    """The scoring loop of betapose_evaluate.py:203-266.  final_result: list of {'imgname', 'result', 'cam_R', 'cam_t'}
-    (compat.result_from_record).  A frame is scored when its first ground-truth entry is `obj_id` and it has a pose;
-    ADD and 2-D reprojection only when the boxes overlap by IoU >= 0.5.  All arithmetic in one bp_score_poses launch."""
+def collect_scoring_pairs(final_result, bench: Benchmark, obj_id: int, occlusion: bool = False):
+    """Which (ground truth, estimate) pairs the reference's loop scores (host logic, no GPU):
+    betapose_evaluate.py:216-240 -- only the frame's FIRST ground-truth entry counts, and only if it is `obj_id`;
+    occlusion_betapose_evaluate.py:216-236 -- every ground-truth entry of the frame that is `obj_id` (the Occlusion
+    sequence annotates several objects per frame).  Frames without a pose are skipped either way.
+    -> lists (R_gt, t_gt, box_gt corners, R_est, t_est, box_est)."""
     Rg, tg, bg, Re, te, be = [], [], [], [], [], []
     for f in final_result:
         nr = int(os.path.basename(f["imgname"])[0:-4])  # '0123.png' -> 123
         fr = bench.frames[nr]
         assert fr.nr == nr
-        gt_obj, gt_pose, gt_bb = fr.gt[0]
-        if gt_obj != obj_id:
-            continue
-        if len(f["result"]) < 1 or len(f["result"][0]) < 1:
-            continue
-        Rg.append(gt_pose[:3, :3]); tg.append(gt_pose[:3, 3])
-        bg.append([gt_bb[0], gt_bb[1], gt_bb[0] + gt_bb[2], gt_bb[1] + gt_bb[3]])  # [xmin, ymin, w, h] -> corners
-        Re.append(np.asarray(f["cam_R"], np.float64).reshape(3, 3)); te.append(np.asarray(f["cam_t"], np.float64).reshape(3))
-        be.append(np.asarray(f["result"][0]["bbox"], np.float64).reshape(4))
+        for gt_obj, gt_pose, gt_bb in (fr.gt if occlusion else fr.gt[:1]):
+            if gt_obj != obj_id:
+                continue
+            if len(f["result"]) < 1 or len(f["result"][0]) < 1:
+                continue
+            Rg.append(gt_pose[:3, :3]); tg.append(gt_pose[:3, 3])
+            bg.append([gt_bb[0], gt_bb[1], gt_bb[0] + gt_bb[2], gt_bb[1] + gt_bb[3]])  # [xmin, ymin, w, h] -> corners
+            Re.append(np.asarray(f["cam_R"], np.float64).reshape(3, 3)); te.append(np.asarray(f["cam_t"], np.float64).reshape(3))
+            be.append(np.asarray(f["result"][0]["bbox"], np.float64).reshape(4))
+    return Rg, tg, bg, Re, te, be
+
+
+def evaluate_results(final_result, bench: Benchmark, obj_id: int, model_vertices: np.ndarray, cam=model3d.CAM_K,
+                     pixel_thresh: float | None = None, device=None, log=print, occlusion: bool = False,
+                     left_keypoints: int | None = None) -> dict:
+    """The scoring loop of betapose_evaluate.py:203-266 (occlusion=True: occlusion_betapose_evaluate.py:203-270, which
+    scores every matching ground-truth entry, uses a 20 px reprojection threshold instead of 5 and names left_keypoints in
+    its summary line).  final_result: list of {'imgname', 'result', 'cam_R', 'cam_t'} (compat.result_from_record).
+    ADD and 2-D reprojection only when the boxes overlap by IoU >= 0.5.  All arithmetic in one bp_score_poses launch."""
+    if pixel_thresh is None:
+        pixel_thresh = 20.0 if occlusion else 5.0
+    Rg, tg, bg, Re, te, be = collect_scoring_pairs(final_result, bench, obj_id, occlusion)
     if not Rg:
         return dict(n_frames=0, n_scored=0, add_accuracy=float("nan"), proj2d_accuracy=float("nan"), iou_accuracy=float("nan"))
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
@@ -101,6 +115,9 @@ def evaluate_results(final_result, bench: Benchmark, obj_id: int, model_vertices
                                   pixel_thresh=pixel_thresh)
     out["n_frames"] = len(Rg)
     log("Mean add accuracy for seq %02d is: %.3f" % (obj_id, out["add_accuracy"]))
-    log("2d reprojection accuracy for seq %02d is: %.3f" % (obj_id, out["proj2d_accuracy"]))
+    if occlusion:
+        log("2d reprojection accuracy with leftkeypoints %d for seq %02d is: %.3f" % (int(left_keypoints or 0), obj_id, out["proj2d_accuracy"]))
+    else:
+        log("2d reprojection accuracy for seq %02d is: %.3f" % (obj_id, out["proj2d_accuracy"]))
     log("Mean IoU for seq %02d is: %.3f" % (obj_id, out["iou_accuracy"]))
     return out

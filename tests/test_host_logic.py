@@ -366,3 +366,35 @@ def test_packed_weights_file_roundtrip_and_replay(tmp_path):
     open(str(tmp_path / "junk.bppw"), "wb").write(b"not a cache")
     with pytest.raises(ValueError):
         weights.PackedWeights.load(str(tmp_path / "junk.bppw"))
+
+
+def test_scoring_pair_selection_standard_and_occlusion():
+    """Which (ground truth, estimate) pairs get scored: betapose_evaluate.py:216-240 looks at a frame's first ground-truth
+    entry only; occlusion_betapose_evaluate.py:216-236 at every entry of the wanted object."""
+    from betapose_b200 import sixd
+
+    b = sixd.Benchmark()
+    eye = np.identity(4)
+
+    def pose(z):
+        p = eye.copy()
+        p[2, 3] = z
+        return p
+
+    gts = [[(5, pose(0.5), [10, 20, 30, 40]), (2, pose(0.6), [1, 2, 3, 4])],      # wanted object first
+           [(2, pose(0.7), [1, 2, 3, 4]), (5, pose(0.8), [50, 60, 10, 10])],      # wanted object second
+           [(5, pose(0.9), [0, 0, 5, 5]), (5, pose(1.0), [7, 7, 5, 5])],          # two instances
+           [(5, pose(1.1), [0, 0, 5, 5])]]                                        # no pose estimated
+    for i, g in enumerate(gts):
+        fr = sixd.Frame(i, f"{i:04d}.png", np.identity(3))
+        fr.gt = list(g)
+        b.frames.append(fr)
+    res = [{"bbox": np.array([1.0, 2.0, 3.0, 4.0])}]
+    final = [{"imgname": f"/x/{i:04d}.png", "result": res if i != 3 else [], "cam_R": np.identity(3), "cam_t": np.full((3, 1), float(i))}
+             for i in range(4)]
+    Rg, tg, bg, Re, te, be = sixd.collect_scoring_pairs(final, b, 5, occlusion=False)
+    assert [t[2] for t in tg] == [0.5, 0.9] and bg[0] == [10, 20, 40, 60] and [t[0] for t in te] == [0.0, 2.0]
+    Rg, tg, bg, Re, te, be = sixd.collect_scoring_pairs(final, b, 5, occlusion=True)
+    assert [t[2] for t in tg] == [0.5, 0.8, 0.9, 1.0] and bg[1] == [50, 60, 60, 70] and [t[0] for t in te] == [0.0, 1.0, 2.0, 2.0]
+    assert len(be) == 4 and all(np.array_equal(x, [1, 2, 3, 4]) for x in be)
+    assert sixd.collect_scoring_pairs(final, b, 9, occlusion=True)[0] == []
