@@ -188,3 +188,34 @@ def convert_sequence(paths, out_dir: str, fmt: str = "ppm", frame_h: int = 480, 
                     np.save(q, fr)
                 out_paths.append(q)
     return out_paths
+
+
+def _main(argv=None):
+    """python -m betapose_b200.ingest INDIR OUTDIR [--fmt ppm|npy] [--frame_h 480 --frame_w 640] [--threads 0]
+    Decodes every frame of INDIR once (native pool; Pillow for what it does not read) into OUTDIR as PPM / .npy."""
+    import argparse
+    import os
+    import time
+
+    ap = argparse.ArgumentParser(prog="python -m betapose_b200.ingest")
+    ap.add_argument("indir")
+    ap.add_argument("outdir")
+    ap.add_argument("--fmt", choices=("ppm", "npy"), default="ppm")
+    ap.add_argument("--frame_h", type=int, default=480)
+    ap.add_argument("--frame_w", type=int, default=640)
+    ap.add_argument("--threads", type=int, default=0)
+    a = ap.parse_args(argv)
+    names = sorted(f for f in os.listdir(a.indir) if f.lower().endswith((".png", ".jpg", ".jpeg", ".ppm", ".pgm", ".npy")))
+    if not names:
+        raise SystemExit(f"no frames in {a.indir}")
+    t0 = time.perf_counter()
+    out = convert_sequence([os.path.join(a.indir, n) for n in names], a.outdir, a.fmt, a.frame_h, a.frame_w, a.threads)
+    dt = time.perf_counter() - t0
+    print(f"{len(out)} frames -> {a.outdir} ({a.fmt}) in {dt:.2f} s ({len(out) / dt:.0f} frames/s)")
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+
+    sys.exit(_main())
