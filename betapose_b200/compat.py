@@ -230,8 +230,12 @@ def pnp(points_3D, points_2D, cameraMatrix, mode: int = stages.MODE_RANSAC):
 # ---------------------------------------------------------------------------------------------- output
 def result_from_record(rec, imgname: str, K: int = 50) -> dict:
     """bp_record -> the dict DataWriter appends (dataloader.py:708-730): {'imgname', 'result', 'cam_R', 'cam_t'}."""
-    if int(rec["status"]) != 1:
+    if int(rec["status"]) == 0:  # no detection, or the pose was rejected by pose-NMS: DataWriter appends result = [] (:727-728)
         return {"imgname": imgname, "result": [], "cam_R": [], "cam_t": []}
+    # status 1, and status -1 = a pose-NMS survivor whose PnP found no consensus: the reference appends bbox, key-points
+    # and cam_R / cam_t for EVERY survivor (dataloader.py:715-727; solvePnP's return flag is ignored), so the frame stays
+    # in Betapose-results.json and in the IoU / ADD / 2-D statistics.  cam_R / cam_t then hold the solver's last estimate
+    # (best hypothesis; all zeros if none could be solved), which scores as a miss.
     kp = np.asarray(rec["keypoints"], np.float32).reshape(50, 3)[:K]
     human = {"bbox": np.asarray(rec["box"]), "keypoints": kp[:, :2], "kp_score": kp[:, 2:3], "proposal_score": float(rec["proposal_score"])}
     return {"imgname": imgname, "result": [human], "cam_R": np.asarray(rec["R"]).reshape(3, 3), "cam_t": np.asarray(rec["t"]).reshape(3, 1)}

@@ -51,9 +51,11 @@ void bp_engine_destroy(bp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (void* p : e->owned) cudaFree(p);
-  if (e->resize_tmp) cudaFree(e->resize_tmp);
-  if (e->pnp_scratch) cudaFree(e->pnp_scratch);
-  if (e->hm_scratch) cudaFree(e->hm_scratch);
+  for (auto& kv : e->scratch) {
+    if (kv.second.resize_tmp) cudaFree(kv.second.resize_tmp);
+    if (kv.second.pnp) cudaFree(kv.second.pnp);
+    if (kv.second.hm) cudaFree(kv.second.hm);
+  }
   delete e;
 }
 

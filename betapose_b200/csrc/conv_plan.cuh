@@ -48,12 +48,17 @@ struct ConvPlan {
 template <int BN, int BK, int ST, int CG = 1, int NB = 4, int MT = 1>
 inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   using Cfg = ConvCfg<BN, BK, ST, CG, NB, MT>;
-  static bool attr_done = false;  // per-instantiation; set once per process (single device per process)
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
+  static bool attr_done[64] = {};  // per instantiation and per device (the attribute belongs to the device's context)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      attr_done[dev] = true;
+    }
   }
   // programmatic dependent launch: this kernel's prologue overlaps the tail of the previous kernel in the stream
   // (conv_umma_kernel calls griddepcontrol.wait before it touches global memory)

@@ -312,8 +312,11 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
              (double)P * Q * Cout * (s->out_f32 ? 4 : 2) * (s->store_mode == BP_STORE_UPSAMPLE2 ? 4 : 1) +
              (s->res >= 0 ? (double)P * Q * Cout * 2 : 0.0);
   char buf[160];
-  snprintf(buf, sizeof buf, "conv %dx%d/%d %d->%d @%dx%d bn%d bk%d st%d%s%s%s", k, k, s->stride, Cin, Cout, P, Q,
-           plan0.block_n, plan0.block_k, plan0.stages, s->res >= 0 ? " +res" : "",
+  char tile[32] = "";
+  if (plan0.cg == 2) snprintf(tile, sizeof tile, " cg2");
+  else if (plan0.mt > 1) snprintf(tile, sizeof tile, " mt%d", plan0.mt);
+  snprintf(buf, sizeof buf, "conv %dx%d/%d %d->%d @%dx%d bn%d bk%d st%d%s%s%s%s", k, k, s->stride, Cin, Cout, P, Q,
+           plan0.block_n, plan0.block_k, plan0.stages, tile, s->res >= 0 ? " +res" : "",
            s->store_mode == BP_STORE_UPSAMPLE2 ? " up2" : (s->store_mode == BP_STORE_PIXSHUF2 ? " ps2" : ""),
            s->out_f32 ? " f32" : "");
   op.desc = buf;

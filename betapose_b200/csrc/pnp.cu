@@ -311,11 +311,15 @@ pnp_refine_kernel(const float* __restrict__ preds_img, const float* __restrict__
     }
   }
   bool ok = run && bc >= 4;
+  // `have`: some hypothesis was solved.  A survivor of pose-NMS whose PnP fails (status -1) still gets the solver's last
+  // estimate written out: the reference appends cam_R / cam_t for every survivor (dataloader.py:722-727 ignores
+  // solvePnP's return flag), so the frame must stay in the result list and score as a miss, not vanish.
+  const bool have = run && bc >= 0;
   double R[9], t[3];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = ok ? rows[bh * kHypRow + 2 + k] : 0.0;
+  for (int k = 0; k < 9; ++k) R[k] = have ? rows[bh * kHypRow + 2 + k] : 0.0;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) t[k] = ok ? rows[bh * kHypRow + 11 + k] : 0.0;
+  for (int k = 0; k < 3; ++k) t[k] = have ? rows[bh * kHypRow + 11 + k] : 0.0;
   if (ok) {
     // alternate {classify points against the current pose, LM refit on the consensus set} until the set is stable
     WarpLanes ln;
@@ -341,8 +345,8 @@ pnp_refine_kernel(const float* __restrict__ preds_img, const float* __restrict__
     }
   }
   if (tid == 0) {
-    for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = ok ? R[k] : 0.0;
-    for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = ok ? t[k] : 0.0;
+    for (int k = 0; k < 9; ++k) R_out[(long)i * 9 + k] = have ? R[k] : 0.0;
+    for (int k = 0; k < 3; ++k) t_out[(long)i * 3 + k] = have ? t[k] : 0.0;
     status[i] = S.state == 0 ? 0 : ((ok || (flags & BP_PNP_NMS_ONLY)) ? 1 : -1);
   }
   __syncwarp();
@@ -361,31 +365,24 @@ extern "C" int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* ma
   if (n_hyp < 1 || n_hyp > kMaxHyp) return bp_fail(BP_ERR_UNSUPPORTED, "bp_pose_pnp: n_hyp must be in [1, 128]");
   if (mode != 0 && mode != 1) return bp_fail(BP_ERR_INVALID, "bp_pose_pnp: mode");
   // hypothesis scratch (grow-only; (re)allocated at most once per batch size, outside steady state)
-  const size_t need = (size_t)n * kMaxHyp * kHypRow * sizeof(double);
-  if (e->pnp_scratch_bytes < need) {
-    if (e->pnp_scratch) cudaFree(e->pnp_scratch);
-    if (cudaMalloc(&e->pnp_scratch, need) != cudaSuccess) {
-      e->pnp_scratch = nullptr;
-      e->pnp_scratch_bytes = 0;
-      return bp_fail(BP_ERR_CUDA, "bp_pose_pnp: scratch allocation failed");
-    }
-    e->pnp_scratch_bytes = need;
-  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t need = (size_t)n * kMaxHyp * kHypRow * sizeof(double);
+  bp_engine::StreamScratch& sc = e->scratch_for(st);
+  if (!e->grow(reinterpret_cast<void**>(&sc.pnp), &sc.pnp_bytes, need)) return bp_fail(BP_ERR_CUDA, "bp_pose_pnp: scratch allocation failed");
   const double thr2 = (double)reproj_thr * (double)reproj_thr;
   if (n >= 16) {  // throughput: 8 lanes per hypothesis, 16 hypotheses per CTA
     const int groups = mode == 0 ? (n_hyp + 15) / 16 : 1;
     pnp_hypotheses_kernel<8><<<dim3(groups, n), 128, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1],
                                                               cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints,
-                                                              kp_score, proposal, selected, e->pnp_scratch);
+                                                              kp_score, proposal, selected, sc.pnp);
   } else {        // latency: 16 lanes per hypothesis, 8 hypotheses per CTA
     const int groups = mode == 0 ? (n_hyp + 7) / 8 : 1;
     pnp_hypotheses_kernel<16><<<dim3(groups, n), 128, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1],
                                                                cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints,
-                                                               kp_score, proposal, selected, e->pnp_scratch);
+                                                               kp_score, proposal, selected, sc.pnp);
   }
   pnp_refine_kernel<<<n, 32, 0, st>>>(preds_img, maxval, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode,
-                                      flags, thr2, n_hyp, e->pnp_scratch, R, t, inlier, status);
+                                      flags, thr2, n_hyp, sc.pnp, R, t, inlier, status);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
 }

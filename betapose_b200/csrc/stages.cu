@@ -245,10 +245,9 @@ extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int
       const size_t smem = (size_t)max_rows * (in_pitch + mid_pitch);
       if (smem > 100 * 1024) continue;
       if (smem > 48 * 1024) {
-        static bool attr_done = false;  // once per process (one device per process)
-        if (!attr_done) {
+        static bool attr_done[64] = {};  // per device
+        if (bp_attr_once(attr_done)) {
           if (cudaFuncSetAttribute(resize_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) break;
-          attr_done = true;
         }
       }
       dim3 grid((oh + TH - 1) / TH, B);
@@ -260,21 +259,15 @@ extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int
   }
   // fall-back for extreme sizes: two passes through a global uint8 intermediate
   const size_t need = (size_t)B * H * ow * 3;
-  if (e->resize_tmp_bytes < need) {
-    // grow-only scratch; (re)allocation happens at most once per batch size, outside steady state
-    if (e->resize_tmp) cudaFree(e->resize_tmp);
-    if (cudaMalloc(&e->resize_tmp, need) != cudaSuccess) {
-      e->resize_tmp = nullptr;
-      e->resize_tmp_bytes = 0;
-      return bp_fail(BP_ERR_CUDA, "bp_resize_bicubic: scratch allocation failed");
-    }
-    e->resize_tmp_bytes = need;
-  }
+  bp_engine::StreamScratch& sc = e->scratch_for(st);
+  // per-stream, grow-only scratch; (re)allocation happens at most once per batch size, outside steady state
+  if (!e->grow(reinterpret_cast<void**>(&sc.resize_tmp), &sc.resize_tmp_bytes, need))
+    return bp_fail(BP_ERR_CUDA, "bp_resize_bicubic: scratch allocation failed");
   const long n1 = (long)B * H * ow;
   resize_h_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(frames, B * H, W, ow, th->bounds, th->coeffs, th->ksize,
-                                                              e->resize_tmp);
+                                                              sc.resize_tmp);
   const long n2 = (long)B * oh * ow;
-  resize_v_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(e->resize_tmp, B, H, oh, ow, tv->bounds, tv->coeffs,
+  resize_v_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(sc.resize_tmp, B, H, oh, ow, tv->bounds, tv->coeffs,
                                                               tv->ksize, (__half*)out_net, out_f32_chw);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
@@ -773,23 +766,21 @@ extern "C" int bp_heatmap_decode(bp_engine* e, const float* hm, long img_stride,
     S = (4 * e->num_sms + n - 1) / n;
     S = std::max(1, std::min(S, std::min(16, res_h * res_w / 256)));
   }
+  bp_engine::StreamScratch& sc = e->scratch_for(reinterpret_cast<cudaStream_t>(stream));
   if (S > 1) {
     const size_t need = (size_t)n * 16 * 64 * 8 + (size_t)n * 4;
-    if (e->hm_scratch_bytes < need) {
-      if (e->hm_scratch) cudaFree(e->hm_scratch);
-      if (cudaMalloc(&e->hm_scratch, need) != cudaSuccess) {
-        e->hm_scratch = nullptr;
-        e->hm_scratch_bytes = 0;
-        return bp_fail(BP_ERR_CUDA, "bp_heatmap_decode: scratch allocation failed");
-      }
-      cudaMemsetAsync(e->hm_scratch, 0, need, reinterpret_cast<cudaStream_t>(stream));  // arrival counters start at zero
-      e->hm_scratch_bytes = need;
-      e->hm_scratch_n = n;
+    if (sc.hm_bytes < need) {
+      // per-stream and grow-only: the block this replaces stays allocated (graphs captured earlier point into it)
+      if (!e->grow(&sc.hm, &sc.hm_bytes, need)) return bp_fail(BP_ERR_CUDA, "bp_heatmap_decode: scratch allocation failed");
+      // arrival counters start at zero (a blocking memset: allocation is not steady state and must not be captured)
+      if (cudaMemset(sc.hm, 0, need) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        return bp_fail(BP_ERR_CUDA, "bp_heatmap_decode: scratch memset failed (first use of a batch size inside a stream capture?)");
+      sc.hm_n = n;
     }
   }
   // layout of the scratch: [n_alloc][16][64] float | [n_alloc][16][64] int | [n_alloc] counters
-  const int na = e->hm_scratch_n;
-  float* pv = reinterpret_cast<float*>(e->hm_scratch);
+  const int na = sc.hm_n;
+  float* pv = reinterpret_cast<float*>(sc.hm);
   int* pi = reinterpret_cast<int*>(pv + (size_t)na * 16 * 64);
   unsigned* ctr = reinterpret_cast<unsigned*>(pi + (size_t)na * 16 * 64);
   heatmap_decode_kernel<<<dim3(n, S), T, T * 8, reinterpret_cast<cudaStream_t>(stream)>>>(hm, img_stride, k_stride, pos_stride, K, res_h,

@@ -43,6 +43,15 @@ def gather_records(local: torch.Tensor, n_total: int, group=None) -> torch.Tenso
     return out[keep]
 
 
+def records_to_bytes(rec: np.ndarray) -> torch.Tensor:
+    """structured record array (possibly EMPTY: a rank whose shard holds no frame when n_total < world) -> uint8
+    [n, RECORD_BYTES] host tensor.  The explicit width matters: reshape(0, -1) is an error."""
+    from . import _lib
+
+    assert rec.dtype.itemsize == _lib.RECORD_BYTES
+    return torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8).reshape(len(rec), _lib.RECORD_BYTES).copy())
+
+
 def records_from_bytes(buf: torch.Tensor) -> np.ndarray:
     from . import stages
 

@@ -111,7 +111,7 @@ class BetaposeEngine:
             self.img_idx = torch.arange(B, dtype=i32, device=dev)
             self.model_idx = torch.zeros((B,), dtype=i32, device=dev)
             self.frames = torch.zeros((B, frame_h, frame_w, 3), dtype=u8, device=dev)
-        self._cam = (C.c_double * 4)(self.cam_K[0, 0], self.cam_K[1, 1], self.cam_K[0, 2], self.cam_K[1, 2])
+        self._cam = (C.c_double * 4)(*stages.pinhole4(self.cam_K))
         self._head_args = []
         for s in range(self.n_slots):
             hs = self.heads[s]
@@ -169,6 +169,10 @@ class BetaposeEngine:
                    "bp_heatmap_decode")
 
     def _enqueue_tail(self, n: int, image_index0: int, st) -> None:
+        self._enqueue_pnp(n, st)
+        self._enqueue_pack(n, image_index0, st)
+
+    def _enqueue_pnp(self, n: int, st) -> None:
         L, e = _lib.lib(), self.yolo[0].engine.handle
         _lib.check(L.bp_pose_pnp(e, _lib.ptr(self.preds_img), _lib.ptr(self.maxval), _lib.ptr(self.det_score),
                                  _lib.ptr(self.valid), n, self.K, _lib.ptr(self.kp3d), _lib.ptr(self.model_idx),
@@ -176,6 +180,9 @@ class BetaposeEngine:
                                  self.seed & 0xFFFFFFFF, _lib.ptr(self.keypoints), _lib.ptr(self.kp_score),
                                  _lib.ptr(self.proposal), _lib.ptr(self.selected), _lib.ptr(self.R), _lib.ptr(self.t),
                                  _lib.ptr(self.inlier), _lib.ptr(self.status), st), "bp_pose_pnp")
+
+    def _enqueue_pack(self, n: int, image_index0: int, st) -> None:
+        L, e = _lib.lib(), self.yolo[0].engine.handle
         _lib.check(L.bp_pack_records(e, n, self.K, int(image_index0), _lib.ptr(self.box), _lib.ptr(self.det_score),
                                      _lib.ptr(self.keypoints), _lib.ptr(self.kp_score), _lib.ptr(self.proposal),
                                      _lib.ptr(self.R), _lib.ptr(self.t), _lib.ptr(self.status), _lib.ptr(self.records), st),
@@ -183,6 +190,11 @@ class BetaposeEngine:
 
     def _enqueue(self, n: int, groups, image_index0: int) -> None:
         st = _lib.stream_ptr()
+        if self.n_slots > 1:
+            # the key-point model each frame is solved against follows from the grouping of THIS call (a stale
+            # model_idx from an earlier mixed-object batch would pair slot s's networks with another object's model)
+            for slot, b0, cnt in groups:
+                self.model_idx[b0:b0 + cnt].fill_(int(slot))
         if self.concurrent_slots and len(groups) > 1:
             main = torch.cuda.current_stream()
             if not hasattr(self, "_slot_streams"):
@@ -205,7 +217,7 @@ class BetaposeEngine:
     # ------------------------------------------------------------------------------------------------
     def run_device(self, n: int | None = None, groups=None, image_index0: int = 0, graph: bool = False) -> torch.Tensor:
         """Process the first n frames already resident in `self.frames` (grouped by slot: list of (slot, first, count),
-        frames of one slot contiguous; `self.model_idx` must match).  Returns the records tensor view [n, RECORD_BYTES]
+        frames of one slot contiguous; `self.model_idx` is rewritten from the grouping).  Returns the records tensor view [n, RECORD_BYTES]
         (device); nothing has synchronised."""
         n = self.B if n is None else int(n)
         groups = [(0, 0, n)] if groups is None else list(groups)
@@ -216,16 +228,64 @@ class BetaposeEngine:
                 key = (n, tuple(groups), image_index0)
                 g = self._graphs.get(key)
                 if g is None:
-                    # warm-up outside capture (lazy allocations, func attributes), then capture on a side stream
-                    self._enqueue(n, groups, image_index0)
-                    torch.cuda.synchronize()
+                    # warm-up ON the capture stream (the library keeps its kernel scratch per stream: lazy allocations,
+                    # function attributes and descriptor builds for this batch size all happen here, outside capture),
+                    # then capture on that same stream.  One capture stream per engine: graphs of different engines
+                    # never share scratch.
+                    if not hasattr(self, "_capture_stream"):
+                        self._capture_stream = torch.cuda.Stream()
+                    cap = self._capture_stream
+                    cap.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(cap):
+                        self._enqueue(n, groups, image_index0)
+                    cap.synchronize()
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with torch.cuda.graph(g, stream=cap):
                         self._enqueue(n, groups, image_index0)
                     self._graphs[key] = g
                 g.replay()
         self.launches_per_step = self.count_launches(len(groups))
         return self.records[:n]
+
+    def profile_stages(self, n: int | None = None, reps: int = 5) -> dict:
+        """Device time of every stage of one step on the frames resident in `self.frames` (slot 0), CUDA events between the
+        stages, median of `reps` eager passes: the reference's `--profile` readout (betapose_evaluate.py:132-136,178-186:
+        detection / pose / post-processing wall-clock lists without any synchronisation) measured where the work runs.
+        -> {'resize', 'detector', 'decode_argmax', 'crop', 'keypoint_net', 'heatmap_decode', 'pose_pnp', 'pack', 'total'} in ms."""
+        n = self.B if n is None else int(n)
+        L, e, st = _lib.lib(), self.yolo[0].engine.handle, _lib.stream_ptr()
+        yolo, kpd, ha = self.yolo[0], self.kpd[0], self._head_args[0]
+        names = ["resize", "detector", "decode_argmax", "crop", "keypoint_net", "heatmap_decode", "pose_pnp", "pack"]
+        with torch.cuda.device(self.device):
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(reps + 1)]
+            for r in range(reps + 1):  # pass 0 = warm-up
+                k = iter(ev[r])
+                next(k).record()
+                _lib.check(L.bp_resize_bicubic(e, _lib.ptr(self.frames), n, self.frame_h, self.frame_w, self.reso, self.reso,
+                                               C.c_void_p(yolo.tensor_info(0)["ptr"]), None, st), "bp_resize_bicubic")
+                next(k).record()
+                _lib.check(L.bp_net_forward(yolo.handle, n, st), "bp_net_forward(yolo)")
+                next(k).record()
+                _lib.check(L.bp_yolo_decode_argmax(e, ha["ptrs"], ha["grids"], ha["pitches"], ha["n"], ha["anchors"], ha["n_attr"], n,
+                                                   self.reso, self.conf, self.frame_w, self.frame_h, _lib.ptr(self.det), _lib.ptr(self.box),
+                                                   _lib.ptr(self.det_score), _lib.ptr(self.row), _lib.ptr(self.valid), None, st), "bp_yolo_decode_argmax")
+                next(k).record()
+                _lib.check(L.bp_crop_resize(e, _lib.ptr(self.frames), self.frame_h, self.frame_w, _lib.ptr(self.box), _lib.ptr(self.img_idx),
+                                            _lib.ptr(self.valid), n, self.inp_h, self.inp_w, C.c_void_p(kpd.tensor_info(0)["ptr"]), None,
+                                            _lib.ptr(self.pt1), _lib.ptr(self.pt2), st), "bp_crop_resize")
+                next(k).record()
+                _lib.check(L.bp_net_forward(kpd.handle, n, st), "bp_net_forward(kpd)")
+                next(k).record()
+                self._enqueue_decode(0, 0, n, st)
+                next(k).record()
+                self._enqueue_pnp(n, st)
+                next(k).record()
+                self._enqueue_pack(n, 0, st)
+                next(k).record()
+            torch.cuda.synchronize()
+        out = {nm: float(np.median([ev[r][i].elapsed_time(ev[r][i + 1]) for r in range(1, reps + 1)])) for i, nm in enumerate(names)}
+        out["total"] = float(np.median([ev[r][0].elapsed_time(ev[r][-1]) for r in range(1, reps + 1)]))
+        return out
 
     def run_stream(self, batches, graph: bool = True, image_index0: int = 0, after_step=None):
         """Pipelined evaluation of a stream of frame batches (the reference's evaluate loop is a producer/consumer
@@ -307,7 +367,6 @@ class BetaposeEngine:
                 s0 += cnt
             idx = torch.from_numpy(order)
             fr = fr[idx.to(fr.device)] if fr.is_cuda else fr[idx]
-            self.model_idx[:n].copy_(torch.from_numpy(sorted_slots.astype(np.int32)), non_blocking=True)
         self.frames[:n].copy_(fr, non_blocking=True)
         rec = self.run_device(n, groups, image_index0, graph=graph)
         out = stages.records_to_numpy(rec)

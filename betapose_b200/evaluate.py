@@ -35,6 +35,7 @@ def main(argv=None):
     occlusion = o.mode == "occlusion"
     left = o.left_keypoints if occlusion else o.nClasses  # DataWriter(cam_K, 50, ...) vs (cam_K, args.left_keypoints, ...)
     bench_info = model_vertices = kp_sixd = blocks = None
+    has_camera_yml = bool(o.sixd_base) and os.path.exists(os.path.join(o.sixd_base, "camera.yml"))
     if o.sixd_base:
         # the reference's evaluation set-up (betapose_evaluate.py:86-98, 203-206): models, key-point model and ground truth
         # of sequence --obj_id from the benchmark tree; --indir defaults to the sequence's rgb/ folder
@@ -96,8 +97,12 @@ def main(argv=None):
     lo, hi = bdist.shard_range(n_total, rank, world)
     B = min(o.batch, max(1, hi - lo))
     mode = stages.MODE_RANSAC if o.pnp_mode == "ransac" else stages.MODE_ALLPTS
+    # PnP intrinsics: the reference hard-codes the LineMod K for the solver (betapose_evaluate.py:59 -> DataWriter); a
+    # benchmark tree with its own camera.yml is solved and scored with that camera instead (documented divergence)
+    cam_K = bench_info.cam if (bench_info is not None and has_camera_yml) else model3d.CAM_K
     eng = BetaposeEngine(B, yolo_stream, kpd_sd, kp3d, reso=int(o.inp_dim), inp_h=o.inputResH, inp_w=o.inputResW, n_kp=o.nClasses,
-                         left_number=left, conf=o.confidence, pnp_mode=mode, cfg_blocks=blocks, frame_h=o.frame_h, frame_w=o.frame_w)
+                         left_number=left, conf=o.confidence, pnp_mode=mode, cfg_blocks=blocks, frame_h=o.frame_h, frame_w=o.frame_w,
+                         cam_K=cam_K)
     recs = []
     t0 = time.time()
 
@@ -120,7 +125,7 @@ def main(argv=None):
     torch.cuda.synchronize()
     dt = time.time() - t0
     mine = np.concatenate(recs) if recs else np.zeros(0, stages.RECORD_DTYPE)
-    local_bytes = torch.from_numpy(mine.view(np.uint8).reshape(len(mine), -1).copy()).cuda()
+    local_bytes = bdist.records_to_bytes(mine).cuda()  # [0, RECORD_BYTES] on a rank whose shard is empty (n_total < world)
     allrec = stages.records_to_numpy(bdist.gather_records(local_bytes, n_total))
     if rank == 0:
         results = [compat.result_from_record(allrec[i], names[int(allrec[i]["image_index"])], o.nClasses) for i in range(n_total)]
@@ -129,9 +134,23 @@ def main(argv=None):
         if bench_info is not None:
             from . import sixd
 
-            sixd.evaluate_results(results, bench_info, o.obj_id, model_vertices, occlusion=occlusion, left_keypoints=o.left_keypoints)
+            # the reference scores with bench_info.cam (betapose_evaluate.py:248-249), which load_sixd fills from
+            # <sixd_base>/camera.yml and leaves at identity otherwise; the identity fallback is meaningless for a
+            # reprojection in pixels, so without camera.yml the LineMod intrinsics of betapose_evaluate.py:59 are used
+            cam = bench_info.cam if has_camera_yml else model3d.CAM_K
+            sixd.evaluate_results(results, bench_info, o.obj_id, model_vertices, cam=cam, occlusion=occlusion, left_keypoints=o.left_keypoints)
         if o.profile:
             print(f"rank 0: {hi - lo} frames in {dt:.3f} s ({(hi - lo) / dt:.1f} frames/s incl. host frame generation / decoding)")
+            # per-stage readout (betapose_evaluate.py:132-136,178-186 prints det / pose / post wall-clock means): device time of
+            # every stage of one batch, CUDA events, on the last batch's frames
+            nb = min(B, hi - lo)
+            if nb > 0:
+                sm = eng.profile_stages(nb)
+                print(f"stage times for a batch of {nb} (ms): " + " | ".join(f"{k} {v:.3f}" for k, v in sm.items()))
+                print("det time: {dt:.3f} | pose time: {pt:.3f} | post processing: {pn:.3f}   (ms per batch: resize + detector + decode + crop | "
+                      "key-point net | heat-map decode + pose-NMS + PnP + pack)".format(
+                          dt=sm["resize"] + sm["detector"] + sm["decode_argmax"] + sm["crop"], pt=sm["keypoint_net"],
+                          pn=sm["heatmap_decode"] + sm["pose_pnp"] + sm["pack"]))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

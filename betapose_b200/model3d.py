@@ -39,9 +39,26 @@ def refine(vertices: np.ndarray, n_keep: int) -> np.ndarray:
     return v
 
 
-def load_kp_model(path: str, n_classes: int = 50) -> np.ndarray:
+def load_kp_model(path: str, n_classes: int = 50, short: str = "error") -> np.ndarray:
+    """Key-point model of one object: PLY x 0.001 -> refine(n_classes) (betapose_evaluate.py:75-83).
+
+    A model with FEWER than n_classes points cannot be used by the reference at all: its pnp() asserts equal counts of
+    3-D and 2-D points (utils/utils.py:23) and the key-point network always predicts n_classes maps.  That is the case
+    of the one shipped PLY with 17 vertices, 1_keypoint_designator/assets/sifts/10.ply (LineMod object 10, the
+    `Semmetry_obj10` entry of KPD/src/main_fast_inference.py:29-32).
+      short = "error" (default): refuse at load time instead of failing per frame, like the reference would;
+      short = "cycle": pad to n_classes by cycling, kp3d[k] = ply[k % n_points] -- heat-map k is then read as a detector
+                       of model point k % n_points.  This is the documented choice for running all 13 objects from the
+                       shipped fixtures (BASELINE.json configs[3]; SURVEY.md 8(d) "pad to 50 by cycling or exclude")."""
     v = refine(load_ply(path), n_classes)
     if v.shape[0] != n_classes:
+        if short == "cycle" and 0 < v.shape[0] < n_classes:
+            return pad_by_cycling(v, n_classes)
         # the reference's pnp() asserts equal counts (utils/utils.py:23); fail at load time instead of per frame
         raise ValueError(f"{path}: {v.shape[0]} key-points, the key-point network predicts {n_classes}")
     return v
+
+
+def pad_by_cycling(v: np.ndarray, n_classes: int) -> np.ndarray:
+    v = np.asarray(v, np.float64)
+    return v[np.arange(n_classes) % v.shape[0]].copy()

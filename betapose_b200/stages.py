@@ -152,6 +152,16 @@ def heatmap_decode(hm: torch.Tensor, pt1: torch.Tensor, pt2: torch.Tensor, layou
     return dict(preds_hm=ph, preds_img=pi, maxval=mv, idx=idx)
 
 
+def pinhole4(cam_K) -> tuple[float, float, float, float]:
+    """(fx, fy, cx, cy) of a 3x3 camera matrix.  The PnP and scoring kernels model a plain pinhole camera; a matrix with
+    skew or a non-unit last row (which cv2.solvePnP / utils/metrics.py would honour) is refused instead of being
+    silently mis-read."""
+    K = np.asarray(cam_K, np.float64)
+    if K.shape != (3, 3) or K[0, 1] != 0 or K[1, 0] != 0 or K[2, 0] != 0 or K[2, 1] != 0 or K[2, 2] != 1:
+        raise _lib.BetaposeError(f"camera matrix must be [[fx,0,cx],[0,fy,cy],[0,0,1]] (no skew), got {K.tolist()}")
+    return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+
+
 MODE_RANSAC, MODE_ALLPTS = 0, 1
 PNP_RAW_POINTS, PNP_NMS_ONLY = 1, 2
 
@@ -165,8 +175,7 @@ def pose_pnp(preds_img: torch.Tensor, maxval: torch.Tensor, det_score: torch.Ten
     n, K = int(preds_img.shape[0]), int(preds_img.shape[1])
     dev = preds_img.device
     assert kp3d.dtype == torch.float64 and kp3d.is_cuda
-    cam = torch.tensor([cam_K[0][0], cam_K[1][1], cam_K[0][2], cam_K[1][2]], dtype=torch.float64)
-    cam_arr = (C.c_double * 4)(*cam.tolist())
+    cam_arr = (C.c_double * 4)(*pinhole4(cam_K))
     out = dict(
         keypoints=torch.empty((n, K, 2), dtype=torch.float32, device=dev),
         kp_score=torch.empty((n, K), dtype=torch.float32, device=dev),
@@ -223,8 +232,7 @@ def score_poses(R_est, t_est, box_est, R_gt, t_gt, box_gt, model, cam_K=CAM_K, s
     be, bg = box_est.to(dev, torch.float32).contiguous(), box_gt.to(dev, torch.float32).contiguous()
     m = model.to(dev, torch.float64).contiguous()
     V = int(m.shape[-2])
-    K = np.asarray(cam_K, np.float64)
-    cam = (C.c_double * 4)(K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    cam = (C.c_double * 4)(*pinhole4(cam_K))
     add = torch.empty(n, dtype=torch.float64, device=dev)
     proj = torch.empty(n, dtype=torch.float64, device=dev)
     iou = torch.empty(n, dtype=torch.float32, device=dev)

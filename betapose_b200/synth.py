@@ -221,6 +221,78 @@ def cached_kpd_state_dict(seed: int = 2000) -> dict:
     return sd
 
 
+# ------------------------------------------------------------------------------------------------ per-object variants
+# BASELINE.json configs[3] mixes the 13 LineMod objects, each with its own detector and key-point network.  Calibrating 13
+# random weight sets costs ~15 s of CPU each; instead object v > 0 gets object 0's networks seen through a fixed input
+# symmetry: every convolution kernel mirrored left-right and / or up-down and the colour channels of the stem permuted,
+#   f_v(x) ~ mirror(f_0(mirror(permute_rgb(x)))).
+# The weights are different bytes and the networks different functions of the frame, while every layer keeps the
+# activation statistics object 0 was calibrated to (the synthetic frames have no preferred direction or colour), so the
+# variants are as fp16-safe and input-dependent as the original.  (Mirroring is exact only up to the one-pixel alignment
+# shift of stride-2 layers on even sizes; that does not matter for statistics.)
+_RGB_PERMS = ((0, 1, 2), (1, 2, 0), (2, 0, 1), (0, 2, 1), (2, 1, 0), (1, 0, 2))
+
+
+def _variant_ops(v: int):
+    v = int(v)
+    return _RGB_PERMS[v % 6], bool((v // 6) & 1) != bool(v & 1), bool((v // 12) & 1) != bool((v >> 1) & 1)  # perm, flip_lr, flip_ud
+
+
+def _variant_kernel(w: np.ndarray, flip_lr: bool, flip_ud: bool) -> np.ndarray:
+    if flip_lr:
+        w = w[:, :, :, ::-1]
+    if flip_ud:
+        w = w[:, :, ::-1, :]
+    return w
+
+
+def variant_yolo_weights(stream: np.ndarray, v: int, blocks: list[dict] | None = None) -> np.ndarray:
+    """darknet fp32 stream of object-variant v (v = 0: the stream itself)."""
+    if v == 0:
+        return stream
+    from . import net as _net, weights as _weights
+
+    blocks = blocks if blocks is not None else yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
+    perm, lr, ud = _variant_ops(v)
+    params, used = _net.split_darknet_stream(blocks, np.asarray(stream, np.float32))
+    assert used == stream.size
+    first = True
+    out = []
+    for p in params:
+        if p is None:
+            out.append(None)
+            continue
+        q = dict(p)
+        w = _variant_kernel(p["weight"], lr, ud)
+        if first:
+            w = w[:, list(perm)]
+            first = False
+        q["weight"] = np.ascontiguousarray(w)
+        out.append(q)
+    return _weights.darknet_stream_from_params(blocks, out)
+
+
+def variant_kpd_state_dict(sd: dict, v: int) -> dict:
+    """FastPose state_dict of object-variant v (v = 0: the dict itself)."""
+    if v == 0:
+        return sd
+    perm, lr, ud = _variant_ops(v)
+    out = {}
+    for k, t in sd.items():
+        if t.dim() == 4:
+            w = t
+            if lr:
+                w = w.flip(3)
+            if ud:
+                w = w.flip(2)
+            if k == "preact.conv1.weight":
+                w = w[:, list(perm)]
+            out[k] = w.contiguous()
+        else:
+            out[k] = t
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ keypoint models
 def synth_kp_model(seed: int = 1, n: int = 50, radius: float = 0.045) -> np.ndarray:
     """[n,3] float64 metres: points on a bumpy ellipsoid of LineMod-object size (the 13 designated-keypoint PLYs

@@ -193,6 +193,43 @@ def load_metrics() -> types.ModuleType:
     return _load("utils.metrics", "utils/metrics.py")
 
 
+def load_pnp():
+    """The reference's own ``pnp`` (3_6Dpose_estimator/utils/utils.py:17-41): the module cannot be imported (it pulls
+    renderer / vispy / scipy.misc at import), so the text of that one function is exec'd as written."""
+    import cv2
+
+    root = ref_root()
+    src = open(os.path.join(root, _E, "utils/utils.py")).read()
+    a = src.index("def pnp(")
+    b = src.index("    return R, t", a) + len("    return R, t")
+    ns = {"np": np, "cv2": cv2}
+    exec(compile(src[a:b] + "\n", "utils/utils.py<pnp>", "exec"), ns)
+    return ns["pnp"]
+
+
+def load_datawriter():
+    """``class DataWriter`` of 3_6Dpose_estimator/dataloader.py:649-763 exec'd as written (the module as a whole drags in
+    renderer / vispy), with the names it uses bound to the reference's own functions: getPrediction, pose_nms, pnp, opt.
+    Used to generate the a12 golden (result assembly + write_json), tests/golden/make_golden.py."""
+    import json
+    import time
+    from queue import Queue
+    from threading import Thread
+
+    import cv2
+    import torch
+
+    ref = load_reference()
+    root = ref_root()
+    src = open(os.path.join(root, _E, "dataloader.py")).read()
+    a = src.index("class DataWriter:")
+    b = src.index("class Mscoco", a)
+    ns = {"np": np, "cv2": cv2, "os": os, "time": time, "json": json, "torch": torch, "Queue": Queue, "Thread": Thread,
+          "opt": ref.opt, "getPrediction": ref.getPrediction, "pose_nms": ref.pose_nms, "pnp": load_pnp(), "write_json": ref.write_json}
+    exec(compile(src[a:b], "dataloader.py<DataWriter>", "exec"), ns)
+    return ns["DataWriter"]
+
+
 def ref_pnp(points_3D, points_2D, cameraMatrix):
     """The reference's ``pnp`` body (3_6Dpose_estimator/utils/utils.py:17-41) cannot be imported (the module
     pulls renderer/vispy at import); its two live statements are the cv2 calls below."""

@@ -183,8 +183,117 @@ def versions():
     return np.array([f"torch {torch.__version__}", f"cv2 {cv2.__version__}", f"Pillow {PIL.__version__}", f"numpy {np.__version__}"])
 
 
+def make_a12_golden():
+    """a12: the reference's result assembly and output format -- `DataWriter.update` (dataloader.py:678-741: getPrediction ->
+    pose_nms -> key-point selection -> pnp -> final_result.append) and `write_json` (pPose_nms.py:284-371), both exec'd as
+    written.  Frames: two with planted poses, one whose peaks are all below the 0.3 threshold (rejected: result = []), one
+    without a detection (boxes None: nothing appended).  Run with left_number = 50 (betapose_evaluate.py:139) and 10
+    (occlusion_betapose_evaluate.py:139).  The active solver is cv2.solvePnP ITERATIVE (utils/utils.py:25-29); the poses are
+    chosen so that it converges to the least-squares minimum (checked below against EPnP + LM on the same points)."""
+    import json
+    import math
+    import time
+
+    import cv2
+
+    from oracle import pnp as opnp
+
+    ref = ref_shim.load_reference()
+    DataWriter = ref_shim.load_datawriter()
+    kp = R.load_ply_vertices(os.path.join(ref.sift_dir, "1.ply"))
+    rng = np.random.default_rng(1212)
+    W, H = 640, 480
+    frames = []
+    for case in range(4):
+        for attempt in range(200):
+            rv = rng.standard_normal(3)
+            rv *= rng.uniform(0.2, math.pi * 0.9) / np.linalg.norm(rv)
+            Rm = cv2.Rodrigues(rv)[0]
+            t = np.array([rng.uniform(-0.08, 0.08), rng.uniform(-0.06, 0.06), rng.uniform(0.7, 1.0)])
+            pc = kp @ Rm.T + t
+            uv = np.stack([R.CAM_K[0, 0] * pc[:, 0] / pc[:, 2] + R.CAM_K[0, 2], R.CAM_K[1, 1] * pc[:, 1] / pc[:, 2] + R.CAM_K[1, 2]], 1)
+            box = np.array([uv[:, 0].min() - 4, uv[:, 1].min() - 4, uv[:, 0].max() + 4, uv[:, 1].max() + 4], np.float32)
+            pt1, pt2 = R.expand_box(box, W, H)
+            # inverse of transformBoxInvert_batch (A.5): heat-map position of an image point
+            lenH = max(float(pt2[1] - pt1[1]), float(pt2[0] - pt1[0]) * 320 / 256)
+            lenW = lenH * 256 / 320
+            padx = max(0.0, (lenW - 1) / 2 - (float(pt2[0]) - 1 - float(pt1[0])) / 2)
+            pady = max(0.0, (lenH - 1) / 2 - (float(pt2[1]) - 1 - float(pt1[1])) / 2)
+            hx = (uv[:, 0] + 0.3 - float(pt1[0]) + padx) * 80 / lenH - 0.2
+            hy = (uv[:, 1] + 0.3 - float(pt1[1]) + pady) * 80 / lenH - 0.2
+            ix, iy = np.round(hx).astype(int), np.round(hy).astype(int)
+            if ix.min() < 1 or iy.min() < 1 or ix.max() > 62 or iy.max() > 78:
+                continue
+            hm = np.zeros((1, 50, 80, 64), np.float32)  # sparse maps (the file stays small); peaks and their neighbours below
+            peak = rng.uniform(0.35, 0.95, 50).astype(np.float16).astype(np.float32)
+            if case == 2:
+                peak = (peak * 0.25).astype(np.float16).astype(np.float32)  # every peak < 0.3 -> pose rejected
+            for k in range(50):
+                hm[0, k, iy[k], ix[k]] = peak[k]
+                # quarter-pixel refinement towards the true sub-pixel position
+                hm[0, k, iy[k], ix[k] + (1 if hx[k] > ix[k] else -1)] = np.float16(0.2 * peak[k])
+                hm[0, k, iy[k] + (1 if hy[k] > iy[k] else -1), ix[k]] = np.float16(0.2 * peak[k])
+            ph, pi, mv = ref.getPrediction(torch.from_numpy(hm), torch.from_numpy(pt1[None]), torch.from_numpy(pt2[None]), 320, 256, 80, 64)
+            kp2d = pi[0].numpy() - np.float32(0.3)
+            if case != 2:
+                # the active solver must be in its convergence basin on this frame (SURVEY D5), for 50 and for the top-10 points
+                good = True
+                for left in (50, 10):
+                    keep = R.select_keypoints(mv[0, :, 0].numpy(), left)
+                    Ri, ti = ref_shim.load_pnp()(kp[keep], kp2d[keep], R.CAM_K)
+                    sol = opnp.solve_pnp(kp[keep], kp2d[keep], R.CAM_K, mode=opnp.MODE_ALLPTS)
+                    good &= bool(sol["ok"]) and np.abs(Ri - sol["R"]).max() < 1e-6 and np.abs(ti.reshape(3) - sol["t"]).max() < 1e-6
+                if not good:
+                    continue
+            frames.append(dict(hm=hm, box=box, score=np.float32(rng.uniform(0.3, 0.99)), pt1=pt1, pt2=pt2, R_true=Rm, t_true=t))
+            break
+        else:
+            raise RuntimeError("no usable pose found")
+    names = ["0007.png", "0011.png", "0012.png", "0020.png"]
+    out = {"kp3d": kp, "names": np.array(names), "versions": versions()}
+    for i, f in enumerate(frames):
+        out[f"hm{i}"] = f["hm"].astype(np.float16)
+        out[f"box{i}"], out[f"score{i}"], out[f"pt1_{i}"], out[f"pt2_{i}"] = f["box"], f["score"], f["pt1"], f["pt2"]
+    for left in (50, 10):
+        ref.opt.format = None
+        w = DataWriter(R.CAM_K, left, kp).start()
+        orig = np.zeros((H, W, 3), np.uint8)
+        expect = 0
+        for i, f in enumerate(frames):
+            if i == 3:  # a frame without a detection first (dataloader.py:691: boxes is None -> nothing is appended)
+                w.save(None, None, None, None, None, orig, "0015.png")
+            w.save(torch.from_numpy(f["box"][None].copy()), torch.from_numpy(np.array([[f["score"]]], np.float32)), torch.from_numpy(f["hm"].copy()),
+                   torch.from_numpy(f["pt1"][None].copy()), torch.from_numpy(f["pt2"][None].copy()), orig, names[i])
+            expect += 1
+        t0 = time.time()
+        while len(w.results()) < expect and time.time() - t0 < 60:
+            time.sleep(0.05)
+        w.stop()
+        res = w.results()
+        assert len(res) == expect and [r["imgname"] for r in res] == names
+        with tempfile.TemporaryDirectory() as td:
+            ref.write_json(res, td)
+            text = open(os.path.join(td, "Betapose-results.json")).read()
+        js = json.loads(text)
+        assert len(js) == 3 and [e["image_id"] for e in js] == ["0007.png", "0011.png", "0020.png"]
+        out[f"json_left{left}"] = np.array(text)
+        for i, r in enumerate(res):
+            out[f"left{left}_n{i}"] = len(r["result"])
+            if r["result"]:
+                h = r["result"][0]
+                out[f"left{left}_kp{i}"] = np.asarray(h["keypoints"], np.float32)
+                out[f"left{left}_sc{i}"] = np.asarray(h["kp_score"], np.float32)
+                out[f"left{left}_prop{i}"] = np.asarray(h["proposal_score"], np.float32)
+                out[f"left{left}_bbox{i}"] = np.asarray(h["bbox"], np.float32)
+                out[f"left{left}_R{i}"] = np.asarray(r["cam_R"], np.float64)
+                out[f"left{left}_t{i}"] = np.asarray(r["cam_t"], np.float64)
+    np.savez_compressed(os.path.join(HERE, "a12_golden.npz"), **out)
+    print("a12_golden.npz", os.path.getsize(os.path.join(HERE, "a12_golden.npz")))
+
+
 def main():
     make_metrics_golden()
+    make_a12_golden()
     assert ref_shim.available(), "reference tree not found"
     ref = ref_shim.load_reference()
     rng = np.random.default_rng(2024)
@@ -419,6 +528,9 @@ def make_metrics_golden():
     print("metrics_golden.npz", np.array(add)[:4], np.array(iou)[:6])
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "a12":
+    make_a12_golden()
+    sys.exit(0)
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         make_metrics_golden()

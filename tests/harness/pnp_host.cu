@@ -37,7 +37,10 @@ extern "C" int bp_host_pnp(const double* pw, const double* uv, const unsigned ch
         memcpy(bR, R, sizeof bR); memcpy(bt, t, sizeof bt);
       }
     }
-    if (bc < 4) { *best_h = -1; return -1; }
+    if (bc < 4) {  // no consensus: failure, with the best hypothesis as the last estimate (as the kernel and the oracle do)
+      if (bc >= 0) { memcpy(R_out, bR, sizeof bR); memcpy(t_out, bt, sizeof bt); }
+      return -1;
+    }
   } else {
     int m = 0;
     for (int j = 0; j < K; ++j)
@@ -55,7 +58,12 @@ extern "C" int bp_host_pnp(const double* pw, const double* uv, const unsigned ch
       cnt += in;
     }
     if (round > 0 && !changed) break;
-    if (cnt < 4) { memset(inl, 0, K); return -1; }
+    if (cnt < 4) {
+      memset(inl, 0, K);
+      memcpy(R_out, bR, sizeof bR);
+      memcpy(t_out, bt, sizeof bt);
+      return -1;
+    }
     lm_refine(ln, bR, bt, pw, uv, inl, K, fx, fy, cx, cy, BP_PNP_LM_ITERS);
     if (!ransac) break;
   }

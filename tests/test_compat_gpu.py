@@ -101,3 +101,55 @@ def test_pose_nms_and_pnp_seams(kp_model):
     assert np.abs(Rg - Rm).max() < 2e-2
     with pytest.raises(AssertionError):
         compat.pnp(kp_model[:10], uv, R.CAM_K)
+
+
+@pytest.mark.parametrize("left", [50, 10])
+def test_a12_datawriter_assembly_and_json_vs_reference_golden(tmp_path, left):
+    """a12 through the product: the seams DataWriter.update calls (getPrediction -> pose_nms -> selection -> pnp) and
+    write_json, and the engine's own tail (bp_pose_pnp -> bp_pack_records -> result_from_record -> write_json), on the
+    heat-maps of tests/golden/a12_golden.npz; expected = the JSON the reference's own DataWriter + write_json produced."""
+    import json
+    import os
+
+    from betapose_b200 import compat, stages
+    from test_oracle_golden import check_a12_json, load
+
+    g = load("a12_golden.npz")
+    kp3d = g["kp3d"]
+    names = [str(n) for n in g["names"]]
+    # ---- (i) seam by seam, CPU tensors in, like DataWriter.update
+    final = []
+    for i, name in enumerate(names):
+        hm = torch.from_numpy(g[f"hm{i}"].astype(np.float32))
+        boxes, scores = torch.from_numpy(g[f"box{i}"][None].copy()), torch.tensor([[float(g[f"score{i}"])]])
+        ph, pi, ps = compat.getPrediction(hm, torch.from_numpy(g[f"pt1_{i}"][None].copy()), torch.from_numpy(g[f"pt2_{i}"][None].copy()), 320, 256, 80, 64)
+        result = {"imgname": name, "result": compat.pose_nms(boxes, scores, pi, ps)}
+        if result["result"]:
+            kp_score = np.array(result["result"][0]["kp_score"][:, 0])
+            kp_2d = np.array(result["result"][0]["keypoints"])
+            kp_3d = np.array(kp3d)
+            while len(kp_2d) > left:               # dataloader.py:720-724 verbatim semantics
+                d = np.argmin(kp_score, axis=0)
+                kp_score, kp_2d, kp_3d = np.delete(kp_score, d), np.delete(kp_2d, d, axis=0), np.delete(kp_3d, d, axis=0)
+            Rm, t = compat.pnp(kp_3d, kp_2d, R.CAM_K)
+            result.update({"cam_R": Rm, "cam_t": t})
+        else:
+            result.update({"cam_R": [], "cam_t": []})
+        final.append(result)
+    compat.write_json(final, str(tmp_path / "seams"))
+    check_a12_json(json.load(open(tmp_path / "seams" / "Betapose-results.json")), g, left, pose_tol=1e-5)
+    # ---- (ii) the engine's tail in one batch: heat-map decode -> bp_pose_pnp (pose-NMS n=1, selection, PnP) -> records
+    n = len(names)
+    dev = torch.device("cuda")
+    hm = torch.from_numpy(np.concatenate([g[f"hm{i}"].astype(np.float32) for i in range(n)])).to(dev)
+    pt1 = torch.from_numpy(np.stack([g[f"pt1_{i}"] for i in range(n)])).to(dev)
+    pt2 = torch.from_numpy(np.stack([g[f"pt2_{i}"] for i in range(n)])).to(dev)
+    box = torch.from_numpy(np.stack([g[f"box{i}"] for i in range(n)])).to(dev)
+    det = torch.tensor([float(g[f"score{i}"]) for i in range(n)], device=dev)
+    dec = stages.heatmap_decode(hm, pt1, pt2, layout="nchw")
+    pose = stages.pose_pnp(dec["preds_img"], dec["maxval"].reshape(n, 50).contiguous(), det, torch.from_numpy(kp3d).to(dev), left_number=left)
+    rec = stages.records_to_numpy(stages.pack_records(0, box, det, pose))
+    assert rec["status"].tolist() == [1, 1, 0, 1]
+    res = [compat.result_from_record(rec[i], os.path.join("/data/rgb", names[i])) for i in range(n)]
+    compat.write_json(res, str(tmp_path / "engine"))
+    check_a12_json(json.load(open(tmp_path / "engine" / "Betapose-results.json")), g, left, pose_tol=1e-5)

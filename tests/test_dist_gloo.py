@@ -33,7 +33,7 @@ def _worker(rank, world, port, n_total, q):
     rec["image_index"] = np.arange(lo, hi)
     rec["status"] = 1
     rec["pad"][:, 0] = rank + 1
-    local = torch.from_numpy(rec.view(np.uint8).reshape(hi - lo, _lib.RECORD_BYTES).copy())
+    local = D.records_to_bytes(rec)  # also for an empty shard (n_total < world)
     allrec = D.gather_records(local, n_total)
     got = allrec.numpy().view(rec.dtype).reshape(-1)
     ok = (got["image_index"].tolist() == list(range(n_total))) and bool((got["status"] == 1).all())
@@ -44,7 +44,7 @@ def _worker(rank, world, port, n_total, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total", [8, 7])
+@pytest.mark.parametrize("n_total", [8, 7, 1])
 def test_gather_records_world2(n_total):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -396,3 +396,197 @@ def test_sixd_scoring_loop_and_cli(tmp_path, capsys):
     assert (out_dir / "Betapose-results.json").exists()
     for line in ("Mean add accuracy for seq 05 is:", "2d reprojection accuracy for seq 05 is:", "Mean IoU for seq 05 is:"):
         assert line in printed
+
+
+def _stagewise_oracle_check(e, frames, sample, slot_of=None, fp32_nets=None):
+    """Stage-wise parity of an engine run on `frames` for the images in `sample` (indices into the engine's buffers):
+    every stage's output against the oracle fed with the engine's own upstream tensors."""
+    n = len(frames)
+    slot_of = slot_of if slot_of is not None else [0] * n
+    box_g = e.box.cpu().numpy()
+    pi_g, mv_g, sc_g = e.preds_img.cpu().numpy(), e.maxval.cpu().numpy(), e.det_score.cpu().numpy()
+    for b in sample:
+        s = slot_of[b]
+        # a1 (each slot's detector input buffer holds its own group, rows relative to the group start)
+        g0 = min(i for i in range(n) if slot_of[i] == s) if e.concurrent_slots or e.n_slots == 1 else None
+        if g0 is not None:
+            yin = e.yolo[s].input(e.B)[b - g0].float().cpu().numpy()
+            assert np.array_equal(yin[:, :, :3], R.pil_resize_bicubic(frames[b], 416, 416))
+            heads = [e.yolo[s].tensor(h["tensor"], e.B)[b - g0:b - g0 + 1].permute(0, 3, 1, 2).contiguous().cpu().numpy() for h in e.heads[s]]
+            dets, rows = R.write_results(R.yolo_decode(heads), 0.01)
+            assert int(e.row[b]) == int(rows[0])
+            boxes, _ = R.rescale_boxes(dets, 640, 480)
+            np.testing.assert_allclose(box_g[b], boxes[0], rtol=2e-6, atol=3e-5)
+        pt1, pt2 = R.expand_box(box_g[b], 640, 480)
+        assert np.array_equal(e.pt1[b].cpu().numpy(), pt1) and np.array_equal(e.pt2[b].cpu().numpy(), pt2)
+        if g0 is not None:
+            kin = e.kpd[s].input(e.B)[b - g0].float().cpu().numpy()
+            np.testing.assert_allclose(kin[:, :, :3].transpose(2, 0, 1), R.crop_box(frames[b], pt1, pt2), atol=5e-4)
+            hm = e.kpd[s].tensor(e.hm_id[s], e.B)[b - g0:b - g0 + 1].permute(0, 3, 1, 2).contiguous().cpu().numpy()
+            ph, pi, mv, idx, _ = R.get_prediction(hm, pt1[None], pt2[None])
+            assert np.array_equal(e.hm_idx[b].cpu().numpy(), idx[0].astype(np.int32))
+            assert np.array_equal(mv_g[b], mv[0, :, 0])
+            np.testing.assert_allclose(pi_g[b], pi[0], atol=6.2e-5)
+            if fp32_nets is not None:  # the fp16 networks themselves against the fp32 oracle nets on the same inputs
+                fp32_nets(s, b, yin, kin, hm)
+        ref = R.pose_nms_single(sc_g[b], pi_g[b], mv_g[b])
+        st = int(e.status[b])
+        assert (ref is None) == (st == 0)
+        if ref is not None:
+            assert np.array_equal(e.keypoints[b].cpu().numpy(), ref[0])
+            keep = R.select_keypoints(ref[1], e.left_number)
+            assert np.array_equal(np.nonzero(e.selected[b].cpu().numpy())[0], keep)
+            sol = opnp.solve_pnp(e.kp3d[s].cpu().numpy()[keep], ref[0][keep], e.cam_K, mode=0, thr=e.reproj_thr, n_hyp=e.n_hyp, seed=e.seed)
+            # junk key-points of random networks: the consensus problem is ill-posed, so only well-posed frames (a clear
+            # consensus in both) are compared on R, t; status must agree whenever the oracle is confident either way
+            if sol["ok"] and st == 1 and np.array_equal(e.inlier[b].cpu().numpy().astype(bool)[keep], sol["inliers"]):
+                np.testing.assert_allclose(e.R[b].cpu().numpy().reshape(3, 3), sol["R"], atol=1e-6)
+                np.testing.assert_allclose(e.t[b].cpu().numpy(), sol["t"], atol=1e-6)
+
+
+def test_engine_batch64_stagewise_oracle_sample(yolo_blocks, yolo_stream, kpd_sd, kp_model):
+    """BASELINE.json configs[2] as benchmarked: batch 64, CUDA-graph replay -- stage by stage against the oracle on four
+    sampled frames (the CPU port does ~9 images/s, four frames are seconds), including the fp16 networks (CTA-pair and
+    256 / 512-pixel-tile plans) against the fp32 oracle networks on the engine's own inputs."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine
+    from oracle import nets as onets
+
+    e = BetaposeEngine(64, yolo_stream, kpd_sd, kp_model, seed=5)
+    frames = synth.synth_frames(64, seed=77)
+    rec = e.run(frames, graph=True)
+    rec2 = e.run(frames, graph=True)   # replay
+    torch.cuda.synchronize()
+    assert rec.tobytes() == rec2.tobytes()
+    yparams, _ = onets.split_darknet_weights(yolo_blocks, yolo_stream)
+
+    def fp32_nets(s, b, yin, kin, hm):
+        with torch.no_grad():
+            ref_heads = onets.darknet_forward(yolo_blocks, yparams, torch.from_numpy(yin[None, :, :, :3]).permute(0, 3, 1, 2) / 255.0)
+            ref_hm = onets.fastpose_forward(kpd_sd, torch.from_numpy(kin[None, :, :, :3]).permute(0, 3, 1, 2))
+        for h, r in zip(e.heads[s], ref_heads):
+            g = e.yolo[s].tensor(h["tensor"], 64)[b:b + 1].permute(0, 3, 1, 2).cpu()
+            scale = r.abs().max().item()
+            assert (g - r).abs().max().item() <= 3e-2 * scale and (g - r).abs().mean().item() <= 3e-3 * scale
+        scale = ref_hm.abs().max().item()
+        d = (torch.from_numpy(hm) - ref_hm).abs()
+        assert d.max().item() <= 3e-2 * scale and d.mean().item() <= 3e-3 * scale
+
+    _stagewise_oracle_check(e, frames, (0, 21, 42, 63), fp32_nets=fp32_nets)
+    assert (rec["status"] == 1).sum() >= 32
+    del e
+    torch.cuda.empty_cache()
+
+
+def test_graph_replay_survives_scratch_growth(yolo_stream, kpd_sd, kp_model, frames8):
+    """Kernel scratch (heat-map slices, PnP hypothesis rows) is per stream and grow-only: a graph captured at n = 2 must
+    still replay correctly after a later, larger batch (n = 8) and a second engine on the same device made the scratch grow
+    -- the old blocks may not be freed while graphs point into them."""
+    from betapose_b200.engine import BetaposeEngine
+
+    e = BetaposeEngine(8, yolo_stream, kpd_sd, kp_model, seed=5)
+    want2 = e.run(frames8[:2]).copy()                # eager reference, n = 2
+    want8 = e.run(frames8).copy()
+    a = e.run(frames8[:2], graph=True).copy()        # captures n = 2
+    b = e.run(frames8, graph=True).copy()            # captures n = 8: scratch grows
+    big = BetaposeEngine(16, yolo_stream, kpd_sd, kp_model, seed=5)  # second engine, larger batch, same native engine
+    big.run(np.concatenate([frames8, frames8]), graph=True)
+    c = e.run(frames8[:2], graph=True).copy()        # replays the n = 2 graph
+    d = e.run(frames8, graph=True).copy()
+    torch.cuda.synchronize()
+    assert a.tobytes() == want2.tobytes() == c.tobytes()
+    assert b.tobytes() == want8.tobytes() == d.tobytes()
+    del e, big
+    torch.cuda.empty_cache()
+
+
+def test_model_idx_follows_the_grouping(yolo_stream, kpd_sd, kp_model):
+    """A plain run after a mixed-object run must solve every frame against slot 0's key-point model again."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine
+
+    kp2 = synth.synth_kp_model(2, 50)
+    frames = synth.synth_frames(4, seed=9)
+    e = BetaposeEngine(4, [yolo_stream, synth.variant_yolo_weights(yolo_stream, 1)], [kpd_sd, synth.variant_kpd_state_dict(kpd_sd, 1)],
+                       np.stack([kp_model, kp2]), seed=5)
+    single = BetaposeEngine(4, yolo_stream, kpd_sd, kp_model, seed=5)
+    want = single.run(frames).copy()
+    e.run(frames, obj_slots=[1, 0, 1, 1])
+    got = e.run(frames).copy()
+    assert got.tobytes() == want.tobytes()
+    del e, single
+    torch.cuda.empty_cache()
+
+
+LINEMOD_IDS = (1, 2, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14, 15)
+
+
+def linemod13_kp_models():
+    """[13,50,3] key-point models from the shipped PLYs (tests/golden/kp_models.npz, metres); object 10 has 17 points and
+    is padded by cycling (model3d.load_kp_model(short='cycle'))."""
+    import os
+
+    from betapose_b200 import model3d
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kp_models.npz"))
+    out = []
+    for oid in LINEMOD_IDS:
+        v = g[f"obj_{oid}"]
+        assert v.shape[0] == (17 if oid == 10 else 50)
+        out.append(v if v.shape[0] == 50 else model3d.pad_by_cycling(v, 50))
+    return np.stack(out)
+
+
+def test_configs3_thirteen_objects_batch32(yolo_blocks, yolo_stream, kpd_sd):
+    """BASELINE.json configs[3] on one rank: all 13 LineMod objects mixed, 256 / 8 = 32 frames per GPU, object drawn
+    uniformly per frame, one detector + key-point network + shipped key-point model per object (object 10:
+    17 points padded by cycling).  Three sampled objects (among them object 10) are checked against single-object engines
+    bit for bit, and sampled frames stage by stage against the oracle."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine
+
+    kps = linemod13_kp_models()
+    ys = [synth.variant_yolo_weights(yolo_stream, v, yolo_blocks) for v in range(13)]
+    ks = [synth.variant_kpd_state_dict(kpd_sd, v) for v in range(13)]
+    B = 32
+    rng = np.random.default_rng(256)
+    slots = rng.integers(0, 13, B)
+    slots[:3] = [7, 0, 12]  # make sure object 10 (slot 7) and the two ends are present
+    frames = synth.synth_frames(B, seed=91)
+    e = BetaposeEngine(B, ys, ks, kps, seed=5)
+    assert e.concurrent_slots
+    got = e.run(frames, obj_slots=slots, graph=True).copy()
+    again = e.run(frames, obj_slots=slots, graph=True).copy()
+    assert got.tobytes() == again.tobytes() and got["image_index"].tolist() == list(range(B))
+    order = np.argsort(slots, kind="stable")            # the engine's buffers hold the batch grouped by slot
+    slot_sorted = slots[order].tolist()
+    check = [j for j in range(B) if slot_sorted[j] in (7, 0, 12)][:6]
+    _stagewise_oracle_check(e, frames[order], check, slot_of=slot_sorted)
+    del e
+    torch.cuda.empty_cache()
+    for s in (7, 0, 12):
+        single = BetaposeEngine(B, ys[s], ks[s], kps[s], seed=5)
+        idx = np.nonzero(slots == s)[0]
+        ref = single.run(frames[idx]).copy()
+        for f in ref.dtype.names:
+            if f != "image_index":
+                assert np.array_equal(got[f][idx], ref[f]), (s, f)
+        del single
+        torch.cuda.empty_cache()
+
+
+def test_configs4_occlusion_batch16(yolo_stream, kpd_sd, kp_model):
+    """BASELINE.json configs[4] on one rank: the Occlusion-LineMod variant (occlusion_betapose_evaluate.py:139:
+    DataWriter(cam_K, args.left_keypoints, ...), default 10), 128 / 8 = 16 frames per GPU; stage by stage against the
+    oracle, selection = the 10 best-scored key-points."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine
+
+    e = BetaposeEngine(16, yolo_stream, kpd_sd, kp_model, left_number=10, seed=5)
+    frames = synth.synth_frames(16, seed=128)
+    rec = e.run(frames, graph=True).copy()
+    _stagewise_oracle_check(e, frames, range(16))
+    live = rec["status"] != 0
+    assert live.sum() >= 8 and (e.selected.cpu().numpy()[live].sum(1) == 10).all()
+    del e
+    torch.cuda.empty_cache()

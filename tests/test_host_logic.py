@@ -98,10 +98,15 @@ def test_write_json_format(tmp_path):
     rec["R"][0] = np.arange(9)
     rec["t"][0] = [0.1, 0.2, 0.9]
     rec["proposal_score"][0] = 2.5
+    rec["R"][2] = np.arange(9) * 0.5   # status -1: the solver's last estimate (a pose-NMS survivor whose PnP found no consensus)
+    rec["t"][2] = [0.0, 0.1, 0.8]
     res = [compat.result_from_record(rec[i], f"/data/rgb/{i:04d}.png") for i in range(3)]
     out = compat.write_json(res, str(tmp_path))
     on_disk = json.load(open(tmp_path / "Betapose-results.json"))
-    assert on_disk == out and len(out) == 1  # rejected / failed frames emit no entry (pPose_nms.py:296)
+    # a rejected frame emits no entry (pPose_nms.py:296); a survivor whose PnP failed still does (dataloader.py:715-727
+    # appends bbox, key-points, cam_R and cam_t for every survivor), so it stays in the IoU / ADD statistics as a miss
+    assert on_disk == out and [e["image_id"] for e in out] == ["0000.png", "0002.png"]
+    assert out[1]["cam_t"] == [0.0, 0.1, 0.8] and out[1]["cam_R"] == [0.5 * k for k in range(9)] and len(out[1]["keypoints"]) == 150
     e = out[0]
     assert e["image_id"] == "0000.png" and e["cam_R"] == list(map(float, range(9))) and e["cam_t"] == [0.1, 0.2, 0.9]
     assert e["keypoints"][:6] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0] and len(e["keypoints"]) == 150 and e["score"] == 2.5

@@ -267,3 +267,79 @@ def test_net_batch_smaller_than_max(yolo_blocks):
         t = n.tensor(h["tensor"], 4)
         assert torch.equal(t[:3], f[:3])
         assert float(t[3].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ batch 64 (BASELINE configs[2])
+SAMPLE64 = (0, 21, 42, 63)  # first tile, images that straddle 128 / 256 / 512-pixel tile borders in the small layers, last tile
+
+
+def _plan_marks(n):
+    descs = [n.op_desc(i)[0] for i in range(n.num_ops)]
+    return {m for d in descs for m in ("cg2", "mt2", "mt4") if f" {m}" in d}, descs
+
+
+def test_yolov3_batch64_plans_vs_oracle(yolo_blocks, yolo_stream):
+    """The tile plans depend on M = B*P*Q: at batch 64 the detector runs CTA pairs (cta_group::2) on its 256-wide 3x3
+    layers and 256 / 512-pixel tiles on the stem and the Cin = 32 layers -- none of which a batch-2 test launches.  This is
+    the benchmarked configuration against the fp32 oracle, on 4 sampled images, with test_yolov3_full_vs_oracle's
+    tolerances."""
+    from betapose_b200 import stages, synth
+    from oracle import restate as R
+
+    B = 64
+    fr = torch.from_numpy(synth.synth_frames(B, seed=64)).cuda()
+    buf, _ = stages.resize_bicubic(fr, 416, 416)
+    x = stages.net_input_pixels(buf).cpu().numpy().astype(np.uint8)
+    n, got = _run_yolo(yolo_blocks, yolo_stream, x, 416)
+    marks, descs = _plan_marks(n)
+    assert {"cg2", "mt2", "mt4"} <= marks, (marks, descs)  # the plans the benchmark runs are the ones checked here
+    params, _ = onets.split_darknet_weights(yolo_blocks, yolo_stream)
+    xs = torch.from_numpy(x[list(SAMPLE64)]).permute(0, 3, 1, 2).float() / 255.0
+    with torch.no_grad():
+        ref = onets.darknet_forward(yolo_blocks, params, xs)
+    for g, r in zip(got, ref):
+        g = g[list(SAMPLE64)]
+        scale = r.abs().max().item()
+        err = (g - r).abs()
+        assert err.max().item() <= 3e-2 * scale, (err.max().item(), scale)
+        assert err.mean().item() <= 3e-3 * scale
+    pred_g = R.yolo_decode([g[list(SAMPLE64)].numpy() for g in got])
+    pred_r = R.yolo_decode([r.numpy() for r in ref])
+    _, rows_g = R.write_results(pred_g)
+    _, rows_r = R.write_results(pred_r)
+    for b in range(len(SAMPLE64)):
+        if rows_g[b] != rows_r[b]:
+            assert abs(pred_r[b, rows_g[b], 4] - pred_r[b, rows_r[b], 4]) < 5e-3
+    del n
+    torch.cuda.empty_cache()
+
+
+def test_fastpose_batch64_plans_vs_oracle(kpd_sd):
+    """FastPose at batch 64 (CTA pairs on the 256-wide 3x3 layers of the 20x16 stage and the DUCs, 256-pixel tiles on the
+    stem) against the fp32 oracle on 4 sampled crops."""
+    from betapose_b200 import _lib, net as bnet, stages, synth
+
+    B = 64
+    fr = torch.from_numpy(synth.synth_frames(B, seed=65)).cuda()
+    rng = np.random.default_rng(3)
+    x1, y1 = rng.uniform(0, 300, B), rng.uniform(0, 200, B)
+    box = torch.from_numpy(np.stack([x1, y1, x1 + rng.uniform(80, 300, B), y1 + rng.uniform(80, 260, B)], 1).astype(np.float32)).cuda()
+    crop = stages.crop_resize(fr, box, torch.arange(B, dtype=torch.int32, device="cuda"), want_f32=True)
+    n = bnet.Net(B, 320, 256, _lib.IN_F16)
+    hm_id = bnet.build_fastpose(n, kpd_sd, 50)
+    n.input(B).copy_(stages.net_input_pixels(crop["net"]))
+    n.forward(B)
+    torch.cuda.synchronize()
+    marks, descs = _plan_marks(n)
+    assert {"cg2", "mt2"} <= marks, (marks, descs)
+    got = n.tensor(hm_id, B).permute(0, 3, 1, 2).contiguous().cpu()[list(SAMPLE64)]
+    with torch.no_grad():
+        ref = onets.fastpose_forward(kpd_sd, crop["f32"][list(SAMPLE64)].cpu())
+    scale = ref.abs().max().item()
+    err = (got - ref).abs()
+    assert err.max().item() <= 3e-2 * scale, (err.max().item(), scale)
+    assert err.mean().item() <= 3e-3 * scale
+    ig, ir = got.reshape(4, 50, -1).argmax(2), ref.reshape(4, 50, -1).argmax(2)
+    assert (ig == ir).float().mean().item() >= 0.9
+    del n
+    torch.cuda.empty_cache()

@@ -211,3 +211,63 @@ def test_box_nms_oracle_matches_reference_branch():
         assert counts.sum() == len(want) and np.array_equal(np.bincount(want[:, 0].astype(int), minlength=len(pred)), counts)
         for d, r in zip(dets, rows):  # rows index the prediction tensor
             assert pred[int(d[0]), r, 4] == d[5]
+
+
+# ------------------------------------------------------------------------------------------------ a12
+def _a12_oracle_results(g, left):
+    """The reference's DataWriter assembly (dataloader.py:704-730) restated with the oracle stages."""
+    kp3d = g["kp3d"]
+    out = []
+    for i, name in enumerate(g["names"]):
+        hm = g[f"hm{i}"].astype(np.float32)
+        _, pi, mv, _, _ = R.get_prediction(hm, g[f"pt1_{i}"][None], g[f"pt2_{i}"][None])
+        ref = R.pose_nms_single(float(g[f"score{i}"]), pi[0], mv[0])
+        if ref is None:
+            out.append({"imgname": str(name), "result": [], "cam_R": [], "cam_t": []})
+            continue
+        kp2d, sc, prop = ref
+        keep = R.select_keypoints(sc, left)
+        sol = opnp.solve_pnp(kp3d[keep], kp2d[keep], R.CAM_K, mode=opnp.MODE_RANSAC)
+        assert sol["ok"]
+        out.append({"imgname": str(name), "result": [{"bbox": g[f"box{i}"], "keypoints": kp2d, "kp_score": sc.reshape(-1, 1), "proposal_score": prop}],
+                    "cam_R": sol["R"], "cam_t": sol["t"].reshape(3, 1)})
+    return out
+
+
+def check_a12_json(js, g, left, pose_tol):
+    """`js`: parsed Betapose-results.json produced from the golden inputs; compared entry by entry with the file the
+    reference's own write_json wrote (tests/golden/make_golden.py: make_a12_golden)."""
+    import json
+
+    want = json.loads(str(g[f"json_left{left}"]))
+    assert [e["image_id"] for e in js] == [e["image_id"] for e in want]       # rejected / undetected frames emit nothing
+    for e, w in zip(js, want):
+        assert set(e) == set(w) == {"image_id", "cam_R", "cam_t", "keypoints", "score"}
+        assert e["keypoints"] == w["keypoints"]                                # 50 x (x, y, score): exact fp32 values
+        assert abs(e["score"] - w["score"]) <= 1e-6 * abs(w["score"])
+        # the reference's active solver is cv2.solvePnP ITERATIVE; tolerance of record on R, t: 1e-3 (BASELINE.json north_star)
+        assert np.abs(np.array(e["cam_R"]) - np.array(w["cam_R"])).max() < pose_tol
+        assert np.abs(np.array(e["cam_t"]) - np.array(w["cam_t"])).max() < pose_tol
+
+
+@pytest.mark.parametrize("left", [50, 10])
+def test_a12_result_assembly_and_write_json_vs_reference(tmp_path, left):
+    """a12: oracle stages + the product's write_json (host code, no GPU) against the reference's DataWriter + write_json
+    run as written on the same heat-maps (planted poses, a rejected frame, a frame without a detection)."""
+    import json
+
+    from betapose_b200 import compat
+
+    g = load("a12_golden.npz")
+    res = _a12_oracle_results(g, left)
+    for i, r in enumerate(res):  # stage-level: the dict DataWriter appended
+        assert len(r["result"]) == int(g[f"left{left}_n{i}"])
+        if r["result"]:
+            h = r["result"][0]
+            assert np.array_equal(h["keypoints"], g[f"left{left}_kp{i}"]) and np.array_equal(h["kp_score"], g[f"left{left}_sc{i}"])
+            np.testing.assert_allclose(h["proposal_score"], g[f"left{left}_prop{i}"].reshape(()), rtol=1e-6)
+            assert np.array_equal(h["bbox"], g[f"left{left}_bbox{i}"])
+            np.testing.assert_allclose(r["cam_R"], g[f"left{left}_R{i}"], atol=1e-6)
+            np.testing.assert_allclose(r["cam_t"], g[f"left{left}_t{i}"], atol=1e-6)
+    compat.write_json(res, str(tmp_path))
+    check_a12_json(json.load(open(tmp_path / "Betapose-results.json")), g, left, pose_tol=1e-6)
