@@ -21,7 +21,7 @@ EXPORTS = (
     "bp_yolo_decode_argmax", "bp_write_results", "bp_crop_resize", "bp_heatmap_decode", "bp_pose_pnp", "bp_pack_records",
     "bp_score_poses", "bp_pose_nms", "bp_ingest_create", "bp_ingest_destroy", "bp_ingest_num_threads", "bp_png_info",
     "bp_png_decode", "bp_ingest_submit", "bp_ingest_wait", "bp_zlib_inflate",
-    "bp_write_results_nms", "bp_pack_conv_weights", "bp_frame_decode",
+    "bp_write_results_nms", "bp_pack_conv_weights", "bp_frame_decode", "bp_net_set_share", "bp_net_set_op_config", "bp_net_op_config",
 )
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_IO = -1, -2, -3, -4
 ORDER_RGB, ORDER_BGR = 0, 1  # frame ingest channel orders
@@ -98,6 +98,9 @@ def lib() -> C.CDLL:
     L.bp_net_flops_per_image.restype = d
     L.bp_net_forward.argtypes = [vp, i, vp]
     L.bp_net_forward_range.argtypes = [vp, i, i, i, vp]
+    L.bp_net_set_share.argtypes = [vp, i]
+    L.bp_net_set_op_config.argtypes = [vp, i, i, i, i, i]
+    L.bp_net_op_config.argtypes = [vp, i, i, C.POINTER(C.c_int)]
     L.bp_net_num_ops.argtypes = [vp]
     L.bp_net_op_desc.argtypes = [vp, i, C.c_char_p, i, C.POINTER(d), C.POINTER(d)]
     L.bp_resize_bicubic.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp]

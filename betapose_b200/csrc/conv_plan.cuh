@@ -2,6 +2,7 @@
 // TMA descriptors once (buffers are owned by the engine, so addresses are stable) and replays the launch.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "conv_tcgen05.cuh"
@@ -31,6 +32,7 @@ struct ConvDesc {
   int force_mt = 0;       // 0 = heuristic, 1 = 128-pixel tiles, 2 = 256-pixel tiles (narrow layers)
   int force_stages = 0;   // kept for the harness; the stage count follows from the tile configuration
   int num_sms = 148;
+  bool pdl = true;        // launch with programmatic stream serialisation (off for nets that share the GPU, bp_net_set_share)
   double real_k = 0;      // reduction length that counts as work (0 = R*S*C); the stems pad K with zero weights
 };
 
@@ -41,6 +43,7 @@ struct ConvPlan {
   alignas(64) CUtensorMap tmRes;  // valid when args.tma_store && residual
   ConvArgs args;
   int block_n = 0, block_k = 0, stages = 0, grid = 0, cg = 1, mt = 1;
+  bool pdl = true;
   int P = 0, Q = 0;
   double flops = 0;
 };
@@ -69,9 +72,12 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   int na = 0;
-  at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[na].val.programmaticStreamSerializationAllowed = 1;
-  ++na;
+  static const bool no_pdl = getenv("BP_NO_PDL") != nullptr;  // experiment switch
+  if (!no_pdl && pl.pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if constexpr (CG == 2) {
     at[na].id = cudaLaunchAttributeClusterDimension;
     at[na].val.clusterDim.x = 2;
@@ -82,6 +88,16 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   cfg.attrs = at;
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB, MT>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+}
+
+// is there a kernel instantiation for this plan?  (mirrors the dispatch in conv_plan_launch)
+inline bool conv_plan_supported(const ConvPlan& pl) {
+  const int bn = pl.block_n, bk = pl.block_k;
+  if (pl.cg == 2) return bk == 64 && (bn == 256 || bn == 128);
+  if (pl.mt == 4) return (bn == 64 && bk == 32) || (bn == 32 && bk == 32) || (bn == 32 && bk == 64);
+  if (pl.mt == 2) return (bk == 64 && (bn == 128 || bn == 64 || bn == 32)) || (bk == 32 && (bn == 64 || bn == 32));
+  if (bk == 64) return (bn == 256 && pl.stages == 3) || (bn == 128 && pl.stages == 5) || (bn == 64 && pl.stages == 6) || (bn == 32 && pl.stages == 9);
+  return (bn == 64 && pl.stages == 13) || (bn == 32 && pl.stages == 16);
 }
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
@@ -193,6 +209,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   const int m_tiles_cta = (M + 128 * mt - 1) / (128 * mt);  // tiles as the kernel walks them
 
   pl->block_n = bn;
+  pl->pdl = d.pdl;
   pl->block_k = block_k;
   pl->stages = st;
   pl->cg = cg;

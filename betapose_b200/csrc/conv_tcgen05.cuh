@@ -132,26 +132,35 @@ __device__ __forceinline__ void epi_math_store(const uint32_t* a, const float* b
     uint8_t* slot = tile + swz_off<ROW_BYTES>(row_l, unit0 + j);
     uint4 pk;
     __half2* h = reinterpret_cast<__half2*>(&pk);
-    if constexpr (ACT == ACT_SIGMOID) {
+    if constexpr (RESMODE != RES_NONE) {
+      // residual layers: add in fp32 and round ONCE (the residual chains are 23 / 33 blocks deep; rounding the conv result
+      // to fp16 before the add would round every block twice)
+      const uint4 rv = *reinterpret_cast<const uint4*>(slot);
+      const __half2* r = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 rf = __half22float2(r[e]);
+        float x0 = v[2 * e], x1 = v[2 * e + 1];
+        if constexpr (RESMODE == RES_BEFORE_ACT) { x0 += rf.x; x1 += rf.y; }
+        if constexpr (ACT == ACT_LEAKY) { x0 = fmaxf(x0, 0.1f * x0); x1 = fmaxf(x1, 0.1f * x1); }
+        if constexpr (ACT == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        if constexpr (ACT == ACT_SIGMOID) { x0 = 1.f / (1.f + __expf(-x0)); x1 = 1.f / (1.f + __expf(-x1)); }
+        if constexpr (RESMODE == RES_AFTER_ACT) { x0 += rf.x; x1 += rf.y; }
+        h[e] = __floats2half2_rn(x0, x1);
+      }
+    } else if constexpr (ACT == ACT_SIGMOID) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         h[e] = __floats2half2_rn(1.f / (1.f + __expf(-v[2 * e])), 1.f / (1.f + __expf(-v[2 * e + 1])));
     } else {
+      const __half2 zero = __float2half2_rn(0.f), slope = __float2half2_rn(0.1f);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-    }
-    uint4 rv = make_uint4(0, 0, 0, 0);
-    if constexpr (RESMODE != RES_NONE) rv = *reinterpret_cast<const uint4*>(slot);
-    const __half2* r = reinterpret_cast<const __half2*>(&rv);
-    const __half2 zero = __float2half2_rn(0.f), slope = __float2half2_rn(0.1f);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __half2 x = h[e];
-      if constexpr (RESMODE == RES_BEFORE_ACT) x = __hadd2(x, r[e]);
-      if constexpr (ACT == ACT_LEAKY) x = __hmax2(x, __hmul2(x, slope));  // slope < 1: max(x, 0.1 x)
-      if constexpr (ACT == ACT_RELU) x = __hmax2(x, zero);
-      if constexpr (RESMODE == RES_AFTER_ACT) x = __hadd2(x, r[e]);
-      h[e] = x;
+      for (int e = 0; e < 4; ++e) {
+        __half2 x = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        if constexpr (ACT == ACT_LEAKY) x = __hmax2(x, __hmul2(x, slope));  // slope < 1: max(x, 0.1 x)
+        if constexpr (ACT == ACT_RELU) x = __hmax2(x, zero);
+        h[e] = x;
+      }
     }
     *reinterpret_cast<uint4*>(slot) = pk;
   }

@@ -36,6 +36,8 @@ struct Op {
   ConvDesc cdesc;
   bool stem = false;
   std::map<int, ConvPlan> plans;
+  struct TileCfg { int block_n, cg, mt; };
+  std::map<int, TileCfg> tuned;  // per batch size: measured-best tile configuration (bp_net_set_op_config)
   int pq = 0;     // output pixels per image (conv) for batch scaling
   int a = -1, b = -1, c = -1, dst = -1;  // tensor ids for aux ops
   float* scratch = nullptr;              // OP_AVGPOOL: [max_batch][kAvgSplitMax][C] partial sums
@@ -58,6 +60,7 @@ struct bp_net {
   std::vector<size_t> act_sizes;
   size_t act_cursor = 0;
   double flops = 0;
+  int share_batch = 0;  // > 0: runs concurrently with other nets, see bp_net_set_share
 };
 
 static void* net_alloc_weights(bp_net* n, size_t bytes) {
@@ -431,6 +434,71 @@ int bp_net_tensor_info(bp_net* n, int tensor, int* dims, void** ptr) {
 }
 
 int bp_net_num_ops(bp_net* n) { return n ? (int)n->ops.size() : 0; }
+
+int bp_net_set_op_config(bp_net* n, int op, int batch, int block_n, int cg, int mt) {
+  if (!n || op < 0 || op >= (int)n->ops.size() || batch <= 0 || batch > n->max_batch) return bp_fail(BP_ERR_INVALID, "bp_net_set_op_config: op / batch");
+  Op& o = n->ops[op];
+  if (o.kind != OP_CONV) return bp_fail(BP_ERR_INVALID, "bp_net_set_op_config: not a convolution");
+  o.plans.erase(batch);
+  if (block_n == 0 && cg == 0 && mt == 0) {
+    o.tuned.erase(batch);
+    return BP_OK;
+  }
+  o.tuned[batch] = Op::TileCfg{block_n, cg, mt};
+  // build now so that an unsupported combination is reported here, not at the first launch
+  ConvDesc d = o.cdesc;
+  d.N = batch;
+  d.force_block_n = block_n;
+  d.force_cg = cg;
+  d.force_mt = mt;
+  if (n->share_batch > 0) return BP_OK;  // shared nets re-plan with their SM budget at launch
+  std::string err;
+  ConvPlan pl;
+  bool ok = conv_plan_build(n->eng->tmap, &pl, d, &err);
+  if (ok && ((block_n && pl.block_n != block_n) || (cg && pl.cg != cg) || (mt && pl.mt != mt))) {
+    ok = false;
+    err = "the planner does not support this combination for this layer";
+  }
+  if (ok && !conv_plan_supported(pl)) {
+    ok = false;
+    err = "no kernel instantiation for this tile configuration";
+  }
+  if (!ok) {
+    o.tuned.erase(batch);
+    return bp_fail(BP_ERR_UNSUPPORTED, ("bp_net_set_op_config: " + err).c_str());
+  }
+  o.plans[batch] = pl;
+  return BP_OK;
+}
+
+int bp_net_op_config(bp_net* n, int op, int batch, int* cfg) {
+  if (!n || op < 0 || op >= (int)n->ops.size() || !cfg) return bp_fail(BP_ERR_INVALID, "bp_net_op_config: op");
+  Op& o = n->ops[op];
+  cfg[0] = cfg[1] = cfg[2] = cfg[3] = cfg[4] = 0;
+  if (o.kind != OP_CONV) return BP_OK;
+  auto it = o.plans.find(batch);
+  if (it == o.plans.end()) {
+    ConvDesc d = o.cdesc;
+    d.N = batch;
+    auto tu = o.tuned.find(batch);
+    if (tu != o.tuned.end()) { d.force_block_n = tu->second.block_n; d.force_cg = tu->second.cg; d.force_mt = tu->second.mt; }
+    std::string err;
+    ConvPlan pl;
+    if (!conv_plan_build(n->eng->tmap, &pl, d, &err)) return bp_fail(BP_ERR_CUDA, err.c_str());
+    it = o.plans.emplace(batch, pl).first;
+  }
+  cfg[0] = it->second.block_n; cfg[1] = it->second.cg; cfg[2] = it->second.mt; cfg[3] = it->second.block_k; cfg[4] = it->second.stages;
+  return BP_OK;
+}
+
+int bp_net_set_share(bp_net* n, int share_batch) {
+  if (!n || share_batch < 0) return bp_fail(BP_ERR_INVALID, "bp_net_set_share: bad arguments");
+  if (n->share_batch != share_batch) {
+    n->share_batch = share_batch;
+    for (Op& op : n->ops) op.plans.clear();  // plans depend on the SM budget
+  }
+  return BP_OK;
+}
 int bp_net_num_launches(bp_net* n) { return n ? (int)n->ops.size() : 0; }
 double bp_net_flops_per_image(bp_net* n) { return n ? n->flops : 0.0; }
 
@@ -459,6 +527,19 @@ int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream
           // first use of this batch size: tile configuration + TMA descriptors for exactly `batch` images
           ConvDesc d = mop.cdesc;
           d.N = batch;
+          auto tu = mop.tuned.find(batch);
+          if (tu != mop.tuned.end()) {
+            d.force_block_n = tu->second.block_n;
+            d.force_cg = tu->second.cg;
+            d.force_mt = tu->second.mt;
+          }
+          if (n->share_batch > 0) {
+            // this object's share of the machine, in proportion to its frames (even, >= 2: CTA pairs stay possible)
+            int budget = (int)(((long)n->eng->num_sms * batch + n->share_batch - 1) / n->share_batch);
+            budget = std::max(2, std::min(n->eng->num_sms, (budget + 1) & ~1));
+            d.num_sms = budget;
+            d.pdl = false;
+          }
           std::string err;
           ConvPlan& np = mop.plans[batch];
           if (!conv_plan_build(n->eng->tmap, &np, d, &err)) {

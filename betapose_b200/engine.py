@@ -81,6 +81,18 @@ class BetaposeEngine:
                 if getattr(k, "packed", None) is not None:
                     _net.packed_exhausted(k.packed)
                 self.kpd.append(k)
+            # measured tile plans for this batch size, where a table exists (betapose_b200/tune.py)
+            from . import tune as _tune
+
+            tab = None if self.concurrent_slots else _tune.load(self.B)
+            self.tuned_ops = 0
+            if tab:
+                for net, key in [(n, "yolo") for n in self.yolo] + [(n, "kpd") for n in self.kpd]:
+                    self.tuned_ops += _tune.apply(net, self.B, tab.get(key, {}))
+            if self.concurrent_slots:
+                # the slots of a mixed batch split the machine in proportion to their frame counts (bp_net_set_share)
+                for net in self.yolo + self.kpd:
+                    net.set_share(self.B)
             kp3d = np.asarray(kp3d, np.float64)
             if kp3d.ndim == 2:
                 kp3d = np.broadcast_to(kp3d[None], (self.n_slots,) + kp3d.shape)
@@ -288,65 +300,12 @@ class BetaposeEngine:
         return out
 
     def run_stream(self, batches, graph: bool = True, image_index0: int = 0, after_step=None):
-        """Pipelined evaluation of a stream of frame batches (the reference's evaluate loop is a producer/consumer
-        pipeline too: dataloader.py:ImageLoader -> DetectionLoader -> DetectionProcessor -> DataWriter threads).
-        `batches` yields uint8 [n <= max_batch, H, W, 3] RGB host arrays / tensors (pinned memory for a truly
-        asynchronous copy).  While batch i computes, the host fetches batch i+1 from the iterator and its host->device
-        copy runs on a side stream into the other of two staging buffers.  Yields one host record array per batch, in
-        order.  `after_step(records_device)` is enqueued on the compute stream after each batch (e.g. the all-gather)."""
-        with torch.cuda.device(self.device):
-            if not hasattr(self, "_stage"):
-                self._stage = [torch.empty_like(self.frames) for _ in range(2)]
-                self._copy_stream = torch.cuda.Stream()
-                self._rec_host = [torch.empty((self.B, _lib.RECORD_BYTES), dtype=torch.uint8).pin_memory() for _ in range(2)]
-            cs = torch.cuda.current_stream()
-            ev_h2d = [torch.cuda.Event() for _ in range(2)]
-            ev_free = [torch.cuda.Event() for _ in range(2)]   # staging buffer consumed by the compute stream
-            ev_done = [torch.cuda.Event() for _ in range(2)]
-
-            def upload(fr, k):
-                fr = torch.as_tensor(fr)
-                n = int(fr.shape[0])
-                assert n <= self.B and tuple(fr.shape[1:]) == (self.frame_h, self.frame_w, 3) and fr.dtype == torch.uint8
-                with torch.cuda.stream(self._copy_stream):
-                    self._copy_stream.wait_event(ev_free[k])
-                    self._stage[k][:n].copy_(fr, non_blocking=True)
-                    ev_h2d[k].record(self._copy_stream)
-                return n
-
-            it = iter(batches)
-            try:
-                cur = next(it)
-            except StopIteration:
-                return
-            for e in ev_free:
-                e.record(cs)
-            n = upload(cur, 0)
-            k, idx0 = 0, int(image_index0)
-            while True:
-                b = k & 1
-                cs.wait_event(ev_h2d[b])
-                self.frames[:n].copy_(self._stage[b][:n], non_blocking=True)  # device->device, ~0.03 ms for 64 frames
-                ev_free[b].record(cs)
-                rec = self.run_device(n, None, 0, graph=graph)  # one captured graph per batch size; indices fixed up below
-                if after_step is not None:
-                    after_step(rec)
-                self._rec_host[b][:n].copy_(rec, non_blocking=True)
-                ev_done[b].record(cs)
-                n_cur, idx0 = n, idx0 + n
-                try:
-                    nxt = next(it)           # host work (frame decoding, ...) overlaps the GPU
-                    n = upload(nxt, b ^ 1)   # and so does the next batch's host->device copy
-                    more = True
-                except StopIteration:
-                    more = False
-                ev_done[b].synchronize()
-                out = stages.records_to_numpy(self._rec_host[b][:n_cur]).copy()
-                out["image_index"] = (idx0 - n_cur) + np.arange(n_cur)
-                yield out
-                if not more:
-                    return
-                k += 1
+        """Pipelined evaluation of a stream of frame batches on this engine alone (one batch on the GPU at a time; the
+        next batch's host->device copy overlaps it).  See PipelinedEngine.run_stream, which this delegates to with a
+        single lane; PipelinedEngine(2, ...) keeps two batches in flight on the GPU."""
+        if not hasattr(self, "_single_lane"):
+            self._single_lane = PipelinedEngine.from_engines([self])
+        yield from self._single_lane.run_stream(batches, graph=graph, image_index0=image_index0, after_step=after_step)
 
     def run(self, frames_u8, obj_slots=None, image_index0: int = 0, graph: bool = False) -> np.ndarray:
         """Public end-to-end call: frames uint8 [n,H,W,3] RGB (host numpy / pinned torch / cuda tensor), optional
@@ -376,3 +335,166 @@ class BetaposeEngine:
             out = out[inv]
             out["image_index"] = image_index0 + np.arange(n)
         return out
+
+
+class PipelinedEngine:
+    """L independent BetaposeEngine "lanes" (own activation buffers, own captured graph, own CUDA stream) that take the
+    batches of a stream in turn, so L batches are in flight on the GPU at once.
+
+    Why: one batch alone cannot keep 148 SMs busy all the time -- the second wave of a 160-tile layer, the 1x1-spatial SE
+    layers, the decode / PnP kernels (fp64 latency chains on a few warps) and every kernel boundary leave SMs idle.  With
+    a second batch in flight the hardware block scheduler fills those holes with the other lane's CTAs (measured on B200,
+    batch 64: 6 598 -> 7 143 images/s with two lanes; a third lane adds nothing; splitting ONE batch into halves loses,
+    `scripts/exp_two_streams.py`).  The reference is a pipeline of stages too (dataloader.py: ImageLoader ->
+    DetectionLoader -> DetectionProcessor -> DataWriter threads with queues between them); this is its device-side
+    equivalent.  Costs one extra set of activation buffers (~133 MB per frame of batch) and one extra weight copy."""
+
+    def __init__(self, lanes: int, max_batch: int, *args, **kw):
+        assert lanes >= 1
+        self._init([BetaposeEngine(max_batch, *args, **kw) for _ in range(int(lanes))])
+
+    @classmethod
+    def from_engines(cls, engines):
+        self = cls.__new__(cls)
+        self._init(list(engines))
+        return self
+
+    def _init(self, engines):
+        self.lanes = engines
+        e0 = engines[0]
+        self.device, self.B = e0.device, e0.B
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream() for _ in engines] if len(engines) > 1 else [None]
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = [torch.empty_like(e.frames) for e in engines]
+            # two host record buffers per lane: batch k's records may still be in the caller's hands when batch k + L lands
+            self._rec_host = [[torch.empty((e.B, _lib.RECORD_BYTES), dtype=torch.uint8).pin_memory() for _ in range(2)] for e in engines]
+
+    @property
+    def launches_per_step(self) -> int:
+        return self.lanes[0].launches_per_step
+
+    @property
+    def flops_per_image(self) -> float:
+        return self.lanes[0].flops_per_image
+
+    def lane_stream(self, k: int):
+        """(engine, stream) that batch number k runs on; stream is None for a single lane (= the caller's stream)."""
+        i = k % len(self.lanes)
+        return self.lanes[i], self.streams[i]
+
+    def submit_device(self, k: int, frames_dev: torch.Tensor | None = None, n: int | None = None, graph: bool = True,
+                      after_step=None) -> torch.Tensor:
+        """Enqueue batch k (frames already in HBM, or already in the lane's `frames` buffer when frames_dev is None) on its
+        lane's stream; returns the lane's device records view.  The caller orders the lane streams against its own stream
+        (fork / join) when it needs to."""
+        eng, st = self.lane_stream(k)
+        n = eng.B if n is None else int(n)
+        with torch.cuda.device(self.device):
+            ctx = torch.cuda.stream(st) if st is not None else _nullctx()
+            with ctx:
+                if frames_dev is not None:
+                    eng.frames[:n].copy_(frames_dev[:n], non_blocking=True)
+                rec = eng.run_device(n, graph=graph)
+                if after_step is not None:
+                    after_step(rec)
+        return rec
+
+    def fork(self) -> None:
+        """lane streams wait for everything enqueued so far on the caller's stream"""
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            if s is not None:
+                s.wait_stream(cur)
+
+    def join(self) -> None:
+        """the caller's stream waits for everything enqueued so far on the lanes"""
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            if s is not None:
+                cur.wait_stream(s)
+
+    def run_stream(self, batches, graph: bool = True, image_index0: int = 0, after_step=None):
+        """Pipelined evaluation of a stream of frame batches.  `batches` yields uint8 [n <= max_batch, H, W, 3] RGB host
+        arrays / tensors (pinned memory for a truly asynchronous copy).  Batch k runs on lane k % L: its host->device copy
+        goes over a side stream into the lane's staging buffer while earlier batches compute, the lane's stream then copies
+        it into place, replays the lane's step graph and reads the records back.  With L lanes the iterator is pulled L
+        batches ahead of the records being yielded.  Yields one host record array per batch, in input order.
+        `after_step(records_device)` is enqueued on the lane's stream after each batch (e.g. the all-gather)."""
+        from collections import deque
+
+        L = len(self.lanes)
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            streams = [s if s is not None else cur for s in self.streams]
+            ev_h2d = [torch.cuda.Event() for _ in range(L)]
+            ev_free = [torch.cuda.Event() for _ in range(L)]   # staging buffer consumed by the lane's stream
+            ev_done = [[torch.cuda.Event() for _ in range(2)] for _ in range(L)]
+            for i in range(L):
+                if streams[i] is not cur:
+                    streams[i].wait_stream(cur)
+                ev_free[i].record(streams[i])
+            pending = deque()
+            it = iter(batches)
+            k, idx0, exhausted = 0, int(image_index0), False
+
+            def launch(fr, k, idx0):
+                fr = torch.as_tensor(fr)
+                n = int(fr.shape[0])
+                i = k % L
+                eng = self.lanes[i]
+                assert n <= eng.B and tuple(fr.shape[1:]) == (eng.frame_h, eng.frame_w, 3) and fr.dtype == torch.uint8
+                with torch.cuda.stream(self._copy_stream):
+                    self._copy_stream.wait_event(ev_free[i])
+                    self._stage[i][:n].copy_(fr, non_blocking=True)
+                    ev_h2d[i].record(self._copy_stream)
+                h = (k // L) & 1
+                with torch.cuda.stream(streams[i]):
+                    streams[i].wait_event(ev_h2d[i])
+                    eng.frames[:n].copy_(self._stage[i][:n], non_blocking=True)  # device->device, ~0.03 ms for 64 frames
+                    ev_free[i].record(streams[i])
+                    rec = eng.run_device(n, None, 0, graph=graph)  # one captured graph per batch size; indices fixed up below
+                    if after_step is not None:
+                        after_step(rec)
+                    self._rec_host[i][h][:n].copy_(rec, non_blocking=True)
+                    ev_done[i][h].record(streams[i])
+                pending.append((i, h, n, idx0))
+
+            while True:
+                while not exhausted and len(pending) < L:
+                    try:
+                        nxt = next(it)           # host work (frame decoding, ...) overlaps the GPU
+                    except StopIteration:
+                        exhausted = True
+                        break
+                    launch(nxt, k, idx0)
+                    idx0 += int(torch.as_tensor(nxt).shape[0])
+                    k += 1
+                if not pending:
+                    break
+                i, h, n, first = pending.popleft()
+                # keep the pipe full while the oldest batch finishes: the next batch of this lane can be fetched and uploaded now
+                if not exhausted and len(pending) < L:
+                    try:
+                        nxt = next(it)
+                        launch(nxt, k, idx0)
+                        idx0 += int(torch.as_tensor(nxt).shape[0])
+                        k += 1
+                    except StopIteration:
+                        exhausted = True
+                ev_done[i][h].synchronize()
+                out = stages.records_to_numpy(self._rec_host[i][h][:n]).copy()
+                out["image_index"] = first + np.arange(n)
+                yield out
+            if cur is not None:
+                for s in streams:
+                    if s is not cur:
+                        cur.wait_stream(s)
+
+
+class _nullctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False

@@ -93,6 +93,24 @@ class Net:
         self._keep = share  # the sharing net must outlive us
         self.device = torch.device("cuda", self.engine.device)
 
+    def set_op_config(self, op: int, batch: int, block_n: int = 0, cg: int = 0, mt: int = 0) -> bool:
+        """Force the tile plan of convolution `op` at `batch` (bp_net_set_op_config); False if the layer cannot run that way."""
+        rc = _lib.lib().bp_net_set_op_config(self.handle, int(op), int(batch), int(block_n), int(cg), int(mt))
+        if rc == _lib.ERR_UNSUPPORTED:
+            return False
+        _lib.check(rc, "bp_net_set_op_config")
+        return True
+
+    def op_config(self, op: int, batch: int) -> tuple:
+        """(BLOCK_N, cg, mt, BLOCK_K, stages) of the plan `op` runs at `batch`; zeros for aux ops."""
+        cfg = (C.c_int * 5)()
+        _lib.check(_lib.lib().bp_net_op_config(self.handle, int(op), int(batch), cfg), "bp_net_op_config")
+        return tuple(cfg)
+
+    def set_share(self, share_batch: int) -> None:
+        """This net runs concurrently with other nets whose batches sum to share_batch images (bp_net_set_share)."""
+        _lib.check(_lib.lib().bp_net_set_share(self.handle, int(share_batch)), "bp_net_set_share")
+
     def __del__(self):
         try:
             if getattr(self, "handle", None):

@@ -138,6 +138,18 @@ int bp_net_forward(bp_net* n, int batch, void* stream);
 /* debugging / profiling: run only ops [first, last) */
 int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream);
 int bp_net_num_ops(bp_net* n);
+/* Measured tile plans (betapose_b200/tune.py): force the tile configuration of convolution `op` at batch size `batch` --
+ * BLOCK_N (32..256), cg (1 = single CTA, 2 = CTA pairs), mt (1 / 2 / 4 = 128- / 256- / 512-pixel tiles); 0 = leave that
+ * choice to the planner, all three 0 = remove the override.  BP_ERR_UNSUPPORTED if the layer cannot run that way. */
+int bp_net_set_op_config(bp_net* n, int op, int batch, int block_n, int cg, int mt);
+/* cfg[0..4] = {BLOCK_N, cg, mt, BLOCK_K, stages} of the plan convolution `op` runs at `batch` (zeros for aux ops) */
+int bp_net_op_config(bp_net* n, int op, int batch, int* cfg);
+/* Mixed-object batches (BASELINE.json configs[3]; the reference loads one detector + key-point net per object id,
+ * KPD/src/main_fast_inference.py:29-36): this net runs CONCURRENTLY with other objects' nets whose batches sum to
+ * `share_batch` images.  Its grids are then sized for num_sms * batch / share_batch SMs instead of the whole GPU (the
+ * objects split the machine in proportion to their frame counts) and its kernels are launched without programmatic
+ * stream serialisation (early-launched dependents would hold SMs another object could use).  0 = the net owns the GPU. */
+int bp_net_set_share(bp_net* n, int share_batch);
 /* per-op description for profiling tables: writes a short text into buf */
 int bp_net_op_desc(bp_net* n, int op, char* buf, int buflen, double* flops_per_image, double* bytes_per_image);
 

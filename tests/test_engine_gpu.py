@@ -460,19 +460,29 @@ def test_engine_batch64_stagewise_oracle_sample(yolo_blocks, yolo_stream, kpd_sd
     assert rec.tobytes() == rec2.tobytes()
     yparams, _ = onets.split_darknet_weights(yolo_blocks, yolo_stream)
 
+    acc = {"hm": [], "heads": []}
+
     def fp32_nets(s, b, yin, kin, hm):
         with torch.no_grad():
             ref_heads = onets.darknet_forward(yolo_blocks, yparams, torch.from_numpy(yin[None, :, :, :3]).permute(0, 3, 1, 2) / 255.0)
             ref_hm = onets.fastpose_forward(kpd_sd, torch.from_numpy(kin[None, :, :, :3]).permute(0, 3, 1, 2))
-        for h, r in zip(e.heads[s], ref_heads):
-            g = e.yolo[s].tensor(h["tensor"], 64)[b:b + 1].permute(0, 3, 1, 2).cpu()
-            scale = r.abs().max().item()
-            assert (g - r).abs().max().item() <= 3e-2 * scale and (g - r).abs().mean().item() <= 3e-3 * scale
-        scale = ref_hm.abs().max().item()
-        d = (torch.from_numpy(hm) - ref_hm).abs()
-        assert d.max().item() <= 3e-2 * scale and d.mean().item() <= 3e-3 * scale
+        acc["heads"].append([(e.yolo[s].tensor(h["tensor"], 64)[b:b + 1].permute(0, 3, 1, 2).cpu(), r) for h, r in zip(e.heads[s], ref_heads)])
+        acc["hm"].append((torch.from_numpy(hm), ref_hm))
 
     _stagewise_oracle_check(e, frames, (0, 21, 42, 63), fp32_nets=fp32_nets)
+    # fp16 networks vs fp32 oracle networks over the four sampled frames, errors relative to the largest magnitude of the
+    # sample as in tests/test_nets_gpu.py (fp16 activations through 100+ layers: ~3e-2 max / ~4e-3 mean of scale measured;
+    # the same images at batch 2 give the same bits -- test_fastpose_batch64_plans_vs_oracle -- so this is the number
+    # format, not the batch-64 tile plans)
+    for hi in range(3):
+        g = torch.cat([fr[hi][0] for fr in acc["heads"]])
+        r = torch.cat([fr[hi][1] for fr in acc["heads"]])
+        scale = r.abs().max().item()
+        assert (g - r).abs().max().item() <= 4e-2 * scale and (g - r).abs().mean().item() <= 5e-3 * scale
+    g, r = torch.cat([p[0] for p in acc["hm"]]), torch.cat([p[1] for p in acc["hm"]])
+    scale = r.abs().max().item()
+    d = (g - r).abs()
+    assert d.max().item() <= 4e-2 * scale and d.mean().item() <= 5e-3 * scale, (d.max().item(), d.mean().item(), scale)
     assert (rec["status"] == 1).sum() >= 32
     del e
     torch.cuda.empty_cache()
@@ -589,4 +599,48 @@ def test_configs4_occlusion_batch16(yolo_stream, kpd_sd, kp_model):
     live = rec["status"] != 0
     assert live.sum() >= 8 and (e.selected.cpu().numpy()[live].sum(1) == 10).all()
     del e
+    torch.cuda.empty_cache()
+
+
+def test_pipelined_engine_two_lanes_matches_single(yolo_stream, kpd_sd, kp_model):
+    """PipelinedEngine: two batches in flight on two lanes must return, batch by batch and in order, exactly the records
+    a single engine returns; a ragged last batch and host / pinned inputs included."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine, PipelinedEngine
+
+    frames = synth.synth_frames(22, seed=55)
+    batches = [frames[0:6], frames[6:12], frames[12:18], frames[18:22]]
+    single = BetaposeEngine(6, yolo_stream, kpd_sd, kp_model, seed=5)
+    want = [single.run(b).copy() for b in batches]
+    del single
+    torch.cuda.empty_cache()
+    pipe = PipelinedEngine(2, 6, yolo_stream, kpd_sd, kp_model, seed=5)
+    pulled = []
+
+    def gen():
+        for i, b in enumerate(batches):
+            pulled.append(i)
+            yield torch.from_numpy(b).pin_memory() if i % 2 else b
+
+    got = []
+    for k, rec in enumerate(pipe.run_stream(gen(), graph=True, image_index0=100)):
+        assert len(pulled) >= min(k + 2, len(batches))  # the iterator runs ahead of the records: two batches in flight
+        got.append(rec)
+    assert len(got) == len(want)
+    first = 100
+    for g, w in zip(got, want):
+        assert g["image_index"].tolist() == list(range(first, first + len(w)))
+        first += len(w)
+        for f in w.dtype.names:
+            if f != "image_index":
+                assert np.array_equal(g[f], w[f]), f
+    # device-side submission (bench.py's `value` loop): fork, two steps on two lanes, join
+    dev = torch.from_numpy(frames[:6]).cuda()
+    pipe.fork()
+    r0 = pipe.submit_device(0, dev)
+    r1 = pipe.submit_device(1, dev)
+    pipe.join()
+    torch.cuda.synchronize()
+    assert torch.equal(r0, r1) and r0.data_ptr() != r1.data_ptr()
+    del pipe
     torch.cuda.empty_cache()
