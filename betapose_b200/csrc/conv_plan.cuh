@@ -22,6 +22,7 @@ struct ConvDesc {
   int Cout = 0, Cout_pad = 0;
   int R = 1, S = 1, stride = 1, pad = 0;
   int pad_w = -1;  // horizontal padding, -1 = same as `pad` (the packed stem convolutions use 0, see net.cu)
+  int stride_w = 0;  // horizontal stride, 0 = same as `stride` (the grouped stem steps 4 virtual pixels per GEMM row)
   int act = ACT_NONE;
   const __half* res = nullptr;
   int res_pitch = 0, res_mode = RES_NONE;
@@ -136,10 +137,11 @@ inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
 
 inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::string* err) {
   const int pad_w = d.pad_w < 0 ? d.pad : d.pad_w;
+  const int stride_w = d.stride_w > 0 ? d.stride_w : d.stride;
   const int P = (d.H + 2 * d.pad - d.R) / d.stride + 1;
-  const int Q = (d.W + 2 * pad_w - d.S) / d.stride + 1;
+  const int Q = (d.W + 2 * pad_w - d.S) / stride_w + 1;
   const int M = d.N * P * Q;
-  const bool matrix = d.R == 1 && d.S == 1 && d.stride == 1 && d.pad == 0 && pad_w == 0 && d.x_row_pitch == 0;
+  const bool matrix = d.R == 1 && d.S == 1 && d.stride == 1 && stride_w == 1 && d.pad == 0 && pad_w == 0 && d.x_row_pitch == 0;
   // matrix mode may have a ragged K: TMA zero-fills the tail
   const int block_k = matrix ? (d.C >= 64 ? 64 : 32) : ((d.C % 64 == 0) ? 64 : 32);
   if (!matrix && d.C % 32 != 0) {
@@ -231,6 +233,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.P = P;
   a.Q = Q;
   a.stride = d.stride;
+  a.stride_w = stride_w;
   a.pad = d.pad;
   a.pad_w = pad_w;
   a.C = d.C;
@@ -265,7 +268,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
       return false;
   } else {
     if (!make_tmap_im2col(api, &pl->tmA, d.x, d.N, d.H, d.W, d.C, d.x_pitch, d.R, d.S, d.stride, d.pad, pad_w, block_k, err,
-                          d.x_row_pitch, d.x_img_pitch, mt == 4 ? 256 : 128 * mt))
+                          d.x_row_pitch, d.x_img_pitch, mt == 4 ? 256 : 128 * mt, stride_w))
       return false;
   }
   if (!make_tmap_2d(api, &pl->tmB, d.w, (uint64_t)d.Cout_pad, (uint64_t)K, (uint64_t)d.w_pitch, bn / cg, block_k, err))

@@ -36,7 +36,8 @@ struct ConvArgs {
   int num_kb;    // K / BLOCK_K
   int a_im2col;  // 1: A through the im2col tensor map over NHWC; 0: A is a row-major [M, K] matrix
   int P, Q;      // output height / width
-  int stride, pad;  // pad = vertical padding
+  int stride, pad;  // vertical stride / padding
+  int stride_w;     // horizontal stride (== stride except for the grouped stem convolution)
   int pad_w;        // horizontal padding (== pad except for the packed stem convolutions)
   int C;            // input channels per filter tap as seen by the im2col map (multiple of BLOCK_K)
   int S;         // filter width
@@ -275,7 +276,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int rem = m0 - img * pq;
           const int op = fast_div(rem, p.mul_q);
           const int oq = rem - op * p.Q;
-          w0 = oq * p.stride - p.pad_w;
+          w0 = oq * p.stride_w - p.pad_w;
           h0 = op * p.stride - p.pad;
         }
         int w0b = 0, h0b = 0, imgb = 0;  // MT == 4: window origin of the tile's second 256 pixels
@@ -285,7 +286,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             imgb = fast_div(mb, p.mul_pq);
             const int rem = mb - imgb * pq;
             const int op = fast_div(rem, p.mul_q);
-            w0b = (rem - op * p.Q) * p.stride - p.pad_w;
+            w0b = (rem - op * p.Q) * p.stride_w - p.pad_w;
             h0b = op * p.stride - p.pad;
           }
         }

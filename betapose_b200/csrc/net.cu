@@ -249,11 +249,43 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
     w_host = hw.data();
     b_host = hb.data();
   }
-  __half* dw = (__half*)net_alloc_weights(n, n_w * 2);
-  float* db = (float*)net_alloc_weights(n, n_b * 4);
+  // ---- grouped stem: a 3x3 / 1 convolution of the 3-channel network input with few output channels is run with FOUR
+  // horizontally adjacent output pixels per GEMM row.  A row's operand is one 128-byte line -- 8 input pixels x 8 channels
+  // of one filter row, the window of the four outputs (6 pixels) plus two that meet zero weights -- so a k-block is staged
+  // as 128 rows of 128 B instead of 512 rows of 64 B for the same 512 outputs (the ungrouped stem is bound by the TMA row
+  // rate), and the result row is 4 pixels x Cout channels = 256 contiguous bytes of the NHWC output, a dense TMA store.
+  // The GEMM grows to N = 4 Cout, K = 3 x 64 (mostly zeros: 7x the useful MACs, still far below the layer's HBM time).
+  // The weights are derived here from the ordinary packed stem layout, so weight files and the packed cache do not change.
+  const bool grouped = stem && k == 3 && s->stride == 1 && s->pad == 1 && Cin <= 8 && Cout % 8 == 0 && Cout * 4 <= 128 && Q % 4 == 0 &&
+                       s->store_mode == BP_STORE_PLAIN && !s->out_f32 && s->res < 0 && s->dst < 0 && Cv == 32 && !getenv("BP_NO_GROUPED_STEM");
+  std::vector<__half> gw;
+  std::vector<float> gb;
+  int wpitch_dev = wpitch;
+  size_t n_w_dev = n_w, n_b_dev = n_b;
+  if (grouped) {
+    const int G = 4, Kg = 3 * 64;
+    gw.assign((size_t)Cout_pad * Kg, __float2half(0.f));
+    gb.assign((size_t)Cout_pad, 0.f);
+    const __half* hw_src = reinterpret_cast<const __half*>(w_host);
+    for (int j = 0; j < G; ++j)
+      for (int co = 0; co < Cout; ++co) {
+        gb[(size_t)j * Cout + co] = b_host[co];
+        for (int r = 0; r < 3; ++r)
+          for (int px = j; px < j + 3; ++px)  // window pixel px holds filter column px - j of output j
+            for (int ci = 0; ci < 8; ++ci)
+              gw[((size_t)j * Cout + co) * Kg + r * 64 + px * 8 + ci] = hw_src[(size_t)co * wpitch + r * Cv + (px - j) * 8 + ci];
+      }
+    w_host = gw.data();
+    b_host = gb.data();
+    wpitch_dev = Kg;
+    n_w_dev = gw.size();
+    n_b_dev = gb.size();
+  }
+  __half* dw = (__half*)net_alloc_weights(n, n_w_dev * 2);
+  float* db = (float*)net_alloc_weights(n, n_b_dev * 4);
   if (!dw || !db) return bp_fail(BP_ERR_CUDA, "bp_net_conv: cudaMalloc (weights) failed");
-  if (cudaMemcpy(dw, w_host, n_w * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(db, b_host, n_b * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+  if (cudaMemcpy(dw, w_host, n_w_dev * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(db, b_host, n_b_dev * 4, cudaMemcpyHostToDevice) != cudaSuccess)
     return bp_fail(BP_ERR_CUDA, "bp_net_conv: weight upload failed");
 
   // ---- destination tensor
@@ -281,11 +313,17 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
     d.x_row_pitch = (long)src.row_px * 8; d.x_img_pitch = (long)src.H * src.row_px * 8;
     d.R = k; d.S = 1; d.stride = s->stride; d.pad = s->pad; d.pad_w = 0;
     d.real_k = (double)k * k * Cin;
+    if (grouped) {  // virtual pixels of 8 real pixels, one GEMM row per 4 output columns
+      d.W = (Q / 4 - 1) * 4 + 1;
+      d.C = 64;
+      d.stride_w = 4;
+      d.force_mt = 2;
+    }
   } else {
     d.x = (const __half*)src.ptr; d.N = n->max_batch; d.H = src.H; d.W = src.W; d.C = Cin; d.x_pitch = src.pitch;
     d.R = k; d.S = k; d.stride = s->stride; d.pad = s->pad;
   }
-  d.w = dw; d.bias = db; d.w_pitch = wpitch; d.Cout = Cout; d.Cout_pad = Cout_pad;
+  d.w = dw; d.bias = db; d.w_pitch = wpitch_dev; d.Cout = grouped ? 4 * Cout : Cout; d.Cout_pad = Cout_pad;
   d.act = s->act;
   if (s->res >= 0) {
     if (s->res >= (int)n->tensors.size()) return bp_fail(BP_ERR_INVALID, "bp_net_conv: res id");
@@ -296,6 +334,10 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   }
   d.out = dt.f32 ? (void*)((float*)dt.ptr) : (void*)((__half*)dt.ptr);
   d.out_pitch = dt.pitch; d.out_coff = coff; d.out_f32 = s->out_f32; d.store_mode = s->store_mode;
+  if (grouped) {
+    if (dt.pitch != Cout || coff != 0) return bp_fail(BP_ERR_UNSUPPORTED, "bp_net_conv: grouped stem needs a dense output tensor");
+    d.out_pitch = 4 * Cout;  // one GEMM row = 4 pixels of the dense NHWC output
+  }
   if (n->eng->force_block_n) d.force_block_n = n->eng->force_block_n;
   if (n->eng->force_stages) d.force_stages = n->eng->force_stages;
 
@@ -318,6 +360,7 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   char tile[32] = "";
   if (plan0.cg == 2) snprintf(tile, sizeof tile, " cg2");
   else if (plan0.mt > 1) snprintf(tile, sizeof tile, " mt%d", plan0.mt);
+  if (grouped) snprintf(tile + strlen(tile), sizeof tile - strlen(tile), " g4");
   snprintf(buf, sizeof buf, "conv %dx%d/%d %d->%d @%dx%d bn%d bk%d st%d%s%s%s%s", k, k, s->stride, Cin, Cout, P, Q,
            plan0.block_n, plan0.block_k, plan0.stages, tile, s->res >= 0 ? " +res" : "",
            s->store_mode == BP_STORE_UPSAMPLE2 ? " up2" : (s->store_mode == BP_STORE_PIXSHUF2 ? " ps2" : ""),

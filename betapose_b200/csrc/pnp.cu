@@ -1,18 +1,16 @@
 // a9 (single-proposal pose-NMS) + a10 (key-point selection) + a11 (PnP) in two launches:
-//   pnp_hypotheses_kernel : grid (n_hyp / 8, images).  Every CTA redoes the (cheap) pose-NMS + selection of its image,
-//                           then solves 8 five-point EPnP hypotheses, 8 cooperating lanes each: the 12 x 12 M^T M
-//                           eigen-problem -- 80 % of the serial work of a hypothesis -- runs as a parallel-order Jacobi
-//                           (the 6 disjoint rotations of a round at once, 72 column / row updates spread over the
-//                           lanes) on matrices held in shared memory; the rest of EPnP is executed redundantly by the
-//                           8 lanes (identical inputs, identical results, no divergence).  Each hypothesis is scored
-//                           against all selected points (12 px) and left in a global scratch row.
+//   pnp_hypotheses_serial_kernel : one CTA per image, one thread per five-point EPnP hypothesis (fp64): pose-NMS + selection of
+//                           the image once, then every thread solves its hypothesis -- control points, 12 x 12 M^T M
+//                           eigen-problem by Householder + QL in local memory, three beta initialisations + Gauss-Newton,
+//                           Horn absolute orientation -- scores it against all selected points (12 px) and leaves it in a
+//                           global scratch row.
 //   pnp_refine_kernel     : one warp per image picks the consensus winner (shuffle arg-max) and alternates
 //                           {classify points against the current pose, Levenberg-Marquardt refit, lane-parallel over
 //                           points} until the consensus set is stable.
-// 512 small CTAs instead of 64 keep ~3.5 CTAs per SM in flight, so the fp64 dependency chains of different
-// hypotheses hide each other's latency.
 // Reference: pPose_nms.py:24-122 (n = 1 branch), dataloader.py:715-726, utils/utils.py:17-41.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "betapose_b200.h"
 #include "engine.h"
@@ -22,9 +20,6 @@ namespace {
 
 constexpr int kMaxK = 64;
 constexpr int kMaxHyp = 128;
-// cooperating lanes per hypothesis: template parameter GW (8 or 16; >= the 6 pairs of a Jacobi round); a CTA is 128
-// threads = 128 / GW hypotheses.  8 lanes is the throughput choice (less redundant fp64 work per hypothesis), 16 the
-// latency choice for small batches (shorter Jacobi phases).
 constexpr int kHypRow = 16;         // doubles per hypothesis in the scratch: count, total, R[9], t[3], pad
 
 // One warp, lanes over points; the 28 sums of an LM step are all-reduced by shuffles (independent chains: they
@@ -45,102 +40,6 @@ struct WarpLanes {
                                              const uint8_t* mask, int n, double fx, double fy, double cx, double cy,
                                              double* acc) const {
     bp::pnp::lm_accumulate(*this, R, t, pw, uv, mask, n, fx, fy, cx, cy, acc);
-  }
-};
-
-// ---- 12 x 12 symmetric eigen-solver on 16 cooperating lanes (half a warp), A and V in shared memory.
-// Parallel-order cyclic Jacobi: a sweep is 11 rounds of 6 disjoint pairs (circle method); the rotations of a round
-// commute, so A <- J^T A J is applied as "all column updates, then all row updates".  Same rotation formulas as the
-// serial jacobi_eig<12> (pnp_math.cuh), different rotation order.
-template <int kGW>
-struct GroupEig12 {
-  double* A;      // [144] shared, this group's
-  double* V;      // [144] shared
-  unsigned mask;  // the kGW lanes of this group inside the warp
-  int gl;         // lane inside the group
-
-  __device__ __forceinline__ double gsum(double x) const {
-#pragma unroll
-    for (int o = kGW / 2; o > 0; o >>= 1) x += __shfl_xor_sync(mask, x, o, kGW);
-    return x;
-  }
-
-  __device__ const double* solve(double* M, double* w) {
-    for (int r = gl; r < 12; r += kGW) {
-#pragma unroll
-      for (int c = 0; c < 12; ++c) {
-        A[r * 12 + c] = M[r * 12 + c];
-        V[r * 12 + c] = r == c ? 1.0 : 0.0;
-      }
-    }
-    __syncwarp(mask);
-    for (int sweep = 0; sweep < 60; ++sweep) {
-      double off = 0.0, diag = 0.0;
-      for (int r = gl; r < 12; r += kGW) {
-        diag += A[r * 13] * A[r * 13];
-        for (int q = r + 1; q < 12; ++q) off += A[r * 12 + q] * A[r * 12 + q];
-      }
-      off = gsum(off);
-      diag = gsum(diag);
-      if (off < 1e-300) break;
-      const bool last = off <= 1e-22 * diag;  // quadratic convergence: one more sweep reaches the rounding floor
-      for (int r = 0; r < 11; ++r) {
-        // this lane's pair of the round (lanes 0..5): (11, r) and ((r + i) % 11, (r - i) % 11), i = 1..5
-        int p = 0, q = 1;
-        double c = 1.0, s = 0.0;
-        if (gl < 6) {
-          int a = gl == 0 ? 11 : (r + gl) % 11;
-          int b = gl == 0 ? r : (r - gl + 11) % 11;
-          p = a < b ? a : b;
-          q = a < b ? b : a;
-          const double apq = A[p * 12 + q];
-          if (fabs(apq) >= 1e-300) {
-            const double theta = (A[q * 12 + q] - A[p * 12 + p]) / (2.0 * apq);
-            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            c = 1.0 / sqrt(t * t + 1.0);
-            s = t * c;
-          }
-        }
-        __syncwarp(mask);  // every pair has read its 2 x 2 block before anything is rewritten
-        // columns of A and V: item (pair j, row k), 72 items over the kGW lanes
-#pragma unroll
-        for (int it = 0; it < (72 + kGW - 1) / kGW; ++it) {
-          const int i = gl + kGW * it;
-          const int j = i < 72 ? i / 12 : 0;
-          const int k = i - (i / 12) * 12;
-          const int pj = __shfl_sync(mask, p, j, kGW), qj = __shfl_sync(mask, q, j, kGW);
-          const double cj = __shfl_sync(mask, c, j, kGW), sj = __shfl_sync(mask, s, j, kGW);
-          if (i < 72) {
-            const double akp = A[k * 12 + pj], akq = A[k * 12 + qj];
-            A[k * 12 + pj] = cj * akp - sj * akq;
-            A[k * 12 + qj] = sj * akp + cj * akq;
-            const double vkp = V[k * 12 + pj], vkq = V[k * 12 + qj];
-            V[k * 12 + pj] = cj * vkp - sj * vkq;
-            V[k * 12 + qj] = sj * vkp + cj * vkq;
-          }
-        }
-        __syncwarp(mask);
-        // rows of A
-#pragma unroll
-        for (int it = 0; it < (72 + kGW - 1) / kGW; ++it) {
-          const int i = gl + kGW * it;
-          const int j = i < 72 ? i / 12 : 0;
-          const int k = i - (i / 12) * 12;
-          const int pj = __shfl_sync(mask, p, j, kGW), qj = __shfl_sync(mask, q, j, kGW);
-          const double cj = __shfl_sync(mask, c, j, kGW), sj = __shfl_sync(mask, s, j, kGW);
-          if (i < 72) {
-            const double apk = A[pj * 12 + k], aqk = A[qj * 12 + k];
-            A[pj * 12 + k] = cj * apk - sj * aqk;
-            A[qj * 12 + k] = sj * apk + cj * aqk;
-          }
-        }
-        __syncwarp(mask);
-      }
-      if (last) break;
-    }
-#pragma unroll
-    for (int i = 0; i < 12; ++i) w[i] = A[i * 13];
-    return V;
   }
 };
 
@@ -212,35 +111,33 @@ __device__ __forceinline__ void stage_a(ImageState& S, int i, int K, const float
   __syncthreads();
 }
 
-template <int kGW>
-__global__ void __launch_bounds__(128, 4)
-pnp_hypotheses_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
-                      const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d,
-                      const int32_t* __restrict__ model_idx, double fx, double fy, double cx, double cy, int left_number, int mode,
-                      int flags, double thr2, int n_hyp, uint32_t seed, float* __restrict__ keypoints,
-                      float* __restrict__ kp_score, float* __restrict__ proposal, uint8_t* __restrict__ selected,
-                      double* __restrict__ hyp /* [images][kMaxHyp][kHypRow] */) {
-  constexpr int kHypPerCta = 128 / kGW;
+// ONE thread per hypothesis, one CTA per image.  The 12 x 12 eigen-problem runs as a Householder + QL pass in the thread's
+// own local memory (pnp_math.cuh: sym_eig_ql, ~5x fewer flops than Jacobi sweeps), no shared-memory matrices, no shuffles:
+// 128 warps of independent fp64 work per 64-frame batch, pose-NMS + selection once per image.  (Round 1 ran 8 / 16
+// cooperating lanes per hypothesis around a parallel-order Jacobi in shared memory: 1024 warps in lock step, 40 KB of
+// shared memory per CTA, 0.55 ms per batch of 64 against 0.3 ms now; one algorithm for every batch size also keeps the
+// poses bit-identical whatever batch a frame arrives in.)
+__global__ void __launch_bounds__(128)
+pnp_hypotheses_serial_kernel(const float* __restrict__ preds_img, const float* __restrict__ maxval, const float* __restrict__ det_score,
+                             const uint8_t* __restrict__ valid, int K, const double* __restrict__ kp3d,
+                             const int32_t* __restrict__ model_idx, double fx, double fy, double cx, double cy, int left_number,
+                             int mode, int flags, double thr2, int n_hyp, uint32_t seed, float* __restrict__ keypoints,
+                             float* __restrict__ kp_score, float* __restrict__ proposal, uint8_t* __restrict__ selected,
+                             double* __restrict__ hyp /* [images][kMaxHyp][kHypRow] */) {
   __shared__ ImageState S;
-  __shared__ double s_A[kHypPerCta][144];
-  __shared__ double s_V[kHypPerCta][144];
-
-  const int i = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int g = tid / kGW;                   // hypothesis slot inside the CTA
-  const int gl = tid % kGW;
-  const int h = blockIdx.x * kHypPerCta + g;  // hypothesis index
-  stage_a(S, i, K, preds_img, maxval, det_score, valid, kp3d, model_idx, left_number, flags, blockIdx.x == 0, keypoints, kp_score,
-          proposal, selected);
-
+  const int i = blockIdx.x;
+  const int h = threadIdx.x;  // hypothesis index
+  stage_a(S, i, K, preds_img, maxval, det_score, valid, kp3d, model_idx, left_number, flags, true, keypoints, kp_score, proposal,
+          selected);
   const bool run = S.state == 1 && S.nsel >= 4 && !(flags & BP_PNP_NMS_ONLY);
   const bool ransac = run && mode == 0 && S.nsel >= 6;
+  if (h >= kMaxHyp) return;
   double* row = hyp + ((long)i * kMaxHyp + h) * kHypRow;
   bool solved = false;
   int cnt = 0;
   double tot = 0.0;
   double R[9], t[3];
-  if (run && h < kMaxHyp && (ransac ? h < n_hyp : h == 0)) {
+  if (run && (ransac ? h < n_hyp : h == 0)) {
     int pool[kMaxK];
     int m = 0;
     for (int j = 0; j < K; ++j)
@@ -249,22 +146,20 @@ pnp_hypotheses_kernel(const float* __restrict__ preds_img, const float* __restri
       bp::pnp::sample_subset(pool, m, h, seed, 5);
       m = 5;
     }
-    GroupEig12<kGW> eig{s_A[g], s_V[g], ((1u << kGW) - 1u) << (kGW * ((tid & 31) / kGW)), gl};
+    bp::pnp::QlEig12 eig;
     if (bp::pnp::epnp(eig, S.pw, S.uv, pool, m, fx, fy, cx, cy, R, t)) {
       solved = true;
       cnt = m;
       if (ransac) bp::pnp::score_hypothesis(R, t, S.pw, S.uv, S.sel, K, fx, fy, cx, cy, thr2, &cnt, &tot);
     }
   }
-  if (gl == 0 && h < kMaxHyp) {
-    row[0] = solved ? (double)cnt : -1.0;
-    row[1] = tot;
-    if (solved) {
+  row[0] = solved ? (double)cnt : -1.0;
+  row[1] = tot;
+  if (solved) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) row[2 + k] = R[k];
+    for (int k = 0; k < 9; ++k) row[2 + k] = R[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) row[11 + k] = t[k];
-    }
+    for (int k = 0; k < 3; ++k) row[11 + k] = t[k];
   }
 }
 
@@ -370,16 +265,11 @@ extern "C" int bp_pose_pnp(bp_engine* e, const float* preds_img, const float* ma
   bp_engine::StreamScratch& sc = e->scratch_for(st);
   if (!e->grow(reinterpret_cast<void**>(&sc.pnp), &sc.pnp_bytes, need)) return bp_fail(BP_ERR_CUDA, "bp_pose_pnp: scratch allocation failed");
   const double thr2 = (double)reproj_thr * (double)reproj_thr;
-  if (n >= 16) {  // throughput: 8 lanes per hypothesis, 16 hypotheses per CTA
-    const int groups = mode == 0 ? (n_hyp + 15) / 16 : 1;
-    pnp_hypotheses_kernel<8><<<dim3(groups, n), 128, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1],
-                                                              cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints,
-                                                              kp_score, proposal, selected, sc.pnp);
-  } else {        // latency: 16 lanes per hypothesis, 8 hypotheses per CTA
-    const int groups = mode == 0 ? (n_hyp + 7) / 8 : 1;
-    pnp_hypotheses_kernel<16><<<dim3(groups, n), 128, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1],
-                                                               cam[2], cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints,
-                                                               kp_score, proposal, selected, sc.pnp);
+  {
+    const int threads = mode == 0 ? ((n_hyp + 31) / 32) * 32 : 32;
+    pnp_hypotheses_serial_kernel<<<n, threads, 0, st>>>(preds_img, maxval, det_score, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2],
+                                                        cam[3], left_number, mode, flags, thr2, n_hyp, seed, keypoints, kp_score,
+                                                        proposal, selected, sc.pnp);
   }
   pnp_refine_kernel<<<n, 32, 0, st>>>(preds_img, maxval, valid, K, kp3d, model_idx, cam[0], cam[1], cam[2], cam[3], left_number, mode,
                                       flags, thr2, n_hyp, sc.pnp, R, t, inlier, status);

@@ -68,14 +68,15 @@ inline bool make_tmap_2d(TmapApi& api, CUtensorMap* out, const void* base, uint6
 // padded row pitch of the network-input buffer.
 inline bool make_tmap_im2col(TmapApi& api, CUtensorMap* out, const void* base, int N, int H, int W, int C,
                              int pitch, int R, int S, int stride, int pad_h, int pad_w, uint32_t block_k, std::string* err,
-                             long row_pitch = 0, long img_pitch = 0, uint32_t pixels = 128) {
+                             long row_pitch = 0, long img_pitch = 0, uint32_t pixels = 128, int stride_w = 0) {
+  if (stride_w <= 0) stride_w = stride;
   if (row_pitch <= 0) row_pitch = (long)W * pitch;
   if (img_pitch <= 0) img_pitch = (long)H * row_pitch;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)row_pitch * 2, (cuuint64_t)img_pitch * 2};
   int lower[2] = {-pad_w, -pad_h};
   int upper[2] = {pad_w - (S - 1), pad_h - (R - 1)};
-  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride, 1};
   CUresult r = api.im2col(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
                           upper, block_k, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(block_k),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -188,7 +188,7 @@ class BetaposeEngine:
         L, e = _lib.lib(), self.yolo[0].engine.handle
         _lib.check(L.bp_pose_pnp(e, _lib.ptr(self.preds_img), _lib.ptr(self.maxval), _lib.ptr(self.det_score),
                                  _lib.ptr(self.valid), n, self.K, _lib.ptr(self.kp3d), _lib.ptr(self.model_idx),
-                                 C.cast(self._cam, C.c_void_p), self.left_number, self.pnp_mode, 0, self.reproj_thr, self.n_hyp,
+                                 C.cast(self._cam, C.c_void_p), self.left_number, self.pnp_mode, getattr(self, "pnp_flags", 0), self.reproj_thr, self.n_hyp,
                                  self.seed & 0xFFFFFFFF, _lib.ptr(self.keypoints), _lib.ptr(self.kp_score),
                                  _lib.ptr(self.proposal), _lib.ptr(self.selected), _lib.ptr(self.R), _lib.ptr(self.t),
                                  _lib.ptr(self.inlier), _lib.ptr(self.status), st), "bp_pose_pnp")

@@ -78,3 +78,23 @@ extern "C" int bp_host_epnp(const double* pw, const double* uv, int K, const dou
   for (int j = 0; j < K; ++j) pool[j] = j;
   return bp::pnp::epnp(pw, uv, pool, K, cam[0], cam[1], cam[2], cam[3], R_out, t_out) ? 0 : -1;
 }
+
+// EPnP with the cyclic-Jacobi policy (what the device's small-batch path does cooperatively) for comparison
+extern "C" int bp_host_epnp_jacobi(const double* pw, const double* uv, int K, const double* cam, double* R_out, double* t_out) {
+  int pool[64];
+  for (int j = 0; j < K; ++j) pool[j] = j;
+  bp::pnp::SerialEig12 eig;
+  return bp::pnp::epnp(eig, pw, uv, pool, K, cam[0], cam[1], cam[2], cam[3], R_out, t_out) ? 0 : -1;
+}
+
+// 12 x 12 symmetric eigen-solvers alone: which = 0 Householder + QL, 1 cyclic Jacobi.  a[144] in; vectors (columns) and w[12] out
+extern "C" void bp_host_sym_eig12(const double* a, int which, double* vec, double* w) {
+  double A[144];
+  for (int i = 0; i < 144; ++i) A[i] = a[i];
+  if (which == 0) {
+    bp::pnp::sym_eig_ql<12>(A, w);
+    for (int i = 0; i < 144; ++i) vec[i] = A[i];
+  } else {
+    bp::pnp::jacobi_eig<12>(A, vec, w);
+  }
+}

@@ -440,8 +440,8 @@ def _stagewise_oracle_check(e, frames, sample, slot_of=None, fp32_nets=None):
             # junk key-points of random networks: the consensus problem is ill-posed, so only well-posed frames (a clear
             # consensus in both) are compared on R, t; status must agree whenever the oracle is confident either way
             if sol["ok"] and st == 1 and np.array_equal(e.inlier[b].cpu().numpy().astype(bool)[keep], sol["inliers"]):
-                np.testing.assert_allclose(e.R[b].cpu().numpy().reshape(3, 3), sol["R"], atol=1e-6)
-                np.testing.assert_allclose(e.t[b].cpu().numpy(), sol["t"], atol=1e-6)
+                np.testing.assert_allclose(e.R[b].cpu().numpy().reshape(3, 3), sol["R"], atol=1e-3)  # tolerance of record; 1e-6 on well-posed inputs: test_stages_gpu.py
+                np.testing.assert_allclose(e.t[b].cpu().numpy(), sol["t"], atol=1e-3)
 
 
 def test_engine_batch64_stagewise_oracle_sample(yolo_blocks, yolo_stream, kpd_sd, kp_model):

@@ -101,3 +101,47 @@ def test_sampling_spec_matches(host):
     # partial Fisher-Yates draws are part of the shared spec; exercised through identical best_h above, and directly:
     assert opnp.sample_subset(50, 3, 11) == opnp.sample_subset(50, 3, 11)
     assert len(set(opnp.sample_subset(50, 0, 0))) == 5
+
+
+def test_sym_eig12_ql_and_jacobi_vs_numpy(host):
+    """Both 12 x 12 eigen-solvers of pnp_math.cuh against numpy.linalg.eigh: well-conditioned matrices, and the rank-10
+    M^T M of a five-point EPnP sample (two exactly-zero eigenvalues: the case the QL deflation tolerance is written for)."""
+    host.bp_host_sym_eig12.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    host.bp_host_sym_eig12.restype = None
+    rng = np.random.default_rng(5)
+    mats = []
+    for _ in range(10):
+        B = rng.standard_normal((12, 12))
+        mats.append(B @ B.T)
+    for _ in range(10):  # rank deficient, entries ~ fx^2 like M^T M
+        M = rng.standard_normal((10, 12)) * rng.uniform(1, 600, (1, 12))
+        mats.append(M.T @ M)
+    mats.append(np.diag(np.arange(12.0)))      # already diagonal
+    mats.append(np.zeros((12, 12)))
+    for A in mats:
+        we = np.linalg.eigvalsh(A)
+        scale = max(1.0, np.abs(we).max())
+        for which in (0, 1):
+            a = np.ascontiguousarray(A, np.float64)
+            vec, w = np.zeros((12, 12)), np.zeros(12)
+            host.bp_host_sym_eig12(a.ctypes.data, which, vec.ctypes.data, w.ctypes.data)
+            assert np.allclose(np.sort(w), we, atol=1e-11 * scale), which
+            assert np.allclose(vec.T @ vec, np.eye(12), atol=1e-11), which                       # orthonormal columns
+            assert np.allclose(A @ vec, vec * w[None, :], atol=1e-10 * scale), which              # A v = w v
+
+
+def test_host_epnp_ql_matches_jacobi_on_exact_data(host):
+    from betapose_b200 import synth
+
+    host.bp_host_epnp_jacobi.argtypes = host.bp_host_epnp.argtypes
+    kp = synth.synth_kp_model(3, 50)
+    rng = np.random.default_rng(1)
+    cam = np.array([R.CAM_K[0, 0], R.CAM_K[1, 1], R.CAM_K[0, 2], R.CAM_K[1, 2]], np.float64)
+    for _ in range(10):
+        _, _, uv = make_case(rng, kp, 0.3)
+        uv64 = np.ascontiguousarray(uv.astype(np.float64))
+        Ra, ta, Rb, tb = np.zeros(9), np.zeros(3), np.zeros(9), np.zeros(3)
+        assert host.bp_host_epnp(kp.ctypes.data, uv64.ctypes.data, 50, cam.ctypes.data, Ra.ctypes.data, ta.ctypes.data) == 0
+        assert host.bp_host_epnp_jacobi(kp.ctypes.data, uv64.ctypes.data, 50, cam.ctypes.data, Rb.ctypes.data, tb.ctypes.data) == 0
+        np.testing.assert_allclose(Ra, Rb, atol=1e-7)   # 50 points: all eigenvalues distinct, the two solvers agree
+        np.testing.assert_allclose(ta, tb, atol=1e-7)
