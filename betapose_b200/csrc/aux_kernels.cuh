@@ -60,55 +60,60 @@ __global__ void maxpool3x3s2_kernel(TView in, TView out, int N) {
 // slices so that even a 64-image batch fills the machine; every block leaves its partial sums in `scratch`
 // ([N][S][C] fp32) and the last block to finish an (image, channel-block) adds the S partials in a fixed order
 // (bit-reproducible: no floating-point atomics) and writes the fp16 mean.
-__global__ void global_avgpool_kernel(TView in, __half* out, int out_pitch, float* scratch, unsigned* counters, int S) {
+// The ORDER of the summation is a property of the tensor shape alone: the H*W positions are always cut into S0 "virtual"
+// slices (S0 from H*W only); the launch uses S <= S0 blocks per image, block sl taking the virtual slices sl, sl + S, ...,
+// and the S0 partials are added in slice order.  So a frame's result does not depend on the batch it arrives in.
+__global__ void global_avgpool_kernel(TView in, __half* out, int out_pitch, float* scratch, unsigned* counters, int S, int S0) {
   __shared__ float red[8][32][8];
   __shared__ bool s_last;
   const int n = blockIdx.y;
-  const int sl = blockIdx.z;
   const int cg = blockIdx.x * 32 + (threadIdx.x & 31);
   const int pl = threadIdx.x >> 5;
   const int HW = in.H * in.W;
-  const int chunk = (HW + S - 1) / S;
-  const int px0 = sl * chunk, px1 = min(HW, px0 + chunk);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int chunk = (HW + S0 - 1) / S0;
   const bool live = cg * 8 < in.C;
-  if (live) {
-    const __half* ip = reinterpret_cast<const __half*>(in.ptr) + (long)n * HW * in.pitch + cg * 8;
-    for (int px = px0 + pl; px < px1; px += 8) {
-      const uint4 v = ldg16(ip + (long)px * in.pitch);
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
+  float* part = scratch + ((long)n * S0) * in.C + cg * 8;
+  for (int vs = blockIdx.z; vs < S0; vs += S) {
+    const int px0 = vs * chunk, px1 = min(HW, px0 + chunk);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+      const __half* ip = reinterpret_cast<const __half*>(in.ptr) + (long)n * HW * in.pitch + cg * 8;
+      for (int px = px0 + pl; px < px1; px += 8) {
+        const uint4 v = ldg16(ip + (long)px * in.pitch);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h[i]);
+          acc[2 * i] += f.x;
+          acc[2 * i + 1] += f.y;
+        }
+      }
+    }
+    __syncthreads();  // the previous virtual slice's partials have been read out of `red`
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl][threadIdx.x & 31][i] = acc[i];
+    __syncthreads();
+    if (pl == 0 && live) {
+      float4 lo, hi;
+      float* f = &lo.x;
+      float* g = &hi.x;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        acc[2 * i] += f.x;
-        acc[2 * i + 1] += f.y;
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          a += red[l][threadIdx.x & 31][i];
+          b += red[l][threadIdx.x & 31][4 + i];
+        }
+        f[i] = a;
+        g[i] = b;
       }
+      float* dst = part + (long)vs * in.C;
+      *reinterpret_cast<float4*>(dst) = lo;
+      *reinterpret_cast<float4*>(dst + 4) = hi;
     }
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[pl][threadIdx.x & 31][i] = acc[i];
-  __syncthreads();
-  float* part = scratch + ((long)n * S) * in.C + cg * 8;
-  if (pl == 0 && live) {
-    float4 lo, hi;
-    float* f = &lo.x;
-    float* g = &hi.x;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a = 0.f, b = 0.f;
-#pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        a += red[l][threadIdx.x & 31][i];
-        b += red[l][threadIdx.x & 31][4 + i];
-      }
-      f[i] = a;
-      g[i] = b;
-    }
-    float* dst = part + (long)sl * in.C;
-    *reinterpret_cast<float4*>(dst) = lo;
-    *reinterpret_cast<float4*>(dst + 4) = hi;
-    __threadfence();
-  }
+  if (pl == 0 && live) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned* ctr = counters + (long)n * gridDim.x + blockIdx.x;
@@ -120,7 +125,7 @@ __global__ void global_avgpool_kernel(TView in, __half* out, int out_pitch, floa
   if (s_last && pl == 0 && live) {
     __threadfence();
     float sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < S; ++k) {
+    for (int k = 0; k < S0; ++k) {
       const float4 lo = __ldcg(reinterpret_cast<const float4*>(part + (long)k * in.C));
       const float4 hi = __ldcg(reinterpret_cast<const float4*>(part + (long)k * in.C + 4));
       sum[0] += lo.x; sum[1] += lo.y; sum[2] += lo.z; sum[3] += lo.w;

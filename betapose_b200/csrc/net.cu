@@ -604,11 +604,13 @@ int bp_net_forward_range(bp_net* n, int batch, int first, int last, void* stream
       case OP_AVGPOOL: {
         const Tensor &s = n->tensors[op.a], &d = n->tensors[op.dst];
         const int cblks = (s.C + 255) / 256;
-        // slices per image: enough blocks for ~4 per SM, at least 32 pixels per slice
+        // summation order: S0 virtual slices of >= 32 positions, a function of the tensor shape only (batch-independent
+        // results); blocks per image: enough for ~4 per SM
+        const int S0 = std::max(1, std::min(kAvgSplitMax, (s.H * s.W + 31) / 32));
         int S = (4 * n->eng->num_sms + cblks * batch - 1) / (cblks * batch);
-        S = std::max(1, std::min(S, std::min(kAvgSplitMax, (s.H * s.W + 31) / 32)));
+        S = std::max(1, std::min(S, S0));
         dim3 grid(cblks, batch, S);
-        global_avgpool_kernel<<<grid, 256, 0, st>>>(view_of(s), (__half*)d.ptr, d.pitch, op.scratch, op.counters, S);
+        global_avgpool_kernel<<<grid, 256, 0, st>>>(view_of(s), (__half*)d.ptr, d.pitch, op.scratch, op.counters, S, S0);
         e = cudaGetLastError();
         break;
       }
