@@ -627,26 +627,25 @@ def ours_arm(args):
         pipe.submit_device(i, dev_sets[i % n_sets], graph=bool(args.graph), after_step=gather)
 
     def timed_e2e():
-        """The public streaming API (BetaposeEngine.run_stream) on pinned HOST batches: every step's host->device copy
-        (on a side stream, overlapping the previous step's compute) and the device->host read of its result records
-        are inside the timed region; the caller holds step i's records before step i+1's are requested."""
+        """The public streaming API (PipelinedEngine.run_stream) on pinned HOST batches: every step's host->device copy
+        (on a side stream, overlapping earlier steps' compute) and the device->host read of its result records are inside
+        the timed region.  The timed region is one complete stream of exactly K batches, from an EMPTY pipeline (after a
+        synchronize) until the last record is on the host and the device is idle again: pipeline fill and drain are paid
+        inside it (with L batches in flight, timing K yields of a longer stream would count only K - L batches of work)."""
         last = None
-        stream = pipe.run_stream((host[i % n_sets] for i in range(W + K)), graph=bool(args.graph), after_step=gather)
-        for _ in range(W):
-            last = next(stream)
+        for last in pipe.run_stream((host[i % n_sets] for i in range(W)), graph=bool(args.graph), after_step=gather):
+            pass
         gather.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(K):
-            last = next(stream)
+        for last in pipe.run_stream((host[(W + i) % n_sets] for i in range(K)), graph=bool(args.graph), after_step=gather):
+            pass
         gather.drain()
         torch.cuda.synchronize()
         dt_ms = (time.perf_counter() - t0) * 1e3
-        for _ in stream:
-            pass
-        gather.drain()
         ms = torch.tensor([dt_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)

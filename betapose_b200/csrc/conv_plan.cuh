@@ -101,9 +101,18 @@ inline bool conv_plan_supported(const ConvPlan& pl) {
   return (bn == 64 && pl.stages == 13) || (bn == 32 && pl.stages == 16);
 }
 
+// Four configurations would fill the SM's shared memory to the last kilobyte with a four-buffer epilogue ring.  They run
+// with three buffers instead, which leaves >= 17 KB per SM free: the small stage kernels of the OTHER batch in flight (PnP
+// hypotheses / refit, decode: <= 5 KB per CTA, long-running fp64 chains) can then co-reside with any convolution CTA instead of
+// holding an SM that a persistent, statically scheduled convolution grid has to wait for.
+#ifndef BP_NB_TIGHT
+#define BP_NB_TIGHT 3
+#endif
+constexpr int kNbTight = BP_NB_TIGHT;
+
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
   if (pl.cg == 2) {
-    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 5, 2>(pl, st);
+    if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 5, 2, kNbTight>(pl, st);
     if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, 2>(pl, st);
     return cudaErrorInvalidConfiguration;
   }
@@ -115,9 +124,9 @@ inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
   }
   if (pl.mt == 2) {  // 256-pixel tiles (narrow layers)
     if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 3, 1, 4, 2>(pl, st);
-    if (pl.block_n == 64 && pl.block_k == 64) return launch_cfg<64, 64, 4, 1, 4, 2>(pl, st);
+    if (pl.block_n == 64 && pl.block_k == 64) return launch_cfg<64, 64, 4, 1, kNbTight, 2>(pl, st);
     if (pl.block_n == 32 && pl.block_k == 64) return launch_cfg<32, 64, 5, 1, 4, 2>(pl, st);
-    if (pl.block_n == 64 && pl.block_k == 32) return launch_cfg<64, 32, 8, 1, 4, 2>(pl, st);
+    if (pl.block_n == 64 && pl.block_k == 32) return launch_cfg<64, 32, 8, 1, kNbTight, 2>(pl, st);
     if (pl.block_n == 32 && pl.block_k == 32) return launch_cfg<32, 32, 10, 1, 4, 2>(pl, st);
     return cudaErrorInvalidConfiguration;
   }
@@ -126,7 +135,7 @@ inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
   // as many stages as fit beside the epilogue ring: the loop TMA issue -> data lands -> MMA -> commit -> slot free
   // takes ~3000 cycles under load, and a CTA sustains (bytes in flight) / (that latency)
   BP_CASE(256, 64, 3)
-  BP_CASE(128, 64, 5)
+  if (pl.block_n == 128 && pl.block_k == 64 && pl.stages == 5) return launch_cfg<128, 64, 5, 1, kNbTight>(pl, st);
   BP_CASE(64, 64, 6)
   BP_CASE(32, 64, 9)
   BP_CASE(64, 32, 13)

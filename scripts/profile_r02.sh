@@ -1,0 +1,18 @@
+#!/bin/bash
+# ncu evidence for round 2 (run under gpurun on ONE GPU): launch list, DRAM counters of every kernel of one step,
+# --set full captures of the stage kernels, the PnP kernels and three conv variants.
+set -x
+O=gpurun_out
+M1=gpu__time_duration.sum
+M2=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fp64.sum,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size
+ncu --profile-from-start off --metrics $M1 --clock-control none --csv --log-file $O/r02_launches_b64.csv python scripts/ncu_step.py 64 > $O/r02_ncu1.log 2>&1
+ncu --profile-from-start off --metrics $M2 --clock-control none --csv --log-file $O/r02_counters_b64.csv python scripts/ncu_step.py 64 > $O/r02_ncu2.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'resize|yolo_decode|crop_resize|heatmap_decode|pnp_|pack_records' -o $O/r02_stage_kernels python scripts/ncu_step.py 64 > $O/r02_ncu3.log 2>&1
+# conv: the grouped stem (launch 1 of the detector), a CTA-pair 3x3 layer, a 20x16 1x1 layer of the key-point net
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_umma -c 1 -o $O/r02_conv_stem python scripts/ncu_step.py 64 > $O/r02_ncu4.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'conv_umma_kernel<256, 64, 5, 2' -s 6 -c 1 -o $O/r02_conv_pair python scripts/ncu_step.py 64 > $O/r02_ncu5.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'conv_umma_kernel<256, 64, 3, 1' -s 60 -c 2 -o $O/r02_conv_1x1 python scripts/ncu_step.py 64 > $O/r02_ncu6.log 2>&1
+for f in r02_stage_kernels r02_conv_stem r02_conv_pair r02_conv_1x1; do
+  ncu -i $O/$f.ncu-rep --page raw --csv > $O/$f.raw.csv 2>/dev/null
+done
+ls -la $O/r02_*
