@@ -24,6 +24,7 @@ struct bp_engine {
   int force_block_n = 0;  // tuning overrides (env BP_FORCE_BLOCK_N / BP_FORCE_STAGES)
   int force_stages = 0;
   std::map<std::pair<int, int>, ResizeTables> resize_tables;
+  float* crop_lut = nullptr;  // [3][256] (u / 255) - mean[c], built on first use (bp_crop_resize)
   // Kernel scratch is kept PER STREAM (calls on one stream are ordered, calls on different streams never share a
   // block) and is grow-only: a block that became too small is retired into `owned`, never freed while the engine
   // lives, because CUDA graphs captured earlier have its address baked in (BetaposeEngine captures one graph per

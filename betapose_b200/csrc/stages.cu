@@ -142,17 +142,23 @@ __global__ void resize_v_kernel(const uint8_t* __restrict__ in, int B, int H, in
 }
 
 // Both passes in one kernel: a block owns TH output rows of one image.  It stages the input rows those need in shared
-// memory (16-byte loads), runs Pillow's horizontal pass on them into a uint8 intermediate -- the rounding to 8 bits
-// between the passes is part of the bit-exact semantics --, then the vertical pass, and writes the network-input
-// layout.  No global intermediate, coalesced traffic only; the horizontal pass is redone for the few rows neighbouring
-// tiles share.
-__global__ void __launch_bounds__(256)
+// memory (16-byte loads) together with the coefficient tables, runs Pillow's horizontal pass on them into a uint8
+// intermediate -- the rounding to 8 bits between the passes is part of the bit-exact semantics --, then the vertical pass,
+// and writes the network-input layout.  No global intermediate, coalesced traffic only; the horizontal pass is redone for
+// the few rows neighbouring tiles share.  One thread per output COLUMN in both passes: its horizontal taps (<= kMaxTaps
+// 22-bit coefficients) live in registers for all rows, the vertical taps are a shared-memory broadcast, and no index
+// arithmetic (division / modulo) is left in the inner loops -- the kernel is bound by its integer multiply-adds.
+constexpr int kMaxTaps = 12;
+
+__global__ void __launch_bounds__(448)
 resize_fused_kernel(const uint8_t* __restrict__ in, int H, int W, int oh, int ow, const int32_t* __restrict__ hb,
                     const int32_t* __restrict__ hk, int hks, const int32_t* __restrict__ vb, const int32_t* __restrict__ vk, int vks,
                     int TH, int in_pitch, int mid_pitch, int max_rows, __half* __restrict__ out_net, float* __restrict__ out_f32) {
   extern __shared__ __align__(16) uint8_t rs_smem[];
   uint8_t* s_in = rs_smem;                                  // [max_rows][in_pitch]
   uint8_t* s_mid = rs_smem + (size_t)max_rows * in_pitch;   // [max_rows][mid_pitch]
+  int32_t* s_vk = reinterpret_cast<int32_t*>(s_mid + (size_t)max_rows * mid_pitch);  // [TH][vks] vertical taps of this tile
+  int32_t* s_vb = s_vk + TH * vks;                                                   // [TH][2]
   const int b = blockIdx.y;
   const int y0 = blockIdx.x * TH, y1 = min(oh, y0 + TH);
   const int r0 = vb[2 * y0];
@@ -160,65 +166,71 @@ resize_fused_kernel(const uint8_t* __restrict__ in, int H, int W, int oh, int ow
   const int nrows = r1 - r0;
   const int row_bytes = W * 3;
   const uint8_t* src = in + ((long)b * H + r0) * row_bytes;
+  for (int e = threadIdx.x; e < (y1 - y0) * vks; e += blockDim.x) s_vk[e] = __ldg(vk + (long)y0 * vks + e);
+  for (int e = threadIdx.x; e < (y1 - y0) * 2; e += blockDim.x) s_vb[e] = __ldg(vb + 2 * y0 + e);
   if ((row_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
     const int vec = row_bytes >> 4;
-    for (int e = threadIdx.x; e < nrows * vec; e += blockDim.x) {
-      const int r = e / vec, c = e - r * vec;
-      reinterpret_cast<uint4*>(s_in + (size_t)r * in_pitch)[c] = __ldg(reinterpret_cast<const uint4*>(src + (long)r * row_bytes) + c);
-    }
+    for (int r = 0; r < nrows; ++r)
+      for (int c = threadIdx.x; c < vec; c += blockDim.x)
+        reinterpret_cast<uint4*>(s_in + (size_t)r * in_pitch)[c] = __ldg(reinterpret_cast<const uint4*>(src + (long)r * row_bytes) + c);
   } else {
-    for (int e = threadIdx.x; e < nrows * row_bytes; e += blockDim.x) {
-      const int r = e / row_bytes, c = e - r * row_bytes;
-      s_in[(size_t)r * in_pitch + c] = src[(long)r * row_bytes + c];
+    for (int r = 0; r < nrows; ++r)
+      for (int c = threadIdx.x; c < row_bytes; c += blockDim.x) s_in[(size_t)r * in_pitch + c] = src[(long)r * row_bytes + c];
+  }
+  __syncthreads();
+  for (int xx = threadIdx.x; xx < ow; xx += blockDim.x) {
+    // ---- horizontal pass of column xx over the staged rows
+    const int x0 = __ldg(hb + 2 * xx), n = __ldg(hb + 2 * xx + 1);
+    int k[kMaxTaps];
+#pragma unroll
+    for (int t = 0; t < kMaxTaps; ++t) k[t] = t < n ? __ldg(hk + (long)xx * hks + t) : 0;
+    const uint8_t* p = s_in + x0 * 3;
+    uint8_t* d = s_mid + xx * 3;
+    for (int r = 0; r < nrows; ++r, p += in_pitch, d += mid_pitch) {
+      int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t) {
+        if (t < n) {
+          s0 += p[3 * t] * k[t];
+          s1 += p[3 * t + 1] * k[t];
+          s2 += p[3 * t + 2] * k[t];
+        }
+      }
+      d[0] = (uint8_t)clip8(s0);
+      d[1] = (uint8_t)clip8(s1);
+      d[2] = (uint8_t)clip8(s2);
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nrows * ow; e += blockDim.x) {
-    const int r = e / ow, xx = e - r * ow;
-    const int x0 = hb[2 * xx], n = hb[2 * xx + 1];
-    const int32_t* k = hk + (long)xx * hks;
-    const uint8_t* p = s_in + (size_t)r * in_pitch + x0 * 3;
-    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    for (int x = 0; x < n; ++x) {
-      const int c = __ldg(k + x);
-      s0 += p[3 * x] * c;
-      s1 += p[3 * x + 1] * c;
-      s2 += p[3 * x + 2] * c;
-    }
-    uint8_t* d = s_mid + (size_t)r * mid_pitch + xx * 3;
-    d[0] = (uint8_t)clip8(s0);
-    d[1] = (uint8_t)clip8(s1);
-    d[2] = (uint8_t)clip8(s2);
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < (y1 - y0) * ow; e += blockDim.x) {
-    const int yl = e / ow, xx = e - yl * ow;
-    const int yy = y0 + yl;
-    const int yb = vb[2 * yy] - r0, n = vb[2 * yy + 1];
-    const int32_t* k = vk + (long)yy * vks;
-    const uint8_t* p = s_mid + (size_t)yb * mid_pitch + xx * 3;
-    int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-    for (int y = 0; y < n; ++y) {
-      const int c = __ldg(k + y);
-      const uint8_t* q = p + (size_t)y * mid_pitch;
-      s0 += q[0] * c;
-      s1 += q[1] * c;
-      s2 += q[2] * c;
-    }
-    const int r = clip8(s0), g = clip8(s1), bl = clip8(s2);
-    if (out_net) {
-      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-      __half2* h = reinterpret_cast<__half2*>(&pk);
-      h[0] = __floats2half2_rn((float)r, (float)g);
-      h[1] = __floats2half2_rn((float)bl, 0.f);
-      reinterpret_cast<uint4*>(out_net)[((long)b * oh + yy) * (ow + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + xx] = pk;
-    }
-    if (out_f32) {
-      const long plane = (long)oh * ow;
-      float* o = out_f32 + (long)b * 3 * plane + (long)yy * ow + xx;
-      o[0] = __fdiv_rn((float)r, 255.f);
-      o[plane] = __fdiv_rn((float)g, 255.f);
-      o[2 * plane] = __fdiv_rn((float)bl, 255.f);
+  for (int xx = threadIdx.x; xx < ow; xx += blockDim.x) {
+    // ---- vertical pass of column xx for the TH output rows
+    for (int yl = 0; yl < y1 - y0; ++yl) {
+      const int yy = y0 + yl;
+      const int yb = s_vb[2 * yl] - r0, n = s_vb[2 * yl + 1];
+      const int32_t* k = s_vk + yl * vks;
+      const uint8_t* q = s_mid + (size_t)yb * mid_pitch + xx * 3;
+      int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
+      for (int y = 0; y < n; ++y, q += mid_pitch) {
+        const int c = k[y];
+        s0 += q[0] * c;
+        s1 += q[1] * c;
+        s2 += q[2] * c;
+      }
+      const int r = clip8(s0), g = clip8(s1), bl = clip8(s2);
+      if (out_net) {
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+        __half2* h = reinterpret_cast<__half2*>(&pk);
+        h[0] = __floats2half2_rn((float)r, (float)g);
+        h[1] = __floats2half2_rn((float)bl, 0.f);
+        reinterpret_cast<uint4*>(out_net)[((long)b * oh + yy) * (ow + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + xx] = pk;
+      }
+      if (out_f32) {
+        const long plane = (long)oh * ow;
+        float* o = out_f32 + (long)b * 3 * plane + (long)yy * ow + xx;
+        o[0] = __fdiv_rn((float)r, 255.f);
+        o[plane] = __fdiv_rn((float)g, 255.f);
+        o[2 * plane] = __fdiv_rn((float)bl, 255.f);
+      }
     }
   }
 }
@@ -242,7 +254,8 @@ extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int
         const int yl = std::min(oh, y0 + TH) - 1;
         max_rows = std::max(max_rows, tv->host_bounds[2 * yl] + tv->host_bounds[2 * yl + 1] - tv->host_bounds[2 * y0]);
       }
-      const size_t smem = (size_t)max_rows * (in_pitch + mid_pitch);
+      if (th->ksize > kMaxTaps) break;  // (very strong down-scaling: the two-kernel path below has no tap limit)
+      const size_t smem = (size_t)max_rows * (in_pitch + mid_pitch) + (size_t)TH * (tv->ksize + 2) * sizeof(int32_t);
       if (smem > 100 * 1024) continue;
       if (smem > 48 * 1024) {
         static bool attr_done[64] = {};  // per device
@@ -251,7 +264,8 @@ extern "C" int bp_resize_bicubic(bp_engine* e, const uint8_t* frames, int B, int
         }
       }
       dim3 grid((oh + TH - 1) / TH, B);
-      resize_fused_kernel<<<grid, 256, smem, st>>>(frames, H, W, oh, ow, th->bounds, th->coeffs, th->ksize, tv->bounds, tv->coeffs,
+      const int threads = std::min(448, (ow + 31) / 32 * 32);  // one thread per output column (416 for the detector input)
+      resize_fused_kernel<<<grid, threads, smem, st>>>(frames, H, W, oh, ow, th->bounds, th->coeffs, th->ksize, tv->bounds, tv->coeffs,
                                                   tv->ksize, TH, in_pitch, mid_pitch, max_rows, (__half*)out_net, out_f32_chw);
       cudaError_t err = cudaGetLastError();
       return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
@@ -515,71 +529,102 @@ __device__ CropGeom crop_geometry(const float* bx, int W, int H, int rh, int rw)
   return g;
 }
 
-// one thread per output pixel (3 channels): 4-tap bilinear (align_corners=True) over the zero-padded,
-// mean-subtracted patch; coalesced fp16x4 NHWC store (+ optional fp32 NCHW for the drop-in seam)
-__global__ void crop_resize_kernel(const uint8_t* __restrict__ frames, int H, int W, const float* __restrict__ box,
-                                   const int32_t* __restrict__ img_idx, const uint8_t* __restrict__ valid, int rh, int rw,
-                                   __half* __restrict__ out16, float* __restrict__ out32, float* __restrict__ pt1,
-                                   float* __restrict__ pt2) {
-  // per block, once: the box geometry and the table (u / 255) - mean[c] of im_to_torch + the mean subtraction
-  // (256 x 3 exact fp32 divisions instead of twelve per output pixel)
+// (u / 255) - mean[c] of im_to_torch + the mean subtraction (dataloader.py:802-804, BGR means applied in RGB order), one
+// exact fp32 division per table entry; built once per engine instead of three divisions per output pixel
+__global__ void crop_lut_kernel(float* lut) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 768) return;
+  const float mean[3] = {0.406f, 0.457f, 0.480f};
+  lut[e] = __fadd_rn(__fdiv_rn((float)(e & 255), 255.f), -mean[e >> 8]);
+}
+
+constexpr int kCropPxPerThread = 4;
+
+// 4-tap bilinear (align_corners=True) over the zero-padded, mean-subtracted patch; a block covers 1024 output pixels of one
+// crop (4 per thread, so the per-block set-up -- box geometry, scale factors, the 3 KB value table -- is amortised); coalesced
+// fp16x8 NHWC stores (+ optional fp32 NCHW for the drop-in seam).  Same fp32 operation order as the reference throughout.
+__global__ void __launch_bounds__(256)
+crop_resize_kernel(const uint8_t* __restrict__ frames, int H, int W, const float* __restrict__ box,
+                   const int32_t* __restrict__ img_idx, const uint8_t* __restrict__ valid, int rh, int rw,
+                   const float* __restrict__ lut, __half* __restrict__ out16, float* __restrict__ out32, float* __restrict__ pt1,
+                   float* __restrict__ pt2) {
   __shared__ CropGeom s_g;
+  __shared__ float s_scale[2];
   __shared__ float s_lut[3][256];
   const int i = blockIdx.y;
   const bool ok = !valid || valid[i];
   if (ok) {
-    if (threadIdx.x == 0) s_g = crop_geometry(box + 4 * i, W, H, rh, rw);
-    const float mean[3] = {0.406f, 0.457f, 0.480f};
-    for (int e = threadIdx.x; e < 768; e += blockDim.x) s_lut[e >> 8][e & 255] = __fadd_rn(__fdiv_rn((float)(e & 255), 255.f), -mean[e >> 8]);
+    if (threadIdx.x == 0) {
+      const CropGeom g = crop_geometry(box + 4 * i, W, H, rh, rw);
+      s_g = g;
+      s_scale[0] = rh > 1 ? __fdiv_rn((float)(g.Hp - 1), (float)(rh - 1)) : 0.f;
+      s_scale[1] = rw > 1 ? __fdiv_rn((float)(g.Wp - 1), (float)(rw - 1)) : 0.f;
+    }
+    for (int e = threadIdx.x; e < 768; e += blockDim.x) s_lut[e >> 8][e & 255] = __ldg(lut + e);
   }
   __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= rh * rw) return;
-  float v[3] = {0.f, 0.f, 0.f};
-  if (ok) {
-    const CropGeom g = s_g;
-    const int oy = pix / rw, ox = pix - oy * rw;
-    const float rhs = rh > 1 ? __fdiv_rn((float)(g.Hp - 1), (float)(rh - 1)) : 0.f;
-    const float rws = rw > 1 ? __fdiv_rn((float)(g.Wp - 1), (float)(rw - 1)) : 0.f;
-    const float ys = __fmul_rn(rhs, (float)oy), xs = __fmul_rn(rws, (float)ox);
-    const int y0 = (int)ys, x0 = (int)xs;
-    const int y1 = min(y0 + 1, g.Hp - 1), x1 = min(x0 + 1, g.Wp - 1);
-    const float ly = __fsub_rn(ys, (float)y0), lx = __fsub_rn(xs, (float)x0);
-    const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-    const uint8_t* fr = frames + (long)img_idx[i] * H * W * 3;
-    auto tap = [&](int py, int px, int c) -> float {
-      const int sy = py - g.top, sx = px - g.left;  // position inside the source patch
-      if (sy < 0 || sy >= g.hS || sx < 0 || sx >= g.wS) return 0.f;
-      return s_lut[c][fr[((long)(g.uly + sy) * W + (g.ulx + sx)) * 3 + c]];
-    };
+  const int npix = rh * rw;
+  const CropGeom g = s_g;
+  const float rhs = s_scale[0], rws = s_scale[1];
+  const uint8_t* fr = ok ? frames + (long)img_idx[i] * H * W * 3 : frames;
+  int pix = blockIdx.x * (blockDim.x * kCropPxPerThread) + threadIdx.x;
+  int oy = pix / rw, ox = pix - oy * rw;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float p00 = tap(y0, x0, c), p01 = tap(y0, x1, c), p10 = tap(y1, x0, c), p11 = tap(y1, x1, c);
-      const float t = __fadd_rn(__fmul_rn(hx, p00), __fmul_rn(lx, p01));
-      const float bt = __fadd_rn(__fmul_rn(hx, p10), __fmul_rn(lx, p11));
-      v[c] = __fadd_rn(__fmul_rn(hy, t), __fmul_rn(ly, bt));
+  for (int it = 0; it < kCropPxPerThread; ++it, pix += blockDim.x) {
+    if (pix >= npix) break;
+    if (it) {  // advance (oy, ox) by blockDim.x pixels without a division
+      ox += blockDim.x;
+      while (ox >= rw) {
+        ox -= rw;
+        ++oy;
+      }
     }
-    if (pix == 0) {
+    float v[3] = {0.f, 0.f, 0.f};
+    if (ok) {
+      const float ys = __fmul_rn(rhs, (float)oy), xs = __fmul_rn(rws, (float)ox);
+      const int y0 = (int)ys, x0 = (int)xs;
+      const int y1 = min(y0 + 1, g.Hp - 1), x1 = min(x0 + 1, g.Wp - 1);
+      const float ly = __fsub_rn(ys, (float)y0), lx = __fsub_rn(xs, (float)x0);
+      const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+      // positions inside the source patch; a tap outside it reads the zero padding
+      const int sy0 = y0 - g.top, sy1 = y1 - g.top, sx0 = x0 - g.left, sx1 = x1 - g.left;
+      const bool vy0 = (unsigned)sy0 < (unsigned)g.hS, vy1 = (unsigned)sy1 < (unsigned)g.hS;
+      const bool vx0 = (unsigned)sx0 < (unsigned)g.wS, vx1 = (unsigned)sx1 < (unsigned)g.wS;
+      const uint8_t* r0 = fr + ((long)(g.uly + sy0) * W + g.ulx) * 3;
+      const uint8_t* r1 = fr + ((long)(g.uly + sy1) * W + g.ulx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float p00 = (vy0 && vx0) ? s_lut[c][r0[sx0 * 3 + c]] : 0.f;
+        const float p01 = (vy0 && vx1) ? s_lut[c][r0[sx1 * 3 + c]] : 0.f;
+        const float p10 = (vy1 && vx0) ? s_lut[c][r1[sx0 * 3 + c]] : 0.f;
+        const float p11 = (vy1 && vx1) ? s_lut[c][r1[sx1 * 3 + c]] : 0.f;
+        const float t = __fadd_rn(__fmul_rn(hx, p00), __fmul_rn(lx, p01));
+        const float bt = __fadd_rn(__fmul_rn(hx, p10), __fmul_rn(lx, p11));
+        v[c] = __fadd_rn(__fmul_rn(hy, t), __fmul_rn(ly, bt));
+      }
+    }
+    if (out16) {  // network input layout: [n, rh, rw + BP_IN_PAD_COLS, 8]
+      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+      __half2* h = reinterpret_cast<__half2*>(&pk);
+      h[0] = __floats2half2_rn(v[0], v[1]);
+      h[1] = __floats2half2_rn(v[2], 0.f);
+      reinterpret_cast<uint4*>(out16)[((long)i * rh + oy) * (rw + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + ox] = pk;
+    }
+    if (out32) {
+      const long plane = (long)rh * rw;
+      float* o = out32 + (long)i * 3 * plane + pix;
+      o[0] = v[0];
+      o[plane] = v[1];
+      o[2 * plane] = v[2];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (ok) {
       pt1[2 * i] = g.pt1x; pt1[2 * i + 1] = g.pt1y;
       pt2[2 * i] = g.pt2x; pt2[2 * i + 1] = g.pt2y;
+    } else {
+      pt1[2 * i] = pt1[2 * i + 1] = pt2[2 * i] = pt2[2 * i + 1] = 0.f;
     }
-  } else if (pix == 0) {
-    pt1[2 * i] = pt1[2 * i + 1] = pt2[2 * i] = pt2[2 * i + 1] = 0.f;
-  }
-  if (out16) {  // network input layout: [n, rh, rw + BP_IN_PAD_COLS, 8]
-    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-    __half2* h = reinterpret_cast<__half2*>(&pk);
-    h[0] = __floats2half2_rn(v[0], v[1]);
-    h[1] = __floats2half2_rn(v[2], 0.f);
-    const int oy = pix / rw, ox = pix - oy * rw;
-    reinterpret_cast<uint4*>(out16)[((long)i * rh + oy) * (rw + BP_IN_PAD_COLS) + BP_IN_PAD_LEFT + ox] = pk;
-  }
-  if (out32) {
-    const long plane = (long)rh * rw;
-    float* o = out32 + (long)i * 3 * plane + pix;
-    o[0] = v[0];
-    o[plane] = v[1];
-    o[2 * plane] = v[2];
   }
 }
 
@@ -590,8 +635,18 @@ extern "C" int bp_crop_resize(bp_engine* e, const uint8_t* frames, int H, int W,
                               float* pt2, void* stream) {
   if (!e || !frames || !box || !img_idx || !pt1 || !pt2 || n <= 0 || (!out_net && !out_f32_chw))
     return bp_fail(BP_ERR_INVALID, "bp_crop_resize: bad arguments");
-  dim3 grid((rh * rw + 255) / 256, n);
-  crop_resize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(frames, H, W, box, img_idx, valid, rh, rw,
+  if (!e->crop_lut) {  // first use (engine set-up; not inside a stream capture): the value table
+    float* lut = nullptr;
+    if (cudaMalloc(&lut, 768 * sizeof(float)) != cudaSuccess) return bp_fail(BP_ERR_CUDA, "bp_crop_resize: table allocation failed");
+    crop_lut_kernel<<<3, 256>>>(lut);
+    if (cudaDeviceSynchronize() != cudaSuccess) return bp_fail(BP_ERR_CUDA, "bp_crop_resize: table kernel failed (first use inside a stream capture?)");
+    std::lock_guard<std::mutex> g(e->mu);
+    e->owned.push_back(lut);
+    e->crop_lut = lut;
+  }
+  const int per_block = 256 * kCropPxPerThread;
+  dim3 grid((rh * rw + per_block - 1) / per_block, n);
+  crop_resize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(frames, H, W, box, img_idx, valid, rh, rw, e->crop_lut,
                                                                               (__half*)out_net, out_f32_chw, pt1, pt2);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? BP_OK : bp_fail(BP_ERR_CUDA, cudaGetErrorString(err));
