@@ -733,7 +733,7 @@ def ours_arm(args):
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}); burst {peaks['tf_burst']}",
                 "flops_per_launch": fl / len(conv), "avg_launch_ms": t_nets / len(conv) * 1e3, "launches": len(conv),
                 "nets_ms": t_nets * 1e3, "aux_ms_per_op_events": t_aux * 1e3, "traffic": traffic,
-                "traffic_source": "profiles/conv_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" if traffic else None}
+                "traffic_source": "profiles/conv_dram_traffic.json <- profiles/r02_counters_b64.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" if traffic else None}
         slow = sorted(prof, key=lambda p: -p["ms"])[:8]
         extra["top_ops"] = [{"op": f"{p['net']}[{p['i']}] {p['desc']}", "ms": round(p["ms"], 4),
                              "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["flops"] else None,
