@@ -10,9 +10,9 @@ ncu --profile-from-start off --metrics $M2 --clock-control none --csv --log-file
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'resize|yolo_decode|crop_resize|heatmap_decode|pnp_|pack_records' -o $O/r02_stage_kernels python scripts/ncu_step.py 64 > $O/r02_ncu3.log 2>&1
 # conv: the grouped stem (launch 1 of the detector), a CTA-pair 3x3 layer, a 20x16 1x1 layer of the key-point net
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_umma -c 1 -o $O/r02_conv_stem python scripts/ncu_step.py 64 > $O/r02_ncu4.log 2>&1
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'conv_umma_kernel<256, 64, 5, 2' -s 6 -c 1 -o $O/r02_conv_pair python scripts/ncu_step.py 64 > $O/r02_ncu5.log 2>&1
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'conv_umma_kernel<256, 64, 3, 1' -s 60 -c 2 -o $O/r02_conv_1x1 python scripts/ncu_step.py 64 > $O/r02_ncu6.log 2>&1
-for f in r02_stage_kernels r02_conv_stem r02_conv_pair r02_conv_1x1; do
+# one FastPose 20x16 bottleneck: CTA-pair 3x3 256->256, 1x1 256->1024 + residual, 1x1 1024->256 (ops 60..62 of the key-point net)
+NCU_OPS=kpd:60:63 ncu --profile-from-start off --set full --clock-control none --import-source on -o $O/r02_kpd_bottleneck python scripts/ncu_step.py 64 > $O/r02_ncu5.log 2>&1
+for f in r02_stage_kernels r02_conv_stem r02_kpd_bottleneck; do
   ncu -i $O/$f.ncu-rep --page raw --csv > $O/$f.raw.csv 2>/dev/null
 done
 ls -la $O/r02_*
