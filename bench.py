@@ -869,8 +869,8 @@ def bench_configs3(args, world, rank, dev, timed, Gather):
     t_build = time.time()
     blocks = yolo_cfg.parse_cfg_text(yolo_cfg.default_cfg_text())
     ys0, ks0 = synth.cached_yolo_weights(1000), synth.cached_kpd_state_dict(2000)
-    eng = BetaposeEngine(Bm, [synth.variant_yolo_weights(ys0, v, blocks) for v in range(13)],
-                         [synth.variant_kpd_state_dict(ks0, v) for v in range(13)], linemod13_kp_models())
+    eng = BetaposeEngine(Bm, [(lambda v=v: synth.variant_yolo_weights(ys0, v, blocks)) for v in range(13)],
+                         [(lambda v=v: synth.variant_kpd_state_dict(ks0, v)) for v in range(13)], linemod13_kp_models())
     t_build = time.time() - t_build
     frames = torch.from_numpy(synth.synth_frames(Bm, seed=300 + rank)).to(dev)
     rng = np.random.default_rng(13 + rank)

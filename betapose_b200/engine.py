@@ -31,8 +31,9 @@ class BetaposeEngine:
                  left_number: int = 50, conf: float = 0.01, pnp_mode: int = stages.MODE_RANSAC, reproj_thr: float = 12.0,
                  n_hyp: int = 64, seed: int = 0, cam_K=stages.CAM_K, device=None, concurrent_slots: bool | None = None):
         """yolo_streams: fp32 darknet weight stream (or list, one per object slot); kpd_state_dicts: FastPose
-        state_dict (or list); either may be a weights.PackedWeights (packed-weight cache) instead; kp3d: float64 [K,3]
-        (or [n_slots,K,3]) key-point model in metres."""
+        state_dict (or list); either may be a weights.PackedWeights (packed-weight cache) instead, or a zero-argument
+        callable returning one (evaluated when the slot is built); kp3d: float64 [K,3] (or [n_slots,K,3]) key-point model
+        in metres."""
         _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.B = int(max_batch)
@@ -59,7 +60,14 @@ class BetaposeEngine:
         self.heads: list[list[dict]] = []
         self.hm_id: list[int] = []
         with torch.cuda.device(self.device):
+            yolo_streams, kpd_state_dicts = list(yolo_streams), list(kpd_state_dicts)
             for s in range(self.n_slots):
+                # a slot's weights may be given as a zero-argument callable: produced when the slot is built and released
+                # right after the upload (13 objects x ~0.5 GB of fp32 parameters need not sit in host memory at once)
+                if callable(yolo_streams[s]):
+                    yolo_streams[s] = yolo_streams[s]()
+                if callable(kpd_state_dicts[s]):
+                    kpd_state_dicts[s] = kpd_state_dicts[s]()
                 shared = None if self.concurrent_slots else (self.yolo[0] if s else None)
                 y = _net.Net(self.B, reso, reso, _lib.IN_RAW255, share=shared, device=self.device.index)
                 if isinstance(yolo_streams[s], _weights.PackedWeights):  # packed-weight cache: shapes from the cfg, data as packed
@@ -81,6 +89,7 @@ class BetaposeEngine:
                 if getattr(k, "packed", None) is not None:
                     _net.packed_exhausted(k.packed)
                 self.kpd.append(k)
+                yolo_streams[s] = kpd_state_dicts[s] = None  # release the host copy of this slot's parameters
             # measured tile plans for this batch size, where a table exists (betapose_b200/tune.py)
             from . import tune as _tune
 
