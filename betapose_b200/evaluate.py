@@ -117,8 +117,18 @@ def main(argv=None):
         from .ingest import FrameIngest
 
         ingest = FrameIngest(o.ingest_threads, o.frame_h, o.frame_w)
-        stream = ingest.batches(names[lo:hi], B, depth=o.ingest_depth)
-    for rec in eng.run_stream(stream, graph=True, image_index0=lo):
+        stream = ingest.batches(names[lo:hi], B, depth=o.ingest_depth, in_flight=max(1, o.lanes))
+    # two batches in flight on the GPU (engine.py: PipelinedEngine) unless --lanes 1; the second lane is a second engine
+    # with its own activation buffers, created only when there is more than one batch to run
+    runner = eng
+    if o.lanes > 1 and (hi - lo) > B:
+        from .engine import PipelinedEngine
+
+        runner = PipelinedEngine.from_engines([eng] + [
+            BetaposeEngine(B, yolo_stream, kpd_sd, kp3d, reso=int(o.inp_dim), inp_h=o.inputResH, inp_w=o.inputResW, n_kp=o.nClasses,
+                           left_number=left, conf=o.confidence, pnp_mode=mode, cfg_blocks=blocks, frame_h=o.frame_h, frame_w=o.frame_w,
+                           cam_K=cam_K) for _ in range(o.lanes - 1)])
+    for rec in runner.run_stream(stream, graph=True, image_index0=lo):
         recs.append(rec)
     if ingest is not None:
         ingest.close()

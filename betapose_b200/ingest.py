@@ -126,14 +126,16 @@ class FrameIngest:
             out = np.empty((len(paths), self.H, self.W, 3), np.uint8)
         return self.wait(self.submit(paths, out))
 
-    def batches(self, paths, batch: int, depth: int = 2):
+    def batches(self, paths, batch: int, depth: int = 2, in_flight: int = 1):
         """Yield uint8 [n <= batch, H, W, 3] host tensors (pinned when CUDA is present) for consecutive slices of `paths`,
-        with up to `depth` later batches decoding in the pool meanwhile.  A yielded tensor stays valid until two more
-        batches have been requested -- what BetaposeEngine.run_stream needs: it may still be uploading batch k+1 when it
-        asks for batch k+2, and has finished with batch k by then."""
+        with up to `depth` later batches decoding in the pool meanwhile.  A yielded tensor stays valid until `in_flight + 1`
+        more batches have been requested -- what run_stream needs with `in_flight` lanes (engine.py: PipelinedEngine; 1 for a
+        plain BetaposeEngine): when it asks for batch k it may still be uploading batches k - in_flight .. k - 1 and has
+        synchronised on everything older."""
         paths = list(paths)
         starts = list(range(0, len(paths), batch))
-        n_buf = min(len(starts), depth + 3)
+        in_flight = max(1, int(in_flight))
+        n_buf = min(len(starts), depth + in_flight + 2)
         # the pinned ring is kept between calls (pinning ~60 MB buffers costs tens of ms each): one stream at a time
         if getattr(self, "_streaming", False):
             raise _lib.BetaposeError("FrameIngest.batches: a previous stream of this FrameIngest is still being consumed")
@@ -155,7 +157,7 @@ class FrameIngest:
                 fr = self.wait(tickets.pop(j))
                 nxt = j + depth + 1
                 if nxt < len(starts):
-                    submit(nxt)  # reuses the buffer of batch nxt - (depth + 3) = j - 2: the caller is done with it (see above)
+                    submit(nxt)  # reuses the buffer of batch nxt - n_buf = j - in_flight - 1: the caller is done with it (see above)
                 yield fr
         finally:
             for t in tickets.values():  # abandoned early: let queued decodes finish before their buffers can be reused

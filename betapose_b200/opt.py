@@ -57,6 +57,7 @@ def build_parser() -> argparse.ArgumentParser:
                    help="directory for packed-weight files (BN folded, fp16, kernel order): packed once, memory-mapped afterwards")
     p.add_argument("--ingest_threads", type=int, default=0, help="frame decoder threads (0 = one per hardware thread)")
     p.add_argument("--ingest_depth", type=int, default=2, help="batches decoded ahead of the GPU")
+    p.add_argument("--lanes", type=int, default=2, help="batches in flight on the GPU (engine.py: PipelinedEngine); 1 = one at a time")
     return p
 
 

@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 def engine(yolo_stream, kpd_sd, kp_model):
     from betapose_b200.engine import BetaposeEngine
 
-    return BetaposeEngine(8, yolo_stream, kpd_sd, kp_model, seed=5)
+    e = BetaposeEngine(8, yolo_stream, kpd_sd, kp_model, seed=5)
+    e._test_weights = (yolo_stream, kpd_sd, kp_model)
+    return e
 
 
 def test_engine_stagewise_parity(engine, frames8, kp_model):
@@ -197,6 +199,16 @@ def test_run_stream_from_png_files_through_the_native_ingest(engine, frames8, tm
         assert len(got) == len(ref) == 19
         for f in got.dtype.names:
             assert np.array_equal(got[f], ref[f]), (depth, f)
+    # two lanes: the ring must keep the last two batches intact while they upload (FrameIngest.batches(in_flight=2))
+    from betapose_b200.engine import BetaposeEngine, PipelinedEngine
+
+    second = BetaposeEngine(engine.B, engine._test_weights[0], engine._test_weights[1], engine._test_weights[2], seed=engine.seed)
+    pipe = PipelinedEngine.from_engines([engine, second])
+    with FrameIngest(3) as ing:
+        got = np.concatenate(list(pipe.run_stream(ing.batches(paths, 2, depth=1, in_flight=2), graph=True, image_index0=5)))
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], ref[f]), ("two lanes", f)
+    del pipe, second
 
 
 def test_engine_from_packed_weight_cache_is_bit_identical(engine, yolo_stream, kpd_sd, kp_model, frames8, tmp_path):

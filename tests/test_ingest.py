@@ -219,16 +219,16 @@ def test_batches_generator_order_overlap_and_buffer_lifetime(tmp_path):
         Image.fromarray(ims[i]).save(p, compress_level=1)
         paths.append(p)
     for depth in (0, 1, 2, 5):
-        with FrameIngest(3, H, W) as g:
-            held = []
-            for j, fr in enumerate(g.batches(paths, B, depth=depth)):
-                lo = j * B
-                assert np.array_equal(fr.numpy(), ims[lo: lo + B])
-                held.append((fr, lo))
-                if len(held) > 1:  # the previous batch is still intact after this one was requested
-                    pf, plo = held[-2]
-                    assert np.array_equal(pf.numpy(), ims[plo: plo + B])
-            assert j == (n + B - 1) // B - 1
+        for in_flight in (1, 2, 3):  # lanes of the consumer (PipelinedEngine): the last `in_flight` batches may still be uploading
+            with FrameIngest(3, H, W) as g:
+                held = []
+                for j, fr in enumerate(g.batches(paths, B, depth=depth, in_flight=in_flight)):
+                    lo = j * B
+                    assert np.array_equal(fr.numpy(), ims[lo: lo + B])
+                    held.append((fr, lo))
+                    for pf, plo in held[-1 - in_flight:-1]:  # the previous `in_flight` batches are still intact
+                        assert np.array_equal(pf.numpy(), ims[plo: plo + B])
+                assert j == (n + B - 1) // B - 1
 
 
 def test_library_exports_the_ingest_symbols():
