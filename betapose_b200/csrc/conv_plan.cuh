@@ -34,6 +34,9 @@ struct ConvDesc {
   int force_stages = 0;   // kept for the harness; the stage count follows from the tile configuration
   int num_sms = 148;
   bool pdl = true;        // launch with programmatic stream serialisation (off for nets that share the GPU, bp_net_set_share)
+  float* sk_ws = nullptr;        // stream-K workspace (>= num_sms slots of 128 x 256 fp32) and flags (>= num_sms), owned by the net;
+  unsigned* sk_flags = nullptr;  // null = stream-K off
+  int force_sk = 0;              // 0 = heuristic, 1 = off, 2 = on (where supported)
   double real_k = 0;      // reduction length that counts as work (0 = R*S*C); the stems pad K with zero weights
 };
 
@@ -45,20 +48,21 @@ struct ConvPlan {
   ConvArgs args;
   int block_n = 0, block_k = 0, stages = 0, grid = 0, cg = 1, mt = 1;
   bool pdl = true;
+  bool streamk = false;
   int P = 0, Q = 0;
   double flops = 0;
 };
 
-template <int BN, int BK, int ST, int CG = 1, int NB = 4, int MT = 1>
+template <int BN, int BK, int ST, int CG = 1, int NB = 4, int MT = 1, int SK = 0>
 inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, BK, ST, CG, NB, MT>;
+  using Cfg = ConvCfg<BN, BK, ST, CG, NB, MT, SK>;
   static bool attr_done[64] = {};  // per instantiation and per device (the attribute belongs to the device's context)
   {
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
     if (!attr_done[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<BN, BK, ST, CG, NB, MT, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::SMEM_BYTES);
       if (e != cudaSuccess) return e;
       attr_done[dev] = true;
@@ -88,12 +92,18 @@ inline cudaError_t launch_cfg(const ConvPlan& pl, cudaStream_t st) {
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB, MT>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, BK, ST, CG, NB, MT, SK>, pl.tmA, pl.tmB, pl.tmOut, pl.tmRes, pl.args);
 }
 
 // is there a kernel instantiation for this plan?  (mirrors the dispatch in conv_plan_launch)
+// stream-K instantiations: the two 256-wide kernels (single CTA and CTA pairs) and the 128-wide single-CTA kernel
+inline bool conv_plan_streamk_supported(int bn, int bk, int cg, int mt) {
+  return mt == 1 && bk == 64 && ((bn == 256 && (cg == 1 || cg == 2)) || (bn == 128 && cg == 1));
+}
+
 inline bool conv_plan_supported(const ConvPlan& pl) {
   const int bn = pl.block_n, bk = pl.block_k;
+  if (pl.streamk && !conv_plan_streamk_supported(bn, bk, pl.cg, pl.mt)) return false;
   if (pl.cg == 2) return bk == 64 && (bn == 256 || bn == 128);
   if (pl.mt == 4) return (bn == 64 && bk == 32) || (bn == 32 && bk == 32) || (bn == 32 && bk == 64);
   if (pl.mt == 2) return (bk == 64 && (bn == 128 || bn == 64 || bn == 32)) || (bk == 32 && (bn == 64 || bn == 32));
@@ -111,6 +121,12 @@ inline bool conv_plan_supported(const ConvPlan& pl) {
 constexpr int kNbTight = BP_NB_TIGHT;
 
 inline cudaError_t conv_plan_launch(const ConvPlan& pl, cudaStream_t st) {
+  if (pl.streamk) {
+    if (pl.cg == 2 && pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 5, 2, kNbTight, 1, 1>(pl, st);
+    if (pl.cg == 1 && pl.mt == 1 && pl.block_n == 256 && pl.block_k == 64 && pl.stages == 3) return launch_cfg<256, 64, 3, 1, 4, 1, 1>(pl, st);
+    if (pl.cg == 1 && pl.mt == 1 && pl.block_n == 128 && pl.block_k == 64 && pl.stages == 5) return launch_cfg<128, 64, 5, 1, kNbTight, 1, 1>(pl, st);
+    return cudaErrorInvalidConfiguration;
+  }
   if (pl.cg == 2) {
     if (pl.block_n == 256 && pl.block_k == 64) return launch_cfg<256, 64, 5, 2, kNbTight>(pl, st);
     if (pl.block_n == 128 && pl.block_k == 64) return launch_cfg<128, 64, 6, 2>(pl, st);
@@ -232,6 +248,21 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   // persistent: one CTA per SM (pairs: one cluster of 2 per TPC)
   pl->grid = cg == 2 ? 2 * std::min(((m_tiles + 1) / 2) * n_tiles_live, d.num_sms / 2) : std::min(m_tiles_cta * n_tiles_live, d.num_sms);
   pl->flops = 2.0 * M * (double)d.Cout * (d.real_k > 0 ? d.real_k : (double)K);
+  // Stream-K (conv_tcgen05.cuh: SkPlan): when the tiles do not fill the last round of the persistent grid, cut the (tile,
+  // k-block) units into one contiguous range per cluster.  Worth it when the k-blocks saved per cluster outweigh the
+  // hand-over of one partial accumulator (128 x BLOCK_N fp32 written by one CTA and read by its neighbour, ~2 x 128 KB
+  // through L2 for BLOCK_N = 256, i.e. about 5 (single CTA) to 8 (pairs) k-blocks' worth of staging traffic).
+  pl->streamk = false;
+  if (d.sk_ws && d.sk_flags && d.force_sk != 1 && conv_plan_streamk_supported(bn, block_k, cg, mt)) {
+    const long units = cg == 2 ? d.num_sms / 2 : d.num_sms;
+    const long tiles = (long)((m_tiles + cg - 1) / cg) * n_tiles_live;
+    if (tiles >= units && units > 1) {
+      const long rounds = (tiles + units - 1) / units;
+      const double saved = (double)rounds * num_kb - (double)tiles * num_kb / units;  // k-blocks per cluster
+      const double handover = 2.0 * 128 * bn * 4 / (double)((128 + bn / cg) * block_k * 2);
+      if (d.force_sk == 2 || saved >= 1.5 * handover + 2.0) pl->streamk = true;
+    }
+  }
 
   ConvArgs& a = pl->args;
   a.M = M;
@@ -271,6 +302,10 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.bias = d.bias;
   a.res = d.res;
   a.out = d.out;
+  a.sk_ws = d.sk_ws;
+  a.sk_flags = d.sk_flags;
+  static const int sk_align = getenv("BP_SK_ALIGN") ? atoi(getenv("BP_SK_ALIGN")) : 0;
+  a.sk_align = sk_align;
 
   if (matrix) {
     if (!make_tmap_2d(api, &pl->tmA, d.x, (uint64_t)M, (uint64_t)d.C, (uint64_t)d.x_pitch, mt == 4 ? 256 : 128 * mt, block_k, err))

@@ -58,6 +58,50 @@ struct ConvArgs {
   const float* bias;   // [n_tiles * BLOCK_N], zero padded
   const __half* res;   // residual, same pixel order as the output, res_pitch elements per pixel
   void* out;
+  // stream-K (SK kernels): fp32 partial accumulators [clusters * CG][128][BLOCK_N] and one hand-over flag per slot
+  float* sk_ws;
+  unsigned* sk_flags;
+  int sk_align;  // experiment switch (BP_SK_ALIGN): whole-tile ranges
+};
+
+// ---- stream-K work split (SK kernels).  The (tile, k-block) units of a launch are cut into one CONTIGUOUS range per cluster
+// instead of whole tiles dealt round-robin, so a launch of 160 tiles on 148 SMs takes 1.08 tile times instead of 2.  A range
+// covers the tail [k_first, Kb) of its first tile, whole tiles, and the head [0, k_last_end) of its last tile; a tile is
+// split between at most two neighbouring clusters (the planner only enables this when tiles >= clusters).  Order inside a
+// cluster: the HEAD of the last tile first (its raw fp32 accumulator is stored to the workspace and a flag released), then
+// the whole tiles, and last the TAIL of the first tile -- its accumulator is first LOADED with the neighbour's partial
+// (tcgen05.st), so the MMAs of the remaining k-blocks add onto it exactly as if one CTA had run the whole reduction: the
+// result is bit-identical to the unsplit kernel, and the partial it needs was the first thing the neighbour produced.
+enum : int { SK_FULL = 0, SK_STORE = 1, SK_LOAD = 2 };
+struct SkSeg {
+  int tile, kb0, kb1, mode;
+};
+struct SkPlan {
+  int nA, tf0, nfull, nZ, t_first, k_first, t_last, k_last_end, Kb;
+  __device__ __forceinline__ SkPlan(int c, int G, int T, int Kb_, int align_tiles = 0) : Kb(Kb_) {
+    const long U = (long)T * Kb_;
+    long u0 = (long)c * U / G, u1 = (long)(c + 1) * U / G;
+    if (align_tiles) {  // experiment: contiguous ranges of WHOLE tiles (no split), to separate the effect of the tile order
+      u0 = ((long)c * T / G) * Kb_;
+      u1 = ((long)(c + 1) * T / G) * Kb_;
+    }
+    t_first = (int)(u0 / Kb_);
+    k_first = (int)(u0 - (long)t_first * Kb_);
+    t_last = (int)((u1 - 1) / Kb_);
+    k_last_end = (int)(u1 - (long)t_last * Kb_);
+    nZ = k_first > 0 ? 1 : 0;
+    nA = k_last_end < Kb_ ? 1 : 0;
+    tf0 = t_first + nZ;
+    nfull = (t_last - nA) - tf0 + 1;
+    if (u1 <= u0) nA = nZ = nfull = 0;
+  }
+  __device__ __forceinline__ int count() const { return nA + nfull + nZ; }
+  __device__ __forceinline__ SkSeg seg(int i) const {
+    if (i < nA) return SkSeg{t_last, 0, k_last_end, SK_STORE};
+    i -= nA;
+    if (i < nfull) return SkSeg{tf0 + i, 0, Kb, SK_FULL};
+    return SkSeg{t_first, k_first, Kb, SK_LOAD};
+  }
 };
 
 __device__ __forceinline__ int fast_div(int x, unsigned long long mul) {
@@ -83,7 +127,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // MT = 2: a CTA tile is 256 pixels = two M = 128 MMAs per K step against the same B (two accumulators); one TMA load
 // stages 256 A rows.  Halves the tile count -- and with it the producer / MMA warps' per-tile and per-k-block
 // instruction overhead per pixel -- on the narrow (BLOCK_N <= 64) layers, which are bound by exactly that.
-template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1, int SK = 0>
 struct ConvCfg {
   static constexpr int BLOCK_M = 128 * MT;
   static constexpr int SWZ = BLOCK_K * 2;  // bytes per smem row == swizzle span
@@ -100,7 +144,7 @@ struct ConvCfg {
   // The kernel has NO static shared memory, so the dynamic window starts at the (1024-byte aligned) base of the CTA's
   // shared memory and the swizzled tiles need no alignment slack: [stages][epilogue ring][bias x2][mbarriers].
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4 + NBUF) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + NBUF + SK) * 8 + 16;  // SK: + the "accumulator loaded" barrier
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
@@ -188,12 +232,13 @@ __device__ __forceinline__ void epi_dispatch(int act, int res_mode, const uint32
 #undef BP_EPI
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1, int SK = 0>
 __global__ void __launch_bounds__(320, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
-  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB, MT>;
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB, MT, SK>;
+  static_assert(SK == 0 || MT == 1, "stream-K: 128-pixel tiles only");
   static_assert(MT == 1 || ((MT == 2 || MT == 4) && CG == 1 && 2 * MT * BLOCK_N <= 512), "256 / 512-pixel tiles: single-CTA layers, 2 x MT accumulators in TMEM");
   static_assert(CG == 1 || (CG == 2 && BLOCK_N >= 64), "pairs need BLOCK_N >= 64");
   static_assert(BLOCK_N == 32 || BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
@@ -209,7 +254,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* res_full_bar = tmem_empty_bar + 2;
-  uint32_t* tmem_base_slot_p = reinterpret_cast<uint32_t*>(res_full_bar + Cfg::NBUF);
+  uint64_t* acc_init_bar = res_full_bar + Cfg::NBUF;  // SK only: the epilogue has put a partial accumulator into TMEM
+  uint32_t* tmem_base_slot_p = reinterpret_cast<uint32_t*>(res_full_bar + Cfg::NBUF + SK);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -244,6 +290,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 #pragma unroll
     for (int s = 0; s < Cfg::NBUF; ++s) mbar_init(&res_full_bar[s], 1);
+    if constexpr (SK) mbar_init(acc_init_bar, Cfg::EPI_WARPS * CG);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -257,6 +304,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   griddep_wait();  // from here on the previous kernel's outputs (our activations / residual) are complete and visible
   const uint32_t tmem_base = *tmem_base_slot_p;
+  // tile walk: round-robin whole tiles, or (SK) the segments of this cluster's contiguous unit range
+  const SkPlan skp(cl_id, cl_num, total_tiles, p.num_kb, p.sk_align);
+  const int n_walk = SK ? skp.count() : (cl_id < total_tiles ? (total_tiles - cl_id + cl_num - 1) / cl_num : 0);
+  auto walk = [&](int i) -> SkSeg {
+    if constexpr (SK) return skp.seg(i);
+    else return SkSeg{cl_id + i * cl_num, 0, p.num_kb, SK_FULL};
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one thread: the loop is pure issue
@@ -265,7 +319,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
       uint32_t s = 0, ph = 0;
-      for (int tile = cl_id; tile < total_tiles; tile += cl_num) {
+      for (int wi = 0; wi < n_walk; ++wi) {
+        const SkSeg sg = walk(wi);
+        const int tile = sg.tile;
         const int pm_tile = fast_div(tile, p.mul_nt);
         const int n0 = (tile - pm_tile * p.n_tiles) * BLOCK_N + int(rank) * (BLOCK_N / CG);  // this CTA's share of B
         const int m0 = (pm_tile * CG + int(rank)) * Cfg::BLOCK_M;
@@ -291,7 +347,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         int cb = 0, fr = 0, fs = 0, kcol = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        if constexpr (SK) {
+          if (sg.kb0) {  // the reduction of this segment starts at k-block kb0: (filter row, filter column, channel block) there
+            kcol = sg.kb0 * BLOCK_K;
+            const int tap = sg.kb0 / p.cblocks;
+            cb = (sg.kb0 - tap * p.cblocks) * BLOCK_K;
+            fr = tap / p.S;
+            fs = tap - fr * p.S;
+          }
+        }
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait_a(empty0 + 8u * s, ph ^ 1u);
           const uint32_t sa = smem_base + s * uint32_t(Cfg::STAGE_BYTES);
           const uint32_t fb = CG == 2 ? leader_addr(full0 + 8u * s) : full0 + 8u * s;
@@ -345,12 +410,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // descriptors differ between stages only in the 14-bit start-address field (smem < 256 KB: no carry out of it)
       const uint64_t da0 = umma_smem_desc<Cfg::SWZ>(smem_u32(smem));
       uint32_t s = 0, ph = 0, it = 0;
-      for (int tile = cl_id; tile < total_tiles; tile += cl_num, ++it) {
+      for (int wi = 0; wi < n_walk; ++wi, ++it) {
+        const SkSeg sg = walk(wi);
         const uint32_t acc = it & 1u;
         mbar_wait_a(tempty0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue(s) drained this accumulator
+        if constexpr (SK) {
+          if (sg.mode == SK_LOAD) mbar_wait_a(smem_u32(acc_init_bar), 0u);  // ... and loaded it with the neighbour's partial (once per launch)
+        }
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * uint32_t(MT * BLOCK_N);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int kb_first = (SK && sg.mode == SK_LOAD) ? -1 : sg.kb0;  // k-block whose first MMA overwrites the accumulator
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait_a(full0 + 8u * s, ph);
           tc_fence_after();
           const uint64_t da = da0 + uint64_t(s * uint32_t(Cfg::STAGE_BYTES >> 4));
@@ -358,7 +428,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
           if (elect_one()) {
             if constexpr (CG == 2) {
-              umma_f16_cg2(tmem_acc, da, db, idesc, kb ? 1u : 0u);
+              umma_f16_cg2(tmem_acc, da, db, idesc, kb != kb_first ? 1u : 0u);
 #pragma unroll
               for (int k = 1; k < BLOCK_K / 16; ++k)
                 umma_f16_cg2(tmem_acc, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, 1u);
@@ -369,7 +439,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int sub = 0; sub < MT; ++sub)
                   umma_f16(tmem_acc + uint32_t(sub * BLOCK_N), da + uint64_t(2 * k + sub * (Cfg::A_SUB_BYTES >> 4)),
-                           db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+                           db + uint64_t(2 * k), idesc, (kb != kb_first || k) ? 1u : 0u);
               }
               umma_commit_a(empty0 + 8u * s);  // frees this smem stage once the MMAs above have read it
             }
@@ -398,17 +468,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool use_res = p.res_mode != RES_NONE;
     int it = 0;
     uint32_t chunk_ctr = 0;                  // running chunk index: ring buffer = chunk_ctr % NBUF
-    float bias_next = (cl_id < total_tiles && et < BLOCK_N) ? __ldg(p.bias + (cl_id % p.n_tiles) * BLOCK_N + et) : 0.f;
+    float bias_next = (n_walk > 0 && et < BLOCK_N) ? __ldg(p.bias + (walk(0).tile % p.n_tiles) * BLOCK_N + et) : 0.f;
     const uint32_t tfull_wait0 = smem_u32(&tmem_full_bar[0]);
     const uint32_t tempty_arrive0 = CG == 2 ? leader_addr(smem_u32(&tmem_empty_bar[0])) : smem_u32(&tmem_empty_bar[0]);
     // Residual tiles arrive by TMA in the ring buffers the results later leave from.  The leader runs a prefetch
     // cursor NBUF - 1 chunks ahead of the chunk being computed, across tile boundaries: right after the store of chunk
     // g is committed, `wait_group.read 1` guarantees the store of chunk g - 1 has read its buffer, which is the buffer
     // of chunk g - 1 + NBUF, and that chunk's residual load is issued -- about three chunk times before it is needed.
-    int pf_tile = cl_id, pf_sub = 0, pf_c = 0, pf_n0 = 0, pf_m0 = 0, pf_live = 0;
+    int pf_wi = 0, pf_sub = 0, pf_c = 0, pf_n0 = 0, pf_m0 = 0, pf_live = 0;  // cursor over the walk (segments with an output)
     uint32_t pf_g = 0;  // global index of the next chunk to prefetch
     auto pf_decode = [&]() {
-      if (pf_tile < total_tiles) {
+      if constexpr (SK) {
+        while (pf_wi < n_walk && walk(pf_wi).mode == SK_STORE) ++pf_wi;  // a stored partial has no epilogue output, no residual
+      }
+      if (pf_wi < n_walk) {
+        const int pf_tile = walk(pf_wi).tile;
         const int pm = fast_div(pf_tile, p.mul_nt);
         pf_n0 = (pf_tile - pm * p.n_tiles) * BLOCK_N;
         pf_m0 = (pm * CG + int(rank)) * Cfg::BLOCK_M;
@@ -416,7 +490,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     auto pf_issue = [&]() {  // leader only: load the residual of chunk pf_g (if there is one) and advance the cursor
-      if (pf_tile >= total_tiles) return;
+      if (pf_wi >= n_walk) return;
       const uint32_t rb = pf_g % Cfg::NBUF;
       mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
       tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, pf_n0 + pf_c * CHUNK, pf_m0 + pf_sub * 128);
@@ -425,7 +499,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pf_c = 0;
         if (++pf_sub == MT) {
           pf_sub = 0;
-          pf_tile += cl_num;
+          ++pf_wi;
           pf_decode();
         }
       }
@@ -434,7 +508,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       pf_decode();
       for (int i = 0; i < Cfg::NBUF - 1; ++i) pf_issue();
     }
-    for (int tile = cl_id; tile < total_tiles; tile += cl_num, ++it) {
+    for (int wi = 0; wi < n_walk; ++wi, ++it) {
+      const SkSeg sg = walk(wi);
+      const int tile = sg.tile;
       const int pm_tile = fast_div(tile, p.mul_nt);
       const int n_tile = tile - pm_tile * p.n_tiles;
       const int m0 = (pm_tile * CG + int(rank)) * Cfg::BLOCK_M;
@@ -442,18 +518,82 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const int live = min(N_CHUNKS, (p.Cout - n0 + CHUNK - 1) / CHUNK);  // chunks holding real channels
+      const uint32_t tmem_acc0 = tmem_base + uint32_t(acc * MT * BLOCK_N) + ((uint32_t(q4) * 32u) << 16);
+
+      if constexpr (SK) {
+        // workspace slot layout [32-column group][float4 index j][row][4]: every warp-wide 16-byte access is 512 contiguous bytes
+        if (sg.mode == SK_LOAD) {
+          // the tail of a split tile: put the neighbour's partial accumulator (k-blocks [0, kb0)) into TMEM, then let the MMA
+          // warp add the remaining k-blocks onto it.  This accumulator buffer was drained two segments ago by this epilogue.
+          const int src = (cl_id - 1) * CG + int(rank);
+          if (leader) {
+            while (ld_acquire_gpu(p.sk_flags + src) == 0u) __nanosleep(64);
+            p.sk_flags[src] = 0u;  // consumed: ready for the next launch
+          }
+          bar_sync_named(1, Cfg::EPI_THREADS);
+          __threadfence();
+          const float4* wsrc = reinterpret_cast<const float4*>(p.sk_ws) + (size_t)src * (BLOCK_N / 32) * 8 * 128;
+#pragma unroll 1
+          for (int c = hsel; c < BLOCK_N / 32; c += 2) {
+            uint32_t a[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = __ldcg(wsrc + ((size_t)c * 8 + j) * 128 + row_l);
+              a[4 * j] = __float_as_uint(v.x); a[4 * j + 1] = __float_as_uint(v.y);
+              a[4 * j + 2] = __float_as_uint(v.z); a[4 * j + 3] = __float_as_uint(v.w);
+            }
+            tmem_st_32x32(tmem_acc0 + uint32_t(c * 32), a);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster_a(leader_addr(smem_u32(acc_init_bar)));
+            else mbar_arrive(acc_init_bar);
+          }
+        }
+      }
 
       float* bias_s = s_bias[it & 1];
       if (et < BLOCK_N) bias_s[et] = bias_next;
       {  // bias of the next tile: in flight during this tile's epilogue
-        const int nt = tile + cl_num;
-        if (nt < total_tiles && et < BLOCK_N) bias_next = __ldg(p.bias + (nt - fast_div(nt, p.mul_nt) * p.n_tiles) * BLOCK_N + et);
+        if (wi + 1 < n_walk && et < BLOCK_N) {
+          const int nt = walk(wi + 1).tile;
+          bias_next = __ldg(p.bias + (nt - fast_div(nt, p.mul_nt) * p.n_tiles) * BLOCK_N + et);
+        }
       }
       bar_sync_named(1, Cfg::EPI_THREADS);  // bias visible
 
       mbar_wait_a(tfull_wait0 + 8u * acc, acc_ph);
       tc_fence_after();
-      const uint32_t tmem_acc0 = tmem_base + uint32_t(acc * MT * BLOCK_N) + ((uint32_t(q4) * 32u) << 16);
+
+      if constexpr (SK) {
+        if (sg.mode == SK_STORE) {
+          // the head of a split tile: leave the raw fp32 accumulator (k-blocks [0, kb1)) in this CTA's workspace slot
+          const int dst = cl_id * CG + int(rank);
+          float4* wdst = reinterpret_cast<float4*>(p.sk_ws) + (size_t)dst * (BLOCK_N / 32) * 8 * 128;
+#pragma unroll 1
+          for (int c = hsel; c < BLOCK_N / 32; c += 2) {
+            uint32_t a[32];
+            tmem_ld_32x32(tmem_acc0 + uint32_t(c * 32), a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              __stcg(wdst + ((size_t)c * 8 + j) * 128 + row_l,
+                     make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]), __uint_as_float(a[4 * j + 3])));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster_a(tempty_arrive0 + 8u * acc);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          __threadfence();
+          bar_sync_named(1, Cfg::EPI_THREADS);
+          if (leader) st_release_gpu(p.sk_flags + dst, 1u);
+          continue;
+        }
+      }
 
       if (p.tma_store) {
 #pragma unroll 1

@@ -61,6 +61,8 @@ struct bp_net {
   size_t act_cursor = 0;
   double flops = 0;
   int share_batch = 0;  // > 0: runs concurrently with other nets, see bp_net_set_share
+  float* sk_ws = nullptr;        // stream-K workspace: one 128 x 256 fp32 partial accumulator per SM (conv_plan.cuh)
+  unsigned* sk_flags = nullptr;  // ... and its hand-over flags (zero between launches)
 };
 
 static void* net_alloc_weights(bp_net* n, size_t bytes) {
@@ -123,6 +125,17 @@ int bp_net_create(bp_engine* e, int max_batch, int in_h, int in_w, int in_kind, 
     return bp_fail(BP_ERR_CUDA, "bp_net_create: cudaMalloc failed");
   }
   n->tensors.push_back(t);
+  // Stream-K (conv_tcgen05.cuh: SkPlan) is implemented, bit-exact and OFF by default: measured on B200 it does not pay
+  // (DESIGN.md 9).  BP_STREAMK=1 turns the planner's heuristic on for nets created afterwards.
+  if (getenv("BP_STREAMK") && atoi(getenv("BP_STREAMK")) > 0) {
+    const size_t slots = (size_t)e->num_sms;
+    n->sk_ws = (float*)net_alloc_weights(n, slots * 128 * 256 * sizeof(float));
+    n->sk_flags = (unsigned*)net_alloc_weights(n, slots * sizeof(unsigned));
+    if (!n->sk_ws || !n->sk_flags || cudaMemset(n->sk_flags, 0, slots * sizeof(unsigned)) != cudaSuccess) {
+      bp_net_destroy(n);
+      return bp_fail(BP_ERR_CUDA, "bp_net_create: cudaMalloc (stream-K workspace) failed");
+    }
+  }
   *out = n;
   return BP_OK;
 }
@@ -342,6 +355,8 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (n->eng->force_stages) d.force_stages = n->eng->force_stages;
 
   d.num_sms = n->eng->num_sms;
+  d.sk_ws = n->sk_ws;
+  d.sk_flags = n->sk_flags;
   Op op;
   op.kind = OP_CONV;
   op.cdesc = d;
@@ -361,6 +376,7 @@ int bp_net_conv(bp_net* n, const bp_conv_spec* s) {
   if (plan0.cg == 2) snprintf(tile, sizeof tile, " cg2");
   else if (plan0.mt > 1) snprintf(tile, sizeof tile, " mt%d", plan0.mt);
   if (grouped) snprintf(tile + strlen(tile), sizeof tile - strlen(tile), " g4");
+  if (plan0.streamk) snprintf(tile + strlen(tile), sizeof tile - strlen(tile), " sk");
   snprintf(buf, sizeof buf, "conv %dx%d/%d %d->%d @%dx%d bn%d bk%d st%d%s%s%s%s", k, k, s->stride, Cin, Cout, P, Q,
            plan0.block_n, plan0.block_k, plan0.stages, tile, s->res >= 0 ? " +res" : "",
            s->store_mode == BP_STORE_UPSAMPLE2 ? " up2" : (s->store_mode == BP_STORE_PIXSHUF2 ? " ps2" : ""),

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 CANDIDATES = [(bn, cg, mt) for bn in (256, 128, 64, 32) for (cg, mt) in ((1, 1), (2, 1), (1, 2), (1, 4))]
-_PLAN_RE = re.compile(r" bn\d+ bk\d+ st\d+( cg2| mt\d)?( g4)?")
+_PLAN_RE = re.compile(r" bn\d+ bk\d+ st\d+( cg2| mt\d)?( g4)?( sk)?")
 TUNED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned")
 
 

@@ -370,3 +370,36 @@ def test_fastpose_batch64_plans_vs_oracle(kpd_sd):
     assert _argmax_flips_within_noise(got, ref, err.max().item()) >= 0.8
     del n
     torch.cuda.empty_cache()
+
+
+def test_stream_k_is_bit_identical_to_whole_tiles(kpd_sd):
+    """Stream-K (BP_STREAMK=1: the (tile, k-block) units of a launch cut into one contiguous range per CTA, a split tile's
+    partial accumulator handed to the neighbour through a workspace and loaded back into TMEM before the remaining k-blocks
+    are added) must give the SAME BITS as whole tiles: FastPose at batch 64, where 87 launches of both networks qualify
+    (the 160-tile layers of the 20x16 stage among them).  It is off by default because it is not faster."""
+    import os
+
+    from betapose_b200 import _lib, net as bnet, stages, synth
+
+    B = 64
+    fr = torch.from_numpy(synth.synth_frames(B, seed=66)).cuda()
+    box = torch.tensor([[100.0, 80.0, 400.0, 380.0]], device="cuda").repeat(B, 1)
+    crop = stages.crop_resize(fr, box, torch.arange(B, dtype=torch.int32, device="cuda"))
+    outs = []
+    for sk in ("0", "1"):
+        os.environ["BP_STREAMK"] = sk
+        try:
+            n = bnet.Net(B, 320, 256, _lib.IN_F16)
+            hm_id = bnet.build_fastpose(n, kpd_sd, 50)
+        finally:
+            os.environ.pop("BP_STREAMK", None)
+        n.input(B).copy_(stages.net_input_pixels(crop["net"]))
+        n.forward(B)
+        n.forward(B)   # the hand-over flags must be back at zero after a launch: run twice
+        torch.cuda.synchronize()
+        descs = [n.op_desc(i)[0] for i in range(n.num_ops)]
+        assert (sum(" sk" in d for d in descs) >= 40) == (sk == "1"), descs
+        outs.append(n.tensor(hm_id, B).clone())
+        del n
+    assert torch.equal(outs[0], outs[1])
+    torch.cuda.empty_cache()
