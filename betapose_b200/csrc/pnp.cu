@@ -28,8 +28,10 @@ constexpr int kHypRow = 16;         // doubles per hypothesis in the scratch: co
 struct WarpLanes {
   __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
   __device__ __forceinline__ int count() const { return 32; }
-  __device__ __forceinline__ void allreduce(double* v, int n) const {
-    for (int i = 0; i < n; ++i) {
+  template <int N>
+  __device__ __forceinline__ void allreduce_n(double* v) const {  // N compile-time: v stays in registers
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
       double x = v[i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);

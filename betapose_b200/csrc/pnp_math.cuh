@@ -8,6 +8,15 @@
 #include <math.h>
 #include <stdint.h>
 
+// loop unrolling matters on the device only (arrays with compile-time indices live in registers); the host pass of nvcc and
+// plain g++ do not know the pragma
+#if defined(__CUDA_ARCH__)
+#define BP_UNROLL _Pragma("unroll")
+#define BP_UNROLL_SMALL(N) _Pragma("unroll")
+#else
+#define BP_UNROLL
+#define BP_UNROLL_SMALL(N)
+#endif
 #if defined(__CUDACC__)
 #define BP_HD __host__ __device__ __forceinline__
 // NOTE: these were __noinline__ at first; cicc 12.9 -O3 then merges the stack slots of the caller's local arrays that
@@ -66,7 +75,10 @@ BP_HD_NOINLINE void jacobi_eig(double* A, double* V, double* w) {
     // quadratic convergence: once the off-diagonal mass is below 1e-22 of the diagonal one more sweep reaches the
     // rounding floor
     const bool last = off <= 1e-22 * diag;
+    // N <= 4 (control-point PCA, Horn's quaternion matrix): fully unrolled, matrices in registers
+BP_UNROLL_SMALL(N)
     for (int p = 0; p < N - 1; ++p) {
+BP_UNROLL_SMALL(N)
       for (int q = p + 1; q < N; ++q) {
         const double apq = A[p * N + q];
         if (fabs(apq) < 1e-300) continue;
@@ -243,24 +255,69 @@ BP_HD bool solve_linear(double* A, double* b) {
   return true;
 }
 
+// solve the symmetric positive definite N x N system A x = b by an LDL^T factorisation, every loop unrolled at compile time
+// so that A lives in registers (solve_linear's partial pivoting indexes rows dynamically, which puts its matrix in local
+// memory: on the device that was most of a Levenberg-Marquardt iteration).  A: full symmetric matrix (only the lower
+// triangle is read), destroyed.  false if a pivot is not positive (A not positive definite).
+template <int N>
+BP_HD bool solve_spd(double* A, double* b) {
+  double d[N];
+  bool ok = true;  // (no early exit: it would keep the compiler from unrolling the column loop)
+BP_UNROLL
+  for (int j = 0; j < N; ++j) {
+    double dj = A[j * N + j];
+BP_UNROLL
+    for (int k = 0; k < j; ++k) dj -= A[j * N + k] * A[j * N + k] * d[k];
+    ok = ok && (dj > 0.0);
+    d[j] = dj;
+    const double inv = 1.0 / dj;
+BP_UNROLL
+    for (int i = j + 1; i < N; ++i) {
+      double lij = A[i * N + j];
+BP_UNROLL
+      for (int k = 0; k < j; ++k) lij -= A[i * N + k] * A[j * N + k] * d[k];
+      A[i * N + j] = lij * inv;
+    }
+  }
+BP_UNROLL
+  for (int i = 0; i < N; ++i) {  // L z = b
+BP_UNROLL
+    for (int k = 0; k < i; ++k) b[i] -= A[i * N + k] * b[k];
+  }
+BP_UNROLL
+  for (int i = 0; i < N; ++i) b[i] /= d[i];  // D y = z
+BP_UNROLL
+  for (int i = N - 1; i >= 0; --i) {  // L^T x = y
+BP_UNROLL
+    for (int k = i + 1; k < N; ++k) b[i] -= A[k * N + i] * b[k];
+  }
+  return ok;
+}
+
 // least squares  min |A x - b|  for a 6 x NC system via (ridge-stabilised) normal equations
 template <int NC>
 BP_HD bool lstsq6(const double* A /*6 x NC*/, const double* b /*6*/, double* x /*NC*/) {
   double AtA[NC * NC], Atb[NC];
   double tr = 0.0;
+BP_UNROLL
   for (int i = 0; i < NC; ++i) {
+BP_UNROLL
     for (int j = 0; j < NC; ++j) {
       double s = 0.0;
+BP_UNROLL
       for (int r = 0; r < 6; ++r) s += A[r * NC + i] * A[r * NC + j];
       AtA[i * NC + j] = s;
     }
     double s = 0.0;
+BP_UNROLL
     for (int r = 0; r < 6; ++r) s += A[r * NC + i] * b[r];
     Atb[i] = s;
     tr += AtA[i * NC + i];
   }
+BP_UNROLL
   for (int i = 0; i < NC; ++i) AtA[i * NC + i] += 1e-14 * tr + 1e-300;
-  if (!solve_linear<NC>(AtA, Atb)) return false;
+  if (!solve_spd<NC>(AtA, Atb)) return false;  // A^T A + ridge: symmetric positive definite; unrolled, in registers
+BP_UNROLL
   for (int i = 0; i < NC; ++i) x[i] = Atb[i];
   return true;
 }
@@ -542,6 +599,7 @@ BP_HD bool epnp(const double* pw_all, const double* uv_all, const int* ids, int 
 template <class Lanes>
 BP_HD void lm_accumulate(const Lanes& ln, const double* R, const double* t, const double* pw, const double* uv,
                          const uint8_t* mask, int n, double fx, double fy, double cx, double cy, double* acc /*28*/) {
+BP_UNROLL
   for (int i = 0; i < 28; ++i) acc[i] = 0.0;
   for (int i = ln.lane(); i < n; i += ln.count()) {
     if (!mask[i]) continue;
@@ -559,13 +617,16 @@ BP_HD void lm_accumulate(const Lanes& ln, const double* R, const double* t, cons
     Ju[3] = du[0]; Ju[4] = du[1]; Ju[5] = du[2];
     Jv[0] = dv[2] * qy - dv[1] * qz; Jv[1] = dv[0] * qz - dv[2] * qx; Jv[2] = dv[1] * qx - dv[0] * qy;
     Jv[3] = dv[0]; Jv[4] = dv[1]; Jv[5] = dv[2];
-    int k = 0;
+    // (a, b) -> packed upper-triangle index 6a - a(a-1)/2 + (b - a): compile-time after unrolling, so acc stays in registers
+BP_UNROLL
     for (int a = 0; a < 6; ++a)
-      for (int b = a; b < 6; ++b) acc[k++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+BP_UNROLL
+      for (int b = a; b < 6; ++b) acc[6 * a - a * (a - 1) / 2 + (b - a)] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+BP_UNROLL
     for (int a = 0; a < 6; ++a) acc[21 + a] += Ju[a] * ru + Jv[a] * rv;
     acc[27] += ru * ru + rv * rv;
   }
-  ln.allreduce(acc, 28);
+  ln.template allreduce_n<28>(acc);
 }
 
 template <class Lanes>
@@ -579,7 +640,7 @@ BP_HD double lm_cost(const Lanes& ln, const double* R, const double* t, const do
     const double ru = u - uv[2 * i], rv = v - uv[2 * i + 1];
     c += ru * ru + rv * rv;
   }
-  ln.allreduce(&c, 1);
+  ln.template allreduce_n<1>(&c);
   return c;
 }
 
@@ -619,18 +680,19 @@ BP_HD_NOINLINE void lm_refine(const Lanes& ln, double* R, double* t, const doubl
     double step = 0.0, dc = 0.0;
     for (int tr = 0; tr < 10; ++tr) {
       double A[36], g[6];
-      int k = 0;
+BP_UNROLL
       for (int a = 0; a < 6; ++a)
+BP_UNROLL
         for (int b = a; b < 6; ++b) {
-          A[a * 6 + b] = acc[k];
-          A[b * 6 + a] = acc[k];
-          ++k;
+          A[a * 6 + b] = acc[6 * a - a * (a - 1) / 2 + (b - a)];
+          A[b * 6 + a] = A[a * 6 + b];
         }
+BP_UNROLL
       for (int a = 0; a < 6; ++a) {
         A[a * 6 + a] += lam * A[a * 6 + a];
         g[a] = -acc[21 + a];
       }
-      if (!solve_linear<6>(A, g)) {
+      if (!solve_spd<6>(A, g)) {  // J^T J + lam diag(J^T J): symmetric positive definite unless the points are degenerate
         lam *= 10;
         continue;
       }
@@ -671,6 +733,8 @@ struct SingleLane {  // host / single-thread policy
   BP_HD int lane() const { return 0; }
   BP_HD int count() const { return 1; }
   BP_HD void allreduce(double*, int) const {}
+  template <int N>
+  BP_HD void allreduce_n(double*) const {}
   BP_HD void accumulate(const double* R, const double* t, const double* pw, const double* uv, const uint8_t* mask, int n,
                         double fx, double fy, double cx, double cy, double* acc) const {
     lm_accumulate(*this, R, t, pw, uv, mask, n, fx, fy, cx, cy, acc);
