@@ -38,6 +38,7 @@ struct ConvDesc {
   unsigned* sk_flags = nullptr;  // null = stream-K off
   int force_sk = 0;              // 0 = heuristic, 1 = off, 2 = on (where supported)
   double real_k = 0;      // reduction length that counts as work (0 = R*S*C); the stems pad K with zero weights
+  unsigned long long* trace = nullptr;  // bring-up harness: per-CTA clock stamps (ConvArgs::trace)
 };
 
 struct ConvPlan {
@@ -288,6 +289,11 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
                  (!d.res || d.res_pitch % 8 == 0))
                     ? 1
                     : 0;
+  static const bool no_staged = getenv("BP_NO_STAGED_STORE") != nullptr;  // experiment switch: per-thread stores as in round 1
+  a.staged_store = (!a.tma_store && !no_staged && !d.out_f32 && !d.res && d.store_mode != STORE_PLAIN && d.Cout % 8 == 0 && d.out_pitch % 8 == 0 &&
+                    d.out_coff % 8 == 0 && (d.store_mode != STORE_PIXSHUF2 || d.Cout % 32 == 0))
+                       ? 1
+                       : 0;
   a.out_pitch = d.out_pitch;
   a.out_coff = d.out_coff;
   a.res_pitch = d.res_pitch;
@@ -304,6 +310,7 @@ inline bool conv_plan_build(TmapApi& api, ConvPlan* pl, const ConvDesc& d, std::
   a.out = d.out;
   a.sk_ws = d.sk_ws;
   a.sk_flags = d.sk_flags;
+  a.trace = d.trace;
   static const int sk_align = getenv("BP_SK_ALIGN") ? atoi(getenv("BP_SK_ALIGN")) : 0;
   a.sk_align = sk_align;
 

@@ -48,6 +48,8 @@ struct ConvArgs {
   int store_mode;
   int out_f32;
   int tma_store;  // 1: dense fp16 box -> staged TMA store (+ TMA residual); 0: per-thread stores
+  int staged_store;  // 1 (only when !tma_store): fp16 result staged in the epilogue ring, written out row-wise coalesced (fused
+                     // nearest-x2 upsample / PixelShuffle); 0: every thread stores its own pixel's channels
   int out_pitch;  // elements between consecutive output pixels
   int out_coff;   // channel offset inside the output pixel
   int res_pitch;
@@ -62,7 +64,12 @@ struct ConvArgs {
   float* sk_ws;
   unsigned* sk_flags;
   int sk_align;  // experiment switch (BP_SK_ALIGN): whole-tile ranges
+  // bring-up harness only (null in the library): per CTA kTraceSlots clock64() stamps -- [0] start (after griddepcontrol.wait),
+  // [1] end, then per walked tile i < kTraceTiles: [2+4i] MMA warp may start (accumulator free), [3+4i] its first k-block has
+  // landed, [4+4i] epilogue sees the accumulator complete, [5+4i] epilogue done with the tile
+  unsigned long long* trace;
 };
+constexpr int kTraceTiles = 32, kTraceSlots = 2 + 4 * kTraceTiles;
 
 // ---- stream-K work split (SK kernels).  The (tile, k-block) units of a launch are cut into one CONTIGUOUS range per cluster
 // instead of whole tiles dealt round-robin, so a launch of 160 tiles on 148 SMs takes 1.08 tile times instead of 2.  A range
@@ -304,6 +311,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   griddep_wait();  // from here on the previous kernel's outputs (our activations / residual) are complete and visible
   const uint32_t tmem_base = *tmem_base_slot_p;
+  unsigned long long* const tr = p.trace ? p.trace + (size_t)blockIdx.x * kTraceSlots : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   // tile walk: round-robin whole tiles, or (SK) the segments of this cluster's contiguous unit range
   const SkPlan skp(cl_id, cl_num, total_tiles, p.num_kb, p.sk_align);
   const int n_walk = SK ? skp.count() : (cl_id < total_tiles ? (total_tiles - cl_id + cl_num - 1) / cl_num : 0);
@@ -418,11 +427,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (sg.mode == SK_LOAD) mbar_wait_a(smem_u32(acc_init_bar), 0u);  // ... and loaded it with the neighbour's partial (once per launch)
         }
         tc_fence_after();
+        if (tr && wi < kTraceTiles && lane == 0) tr[2 + 4 * wi] = clock64();
         const uint32_t tmem_acc = tmem_base + acc * uint32_t(MT * BLOCK_N);
         const int kb_first = (SK && sg.mode == SK_LOAD) ? -1 : sg.kb0;  // k-block whose first MMA overwrites the accumulator
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait_a(full0 + 8u * s, ph);
           tc_fence_after();
+          if (tr && wi < kTraceTiles && kb == sg.kb0 && lane == 0) tr[3 + 4 * wi] = clock64();
           const uint64_t da = da0 + uint64_t(s * uint32_t(Cfg::STAGE_BYTES >> 4));
           const uint64_t db = da + uint64_t(Cfg::A_BYTES >> 4);
           // advance 16 elements (32 B) along K inside the swizzle span: +2 in the (addr>>4) field
@@ -566,6 +577,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       mbar_wait_a(tfull_wait0 + 8u * acc, acc_ph);
       tc_fence_after();
+      if (tr && wi < kTraceTiles && leader) tr[4 + 4 * wi] = clock64();
 
       if constexpr (SK) {
         if (sg.mode == SK_STORE) {
@@ -636,10 +648,81 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         }
+      } else if (p.staged_store) {
+        if constexpr (MT != 1) __trap();  // 256-pixel tiles are planned for TMA-store layers only
+        // -------- fused nearest-x2 upsample / PixelShuffle(2) of an fp16 result: the destination of a 128-pixel tile is not a
+        // TMA box, and with every thread storing its own pixel's channels a warp-wide 16-byte store touches 32 different
+        // 128-byte lines (x4 replicas for the upsample: 1x1 512->256 @13x13 ran at 9x its HBM roofline).  So the chunk is
+        // staged in the epilogue ring exactly like a TMA-stored chunk and then written out row-wise: 8 consecutive threads
+        // write the 128 contiguous bytes of one pixel's 64 channels, a warp 4 pixels.  One barrier per chunk suffices: the
+        // ring has >= 3 buffers, and a thread that is writing chunk g + 1 has passed barrier g, which every thread reaches
+        // only after its copy-out of chunk g - 1.
+        constexpr int UNITS = CHUNK / 8;  // 16-byte units per staged row
+        const uint32_t tmem_acc = tmem_acc0;
+        for (int c = 0; c < live; ++c, ++chunk_ctr) {
+          const uint32_t bsel = chunk_ctr % Cfg::NBUF;
+          uint32_t a[32];
+          if constexpr (HALF == 32) {
+            tmem_ld_32x32(tmem_acc + uint32_t(c * CHUNK + hsel * 32), a);
+          } else {
+            tmem_ld_32x16(tmem_acc + uint32_t(c * CHUNK + hsel * 16), a);
+          }
+          tmem_ld_wait();
+          if (c == live - 1) {  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster_a(tempty_arrive0 + 8u * acc);
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
+          }
+          uint8_t* buf = ring + bsel * Cfg::CHUNK_BYTES;
+          const float* bs = bias_s + c * CHUNK + hsel * HALF;
+#pragma unroll
+          for (int j = 0; j < HALF / 8; ++j) {  // same arithmetic as the per-thread path: fp32 bias + activation, one rounding
+            uint4 pk;
+            __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              h2[e] = __floats2half2_rn(apply_act(__uint_as_float(a[j * 8 + 2 * e]) + bs[j * 8 + 2 * e], p.act),
+                                        apply_act(__uint_as_float(a[j * 8 + 2 * e + 1]) + bs[j * 8 + 2 * e + 1], p.act));
+            *reinterpret_cast<uint4*>(buf + swz_off<Cfg::OUT_SWZ>(row_l, hsel * (HALF / 8) + j)) = pk;
+          }
+          bar_sync_named(1, Cfg::EPI_THREADS);
+          __half* o16 = reinterpret_cast<__half*>(p.out);
+          const int pq = p.P * p.Q;
+#pragma unroll
+          for (int i2 = 0; i2 < (128 * UNITS) / Cfg::EPI_THREADS; ++i2) {
+            const int idx = i2 * Cfg::EPI_THREADS + et;
+            const int r = idx / UNITS, u = idx % UNITS;
+            const int row = m0 + r;
+            const int ch = n0 + c * CHUNK + u * 8;
+            if (row >= p.M || ch >= p.Cout) continue;
+            const uint4 pk = *reinterpret_cast<const uint4*>(buf + swz_off<Cfg::OUT_SWZ>(r, u));
+            const int img = fast_div(row, p.mul_pq);
+            const int rem = row - img * pq;
+            const int op = fast_div(rem, p.mul_q);
+            const int oq = rem - op * p.Q;
+            if (p.store_mode == STORE_UPSAMPLE2) {
+              const size_t base = ((size_t)img * (2 * p.P) + 2 * op) * (2 * p.Q) + 2 * oq;
+#pragma unroll
+              for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+                  *reinterpret_cast<uint4*>(o16 + (base + (size_t)dy * (2 * p.Q) + dx) * p.out_pitch + p.out_coff + ch) = pk;
+            } else {  // PixelShuffle(2): weight rows were pre-permuted to o' = sub*(Cout/4) + c, sub = 2*i + j
+              const int c4 = p.Cout >> 2;
+              const int sub = ch / c4;
+              const int cc = ch - sub * c4;
+              const size_t pix = ((size_t)img * (2 * p.P) + 2 * op + (sub >> 1)) * (2 * p.Q) + 2 * oq + (sub & 1);
+              *reinterpret_cast<uint4*>(o16 + pix * p.out_pitch + p.out_coff + cc) = pk;
+            }
+          }
+        }
       } else {
         if constexpr (MT != 1) __trap();  // 256-pixel tiles are planned for TMA-store layers only
         const uint32_t tmem_acc = tmem_acc0;
-        // -------- per-thread stores: fp32 heads, fused nearest-x2 upsample, fused PixelShuffle(2)
+        // -------- per-thread stores: fp32 heads (and any fp16 result the staged paths do not take)
         const int row = m0 + row_l;
         const bool row_ok = row < p.M;
         int img = 0, op = 0, oq = 0;
@@ -674,6 +757,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (!row_ok) continue;
+
+          if (p.out_f32 && !use_res) {
+            // fp32 outputs (detector heads: 18 of 32 channels live, linear; heat-maps: 50 of 64): only the live channels
+            // are touched, bias comes as float4, and the activation switch is one uniform branch per group.  (The generic
+            // code below ran ~1 300 dependent instructions per tile on ONE warp per scheduler -- the 1x1 256->18 head at 52x52
+            // took 4x its HBM time, ncu r03a_head52.)
+            const int nl = min(32, p.Cout - ch0);
+            float* op32 = reinterpret_cast<float*>(p.out) + (size_t)row * p.out_pitch + p.out_coff + ch0;
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g * 4 < nl) {
+                const float4 b = b4[g];
+                float x0 = __uint_as_float(a[g * 4]) + b.x, x1 = __uint_as_float(a[g * 4 + 1]) + b.y;
+                float x2 = __uint_as_float(a[g * 4 + 2]) + b.z, x3 = __uint_as_float(a[g * 4 + 3]) + b.w;
+                if (p.act != ACT_NONE) {
+                  x0 = apply_act(x0, p.act); x1 = apply_act(x1, p.act);
+                  x2 = apply_act(x2, p.act); x3 = apply_act(x3, p.act);
+                }
+                if (g * 4 + 4 <= nl) {
+                  *reinterpret_cast<float4*>(op32 + g * 4) = make_float4(x0, x1, x2, x3);
+                } else {
+                  op32[g * 4] = x0;
+                  if (g * 4 + 1 < nl) op32[g * 4 + 1] = x1;
+                  if (g * 4 + 2 < nl) op32[g * 4 + 2] = x2;
+                }
+              }
+            }
+            continue;
+          }
 
           float v[32];
 #pragma unroll
@@ -755,11 +868,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      if (tr && wi < kTraceTiles && leader) tr[5 + 4 * wi] = clock64();
     }
     if (leader) bulk_wait_group_read<0>();  // smem must stay valid until the last TMA store has read it
   }
 
   tc_fence_before();
+  if (tr && threadIdx.x == 64) tr[1] = clock64();
   if constexpr (CG == 2) cluster_sync_all();  // the peer may still be reading our shared memory / signalling our barriers
   else __syncthreads();
   if (warp == 1) {

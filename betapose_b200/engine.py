@@ -109,28 +109,28 @@ class BetaposeEngine:
             self.kp3d = torch.from_numpy(np.array(kp3d, np.float64, copy=True)).to(self.device)
             dev, B, K = self.device, self.B, self.K
             f32, i32, u8 = torch.float32, torch.int32, torch.uint8
-            self.det = torch.zeros((B, 8), dtype=f32, device=dev)
-            self.box = torch.zeros((B, 4), dtype=f32, device=dev)
-            self.det_score = torch.zeros((B,), dtype=f32, device=dev)
-            self.row = torch.zeros((B,), dtype=i32, device=dev)
-            self.valid = torch.zeros((B,), dtype=u8, device=dev)
-            self.pt1 = torch.zeros((B, 2), dtype=f32, device=dev)
-            self.pt2 = torch.zeros((B, 2), dtype=f32, device=dev)
-            self.preds_hm = torch.zeros((B, K, 2), dtype=f32, device=dev)
-            self.preds_img = torch.zeros((B, K, 2), dtype=f32, device=dev)
-            self.maxval = torch.zeros((B, K), dtype=f32, device=dev)
-            self.hm_idx = torch.zeros((B, K), dtype=i32, device=dev)
-            self.keypoints = torch.zeros((B, K, 2), dtype=f32, device=dev)
-            self.kp_score = torch.zeros((B, K), dtype=f32, device=dev)
-            self.proposal = torch.zeros((B,), dtype=f32, device=dev)
-            self.selected = torch.zeros((B, K), dtype=u8, device=dev)
-            self.R = torch.zeros((B, 9), dtype=torch.float64, device=dev)
-            self.t = torch.zeros((B, 3), dtype=torch.float64, device=dev)
-            self.inlier = torch.zeros((B, K), dtype=u8, device=dev)
-            self.status = torch.zeros((B,), dtype=i32, device=dev)
-            self.records = torch.zeros((B, _lib.RECORD_BYTES), dtype=u8, device=dev)
+            # The small per-frame tensors exist TWICE ("parity" 0 / 1): with the PnP tail of step j running on a side stream
+            # while the main part of step j + 1 is already under way (PipelinedEngine, async tail), consecutive steps of an
+            # engine must not share them.  `self.det`, `self.records`, ... are rebound to one set by _select(parity); every
+            # single-stream entry point uses set 0.
+            def small():
+                return dict(
+                    det=torch.zeros((B, 8), dtype=f32, device=dev), box=torch.zeros((B, 4), dtype=f32, device=dev),
+                    det_score=torch.zeros((B,), dtype=f32, device=dev), row=torch.zeros((B,), dtype=i32, device=dev),
+                    valid=torch.zeros((B,), dtype=u8, device=dev), pt1=torch.zeros((B, 2), dtype=f32, device=dev),
+                    pt2=torch.zeros((B, 2), dtype=f32, device=dev), preds_hm=torch.zeros((B, K, 2), dtype=f32, device=dev),
+                    preds_img=torch.zeros((B, K, 2), dtype=f32, device=dev), maxval=torch.zeros((B, K), dtype=f32, device=dev),
+                    hm_idx=torch.zeros((B, K), dtype=i32, device=dev), keypoints=torch.zeros((B, K, 2), dtype=f32, device=dev),
+                    kp_score=torch.zeros((B, K), dtype=f32, device=dev), proposal=torch.zeros((B,), dtype=f32, device=dev),
+                    selected=torch.zeros((B, K), dtype=u8, device=dev), R=torch.zeros((B, 9), dtype=torch.float64, device=dev),
+                    t=torch.zeros((B, 3), dtype=torch.float64, device=dev), inlier=torch.zeros((B, K), dtype=u8, device=dev),
+                    status=torch.zeros((B,), dtype=i32, device=dev),
+                    records=torch.zeros((B, _lib.RECORD_BYTES), dtype=u8, device=dev),
+                    model_idx=torch.zeros((B,), dtype=i32, device=dev))
+
+            self._sets = [small(), small()]
+            self._select(0)
             self.img_idx = torch.arange(B, dtype=i32, device=dev)
-            self.model_idx = torch.zeros((B,), dtype=i32, device=dev)
             self.frames = torch.zeros((B, frame_h, frame_w, 3), dtype=u8, device=dev)
         self._cam = (C.c_double * 4)(*stages.pinhole4(self.cam_K))
         self._head_args = []
@@ -148,6 +148,11 @@ class BetaposeEngine:
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------------------------------------
+    def _select(self, parity: int) -> None:
+        """bind self.det, self.box, ..., self.records to small-tensor set `parity`"""
+        self.__dict__.update(self._sets[parity & 1])
+        self._parity = parity & 1
+
     @property
     def flops_per_image(self) -> float:
         return self.yolo[0].flops_per_image + self.kpd[0].flops_per_image
@@ -209,8 +214,13 @@ class BetaposeEngine:
                                      _lib.ptr(self.R), _lib.ptr(self.t), _lib.ptr(self.status), _lib.ptr(self.records), st),
                    "bp_pack_records")
 
-    def _enqueue(self, n: int, groups, image_index0: int) -> None:
+    def _enqueue(self, n: int, groups, image_index0: int, parts: str = "all") -> None:
+        """parts: "all" = the whole step; "main" = a1-a8 (resize ... heat-map decode); "tail" = a9-a12 (pose-NMS + PnP + record
+        packing), which only reads the small tensors the main part left (PipelinedEngine runs it on a side stream)."""
         st = _lib.stream_ptr()
+        if parts == "tail":
+            self._enqueue_tail(n, image_index0, st)
+            return
         if self.n_slots > 1:
             # the key-point model each frame is solved against follows from the grouping of THIS call (a stale
             # model_idx from an earlier mixed-object batch would pair slot s's networks with another object's model)
@@ -233,40 +243,49 @@ class BetaposeEngine:
             for slot, b0, cnt in groups:  # slots share activation buffers: decode a slot's heat-maps before the next slot runs
                 self._enqueue_slot(slot, b0, cnt, st)
                 self._enqueue_decode(slot, b0, cnt, st)
-        self._enqueue_tail(n, image_index0, st)
+        if parts == "all":
+            self._enqueue_tail(n, image_index0, st)
 
     # ------------------------------------------------------------------------------------------------
-    def run_device(self, n: int | None = None, groups=None, image_index0: int = 0, graph: bool = False) -> torch.Tensor:
+    def run_device(self, n: int | None = None, groups=None, image_index0: int = 0, graph: bool = False, parts: str = "all",
+                   parity: int = 0) -> torch.Tensor:
         """Process the first n frames already resident in `self.frames` (grouped by slot: list of (slot, first, count),
         frames of one slot contiguous; `self.model_idx` is rewritten from the grouping).  Returns the records tensor view [n, RECORD_BYTES]
-        (device); nothing has synchronised."""
+        (device); nothing has synchronised.  `parts` / `parity`: run only the main part or only the tail of the step, on small-tensor
+        set `parity` (see _enqueue, _select); the caller orders "tail" after "main" of the same parity (PipelinedEngine does)."""
         n = self.B if n is None else int(n)
         groups = [(0, 0, n)] if groups is None else list(groups)
+        assert parts in ("all", "main", "tail")
         with torch.cuda.device(self.device):
-            if not graph:
-                self._enqueue(n, groups, image_index0)
-            else:
-                key = (n, tuple(groups), image_index0)
-                g = self._graphs.get(key)
-                if g is None:
-                    # warm-up ON the capture stream (the library keeps its kernel scratch per stream: lazy allocations,
-                    # function attributes and descriptor builds for this batch size all happen here, outside capture),
-                    # then capture on that same stream.  One capture stream per engine: graphs of different engines
-                    # never share scratch.
-                    if not hasattr(self, "_capture_stream"):
-                        self._capture_stream = torch.cuda.Stream()
-                    cap = self._capture_stream
-                    cap.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(cap):
-                        self._enqueue(n, groups, image_index0)
-                    cap.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=cap):
-                        self._enqueue(n, groups, image_index0)
-                    self._graphs[key] = g
-                g.replay()
+            self._select(parity)
+            try:
+                if not graph:
+                    self._enqueue(n, groups, image_index0, parts)
+                else:
+                    key = (n, tuple(groups), image_index0) if (parts == "all" and not parity) else (n, tuple(groups), image_index0, parts, parity & 1)
+                    g = self._graphs.get(key)
+                    if g is None:
+                        # warm-up ON the capture stream (the library keeps its kernel scratch per stream: lazy allocations,
+                        # function attributes and descriptor builds for this batch size all happen here, outside capture),
+                        # then capture on that same stream.  One capture stream per engine: graphs of different engines
+                        # never share scratch.
+                        if not hasattr(self, "_capture_stream"):
+                            self._capture_stream = torch.cuda.Stream()
+                        cap = self._capture_stream
+                        cap.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(cap):
+                            self._enqueue(n, groups, image_index0, parts)
+                        cap.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=cap):
+                            self._enqueue(n, groups, image_index0, parts)
+                        self._graphs[key] = g
+                    g.replay()
+                rec = self.records[:n]
+            finally:
+                self._select(0)
         self.launches_per_step = self.count_launches(len(groups))
-        return self.records[:n]
+        return rec
 
     def profile_stages(self, n: int | None = None, reps: int = 5) -> dict:
         """Device time of every stage of one step on the frames resident in `self.frames` (slot 0), CUDA events between the
@@ -358,22 +377,33 @@ class PipelinedEngine:
     DetectionLoader -> DetectionProcessor -> DataWriter threads with queues between them); this is its device-side
     equivalent.  Costs one extra set of activation buffers (~133 MB per frame of batch) and one extra weight copy."""
 
-    def __init__(self, lanes: int, max_batch: int, *args, **kw):
+    def __init__(self, lanes: int, max_batch: int, *args, async_tail: bool = True, **kw):
         assert lanes >= 1
-        self._init([BetaposeEngine(max_batch, *args, **kw) for _ in range(int(lanes))])
+        self._init([BetaposeEngine(max_batch, *args, **kw) for _ in range(int(lanes))], async_tail)
 
     @classmethod
-    def from_engines(cls, engines):
+    def from_engines(cls, engines, async_tail: bool = True):
         self = cls.__new__(cls)
-        self._init(list(engines))
+        self._init(list(engines), async_tail)
         return self
 
-    def _init(self, engines):
+    def _init(self, engines, async_tail: bool = True):
         self.lanes = engines
         e0 = engines[0]
         self.device, self.B = e0.device, e0.B
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream() for _ in engines] if len(engines) > 1 else [None]
+            # Asynchronous tail: pose-NMS + PnP + record packing of a lane's step j (two fp64 latency chains on a few warps,
+            # ~0.8 ms at batch 64, 1 KB of data per frame) run on the lane's high-priority TAIL stream while the lane's main
+            # stream already works on step j + 1 (resize, detector, ...): the tail is off the critical path of the lane.
+            # Consecutive steps of a lane alternate between the engine's two small-tensor sets; the main part of step j + 2
+            # waits for the tail of step j.
+            self.async_tail = bool(async_tail)
+            self.tail_streams = [torch.cuda.Stream(priority=-1) for _ in engines] if self.async_tail else [None] * len(engines)
+            self._ev_main = [[torch.cuda.Event() for _ in range(2)] for _ in engines]
+            self._ev_tail = [[torch.cuda.Event() for _ in range(2)] for _ in engines]
+            self._lane_steps = [0] * len(engines)
+            self._primed = [set() for _ in engines]
             self._copy_stream = torch.cuda.Stream()
             self._stage = [torch.empty_like(e.frames) for e in engines]
             # two host record buffers per lane: batch k's records may still be in the caller's hands when batch k + L lands
@@ -392,34 +422,70 @@ class PipelinedEngine:
         i = k % len(self.lanes)
         return self.lanes[i], self.streams[i]
 
+    def _step(self, i: int, lane_stream, n: int, graph: bool, after_step=None, rec_host=None, ev_done=None):
+        """Enqueue one step of lane i whose frames are already in the lane's `frames` buffer (ordered on `lane_stream`):
+        main part on the lane's stream, tail (+ after_step + the records' device->host copy) on the tail stream when the
+        tail is asynchronous, else everything on the lane's stream.  Returns the device records view."""
+        eng = self.lanes[i]
+        if not self.async_tail:
+            rec = eng.run_device(n, graph=graph)
+            tail = lane_stream
+        else:
+            par = self._lane_steps[i] & 1
+            self._lane_steps[i] += 1
+            tail = self.tail_streams[i]
+            if graph and n not in self._primed[i]:
+                # first step of this lane at this batch size: capture the graphs of BOTH small-tensor sets now (the other
+                # set's main + tail run once on the same frames), so that no later step pays for a capture
+                self._primed[i].add(n)
+                with torch.cuda.stream(lane_stream):
+                    eng.run_device(n, graph=True, parts="main", parity=par ^ 1)
+                    eng.run_device(n, graph=True, parts="tail", parity=par ^ 1)
+                    eng.run_device(n, graph=True, parts="main", parity=par)
+                    eng.run_device(n, graph=True, parts="tail", parity=par)
+            lane_stream.wait_event(self._ev_tail[i][par])  # tail of this lane's step j - 2 has released small-tensor set `par`
+            eng.run_device(n, graph=graph, parts="main", parity=par)
+            self._ev_main[i][par].record(lane_stream)
+            tail.wait_event(self._ev_main[i][par])
+            with torch.cuda.stream(tail):
+                rec = eng.run_device(n, graph=graph, parts="tail", parity=par)
+        with torch.cuda.stream(tail):
+            if after_step is not None:
+                after_step(rec)
+            if rec_host is not None:
+                rec_host[:n].copy_(rec, non_blocking=True)
+            if self.async_tail:
+                self._ev_tail[i][par].record(tail)
+            if ev_done is not None:
+                ev_done.record(tail)
+        return rec
+
     def submit_device(self, k: int, frames_dev: torch.Tensor | None = None, n: int | None = None, graph: bool = True,
                       after_step=None) -> torch.Tensor:
         """Enqueue batch k (frames already in HBM, or already in the lane's `frames` buffer when frames_dev is None) on its
-        lane's stream; returns the lane's device records view.  The caller orders the lane streams against its own stream
-        (fork / join) when it needs to."""
+        lane's stream(s); returns the lane's device records view (valid once the lane's tail stream has run: `join()`).  The
+        caller orders the lane streams against its own stream (fork / join) when it needs to."""
         eng, st = self.lane_stream(k)
         n = eng.B if n is None else int(n)
         with torch.cuda.device(self.device):
-            ctx = torch.cuda.stream(st) if st is not None else _nullctx()
-            with ctx:
+            lane_stream = st if st is not None else torch.cuda.current_stream()
+            with torch.cuda.stream(lane_stream):
                 if frames_dev is not None:
                     eng.frames[:n].copy_(frames_dev[:n], non_blocking=True)
-                rec = eng.run_device(n, graph=graph)
-                if after_step is not None:
-                    after_step(rec)
+                rec = self._step(k % len(self.lanes), lane_stream, n, graph, after_step)
         return rec
 
     def fork(self) -> None:
         """lane streams wait for everything enqueued so far on the caller's stream"""
         cur = torch.cuda.current_stream()
-        for s in self.streams:
+        for s in list(self.streams) + list(self.tail_streams):
             if s is not None:
                 s.wait_stream(cur)
 
     def join(self) -> None:
-        """the caller's stream waits for everything enqueued so far on the lanes"""
+        """the caller's stream waits for everything enqueued so far on the lanes (main and tail streams)"""
         cur = torch.cuda.current_stream()
-        for s in self.streams:
+        for s in list(self.streams) + list(self.tail_streams):
             if s is not None:
                 cur.wait_stream(s)
 
@@ -442,6 +508,8 @@ class PipelinedEngine:
             for i in range(L):
                 if streams[i] is not cur:
                     streams[i].wait_stream(cur)
+                if self.tail_streams[i] is not None:
+                    self.tail_streams[i].wait_stream(cur)
                 ev_free[i].record(streams[i])
             pending = deque()
             it = iter(batches)
@@ -462,11 +530,8 @@ class PipelinedEngine:
                     streams[i].wait_event(ev_h2d[i])
                     eng.frames[:n].copy_(self._stage[i][:n], non_blocking=True)  # device->device, ~0.03 ms for 64 frames
                     ev_free[i].record(streams[i])
-                    rec = eng.run_device(n, None, 0, graph=graph)  # one captured graph per batch size; indices fixed up below
-                    if after_step is not None:
-                        after_step(rec)
-                    self._rec_host[i][h][:n].copy_(rec, non_blocking=True)
-                    ev_done[i][h].record(streams[i])
+                    # one captured graph (pair) per batch size; image indices are fixed up on the host below
+                    self._step(i, streams[i], n, graph, after_step, self._rec_host[i][h], ev_done[i][h])
                 pending.append((i, h, n, idx0))
 
             while True:
@@ -496,7 +561,7 @@ class PipelinedEngine:
                 out["image_index"] = first + np.arange(n)
                 yield out
             if cur is not None:
-                for s in streams:
+                for s in streams + [t for t in self.tail_streams if t is not None]:
                     if s is not cur:
                         cur.wait_stream(s)
 

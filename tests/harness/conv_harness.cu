@@ -3,6 +3,7 @@
 // semantics, and times a few production shapes.  Build: see betapose_b200/csrc/Makefile (target conv_harness).
 //   ./conv_harness            -> correctness matrix + timings
 //   ./conv_harness probe      -> im2col probe only
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,7 @@ struct Rng {  // xorshift32: fast enough to fill the batch-64 tensors
 };
 
 static TmapApi g_api;
+static bool g_trace = false;  // `trace` mode: per-CTA clock stamps of the production shapes
 
 struct Case {
   const char* name;
@@ -226,6 +228,54 @@ static int run_case(const Case& cs) {
   if (bad) printf(" first_bad: m=%ld co=%ld", first_bad / cs.Cout, first_bad % cs.Cout);
   if (ms > 0) printf("  %.3f ms  %.1f TFLOP/s", ms, pl.flops / ms * 1e-9);
   printf("\n");
+  if (g_trace && bad == 0) {
+    // one launch with per-CTA clock stamps (ConvArgs::trace): where a CTA's time goes, tile by tile
+    unsigned long long* dtr;
+    const size_t nslots = (size_t)pl.grid * kTraceSlots;
+    CK(cudaMalloc(&dtr, nslots * 8));
+    CK(cudaMemset(dtr, 0, nslots * 8));
+    ConvPlan pt = pl;
+    pt.args.trace = dtr;
+    conv_plan_launch(pt, 0);
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> tr(nslots);
+    CK(cudaMemcpy(tr.data(), dtr, nslots * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dtr);
+    double tot = 0, totmax = 0, fill = 0, main_ = 0, epi = 0, period = 0, idle = 0, first = 0;
+    long nt = 0, np = 0, nc = 0, maxtiles = 0;
+    for (int c = 0; c < pl.grid; ++c) {
+      const unsigned long long* t = tr.data() + (size_t)c * kTraceSlots;
+      if (!t[1] || !t[0]) continue;
+      if (pl.cg == 2 && (c & 1)) {  // the peer CTA of a pair has no MMA stamps: epilogue only
+        continue;
+      }
+      ++nc;
+      tot += double(t[1] - t[0]);
+      totmax = std::max(totmax, double(t[1] - t[0]));
+      long tiles = 0;
+      for (int i = 0; i < kTraceTiles; ++i) {
+        const unsigned long long *q = t + 2 + 4 * i;
+        if (!q[2] || !q[3]) break;
+        ++tiles;
+        if (i == 0) first += double(q[1] - t[0]);   // start -> first k-block landed
+        fill += double(q[1] - q[0]);               // accumulator free -> first k-block of the tile landed
+        main_ += double(q[2] - q[1]);              // first k-block landed -> accumulator complete
+        epi += double(q[3] - q[2]);                // accumulator complete -> epilogue done
+        ++nt;
+        if (i > 0) {
+          period += double(q[2] - (q - 4)[2]);     // accumulator-complete to accumulator-complete
+          idle += q[0] > (q - 4)[2] ? double(q[0] - (q - 4)[2]) : 0.0;  // MMA warp waited for the epilogue to free an accumulator
+          ++np;
+        }
+      }
+      maxtiles = std::max(maxtiles, tiles);
+    }
+    if (nc && nt)
+      printf("    trace: CTAs %ld, tiles/CTA max %ld | CTA active cycles mean %.0f max %.0f | start->first k-block %.0f | per tile: wait for first k-block %.0f, "
+             "main loop %.0f (%.0f per k-block), epilogue %.0f | tile period %.0f | MMA warp blocked on epilogue %.0f\n",
+             nc, maxtiles, tot / nc, totmax, first / nc, fill / nt, main_ / nt, main_ / nt / (double)pl.args.num_kb, epi / nt, np ? period / np : 0.0,
+             np ? idle / np : 0.0);
+  }
   fflush(stdout);
   cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dref); cudaFree(dout);
   if (dres) cudaFree(dres);
@@ -406,6 +456,31 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device: %s sm_%d%d, %d SMs, driver %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
          g_api.driver_version);
+  if (argc > 1 && !strcmp(argv[1], "trace")) {
+    // batch-64 production shapes with per-tile clock stamps: which of {operand arrival, main loop, epilogue} a tile waits for
+    g_trace = true;
+    std::vector<Case> tc = {
+        {"K conv1 1x1 1024->256 @20x16", 64, 20, 16, 1024, 256, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K conv2 3x3 256->256 @20x16", 64, 20, 16, 256, 256, 3, 3, 1, 1, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K conv3 1x1 256->1024 +res", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, RES_BEFORE_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"K conv3 1x1 256->1024 no res", 64, 20, 16, 256, 1024, 1, 1, 1, 0, ACT_RELU, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 1x1 512->256 @26", 64, 26, 26, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 256->512 @26 +res", 64, 26, 26, 256, 512, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 128->256 @52 +res", 64, 52, 52, 128, 256, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 1x1 1024->512 @13", 64, 13, 13, 1024, 512, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 3x3 512->1024 @13 +res", 64, 13, 13, 512, 1024, 3, 3, 1, 1, ACT_LEAKY, RES_AFTER_ACT, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y 1x1 256->128 @52", 64, 52, 52, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, 0, 0, 0, 0, 0, 0, 0, 10},
+        {"Y head 1x1 256->18 f32 @52", 64, 52, 52, 256, 18, 1, 1, 1, 0, ACT_NONE, 0, 0, 1, 0, 2, 0, 0, 0, 10},
+        {"Y 1x1 512->256 @13 up2", 64, 13, 13, 512, 256, 1, 1, 1, 0, ACT_LEAKY, 0, STORE_UPSAMPLE2, 0, 0, 512, 0, 0, 0, 10},
+        {"Y 1x1 256->128 @26 up2", 64, 26, 26, 256, 128, 1, 1, 1, 0, ACT_LEAKY, 0, STORE_UPSAMPLE2, 0, 0, 256, 0, 0, 0, 10},
+        {"K 3x3 128->50 f32 @80x64", 64, 80, 64, 128, 50, 3, 3, 1, 1, ACT_NONE, 0, 0, 1, 0, 2, 0, 0, 0, 10},
+        {"K 3x3 256->512 @40x32 ps2", 64, 40, 32, 256, 512, 3, 3, 1, 1, ACT_RELU, 0, STORE_PIXSHUF2, 0, 0, 0, 0, 0, 0, 10},
+    };
+    int f = 0;
+    for (auto& c : tc) f += run_case(c);
+    printf("TOTAL FAILURES: %d\n", f);
+    return f ? 1 : 0;
+  }
   const bool probe_only = argc > 1 && !strcmp(argv[1], "probe");
   const bool quick = argc > 1 && !strcmp(argv[1], "quick");
   int fails = 0;

@@ -656,3 +656,46 @@ def test_pipelined_engine_two_lanes_matches_single(yolo_stream, kpd_sd, kp_model
     assert torch.equal(r0, r1) and r0.data_ptr() != r1.data_ptr()
     del pipe
     torch.cuda.empty_cache()
+
+
+def test_async_tail_many_steps_and_sync_tail_agree(yolo_stream, kpd_sd, kp_model):
+    """PipelinedEngine runs pose-NMS + PnP + record packing of step j on a tail stream while step j + 1 is under way, alternating
+    between two sets of small per-frame tensors.  Seven DIFFERENT batches through one lane and through two lanes (every set is
+    reused at least once, main part of step j + 2 waits for the tail of step j), graph replay and eager: records identical to
+    the plain per-batch call and to a PipelinedEngine with the tail on the lane's own stream (async_tail=False)."""
+    from betapose_b200 import synth
+    from betapose_b200.engine import BetaposeEngine, PipelinedEngine
+
+    frames = synth.synth_frames(28, seed=77)
+    batches = [frames[4 * i:4 * i + 4] for i in range(7)]
+    e0 = BetaposeEngine(4, yolo_stream, kpd_sd, kp_model, seed=9)
+    want = [e0.run(b).copy() for b in batches]
+    e1 = BetaposeEngine(4, yolo_stream, kpd_sd, kp_model, seed=9)
+
+    def check(got):
+        assert len(got) == len(want)
+        for k, (g, w) in enumerate(zip(got, want)):
+            assert g["image_index"].tolist() == list(range(4 * k, 4 * k + 4))
+            for f in w.dtype.names:
+                if f != "image_index":
+                    assert np.array_equal(g[f], w[f]), (k, f)
+
+    for engines in ([e0], [e0, e1]):
+        for async_tail in (True, False):
+            pipe = PipelinedEngine.from_engines(engines, async_tail=async_tail)
+            assert pipe.async_tail == async_tail
+            for graph in (True, False):
+                check(list(pipe.run_stream(iter(batches), graph=graph)))
+    # device-side submission, three steps per lane, then join: the last records of each lane are those of batches 4 and 5
+    pipe = PipelinedEngine.from_engines([e0, e1])
+    devb = [torch.from_numpy(b).cuda() for b in batches]
+    pipe.fork()
+    recs = [pipe.submit_device(k, devb[k]) for k in range(6)]
+    pipe.join()
+    torch.cuda.synchronize()
+    from betapose_b200 import stages
+    for k in (2, 3, 4, 5):  # per lane: set 0 now holds its third step's records (batches 4 / 5), set 1 its second step's (2 / 3)
+        g = stages.records_to_numpy(recs[k]).copy()
+        for f in want[k].dtype.names:
+            if f != "image_index":
+                assert np.array_equal(g[f], want[k][f]), (k, f)
