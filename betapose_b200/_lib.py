@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbetapose_b200.so")
+LIB_PATH = os.environ.get("BP_LIB_PATH") or os.path.join(_HERE, "libbetapose_b200.so")  # BP_LIB_PATH: an experimental build of the same library
 
 # every symbol include/betapose_b200.h declares (tests check the .so exports all of them)
 EXPORTS = (

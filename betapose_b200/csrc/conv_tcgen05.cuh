@@ -69,7 +69,7 @@ struct ConvArgs {
   // landed, [4+4i] epilogue sees the accumulator complete, [5+4i] epilogue done with the tile
   unsigned long long* trace;
 };
-constexpr int kTraceTiles = 32, kTraceSlots = 2 + 4 * kTraceTiles;
+constexpr int kTraceTiles = 24, kTraceFine = 2 + 4 * kTraceTiles, kTraceSlots = kTraceFine + 5 * 5 + 5 * 3;  // + stamps inside the first 5 chunks
 
 // ---- stream-K work split (SK kernels).  The (tile, k-block) units of a launch are cut into one CONTIGUOUS range per cluster
 // instead of whole tiles dealt round-robin, so a launch of 160 tiles on 148 SMs takes 1.08 tile times instead of 2.  A range
@@ -155,9 +155,21 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
-  static constexpr int EPI_WARPS = 8;                  // two warps per TMEM lane quarter, each takes half of a chunk's columns
+  // EPI_SPLIT warps share a TMEM lane quarter, each takes EPI_COLS = 16 columns of every chunk.  Four per quarter for the
+  // 64-channel chunks (16 epilogue warps, four per scheduler): the epilogue of a chunk is a ~130-instruction dependent chain
+  // per warp (TMEM load, bias, residual, activation, pack, swizzled store, barrier), and with two warps per scheduler it ran
+  // at ~1 070 cycles per chunk -- as long as the four k-blocks of a 1x1 256->1024 tile take (harness trace, round 2: those
+  // layers were bound by the epilogue, and every launch ends with one exposed epilogue).
+#ifndef BP_EPI_WARPS
+#define BP_EPI_WARPS 8
+#endif
+  static constexpr int EPI_WARPS = BLOCK_N >= 64 ? BP_EPI_WARPS : 8;
+  static constexpr int EPI_SPLIT = EPI_WARPS / 4;
+  static constexpr int EPI_COLS = CHUNK / EPI_SPLIT;
+  static_assert(EPI_COLS == 16 || EPI_COLS == 32, "epilogue threads take 16 or 32 columns of a chunk");
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
-  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr int STORE_WARP = 2 + EPI_WARPS;      // issues the TMA stores / residual loads of the staged chunks
+  static constexpr int THREADS = 64 + EPI_THREADS + 32;
 };
 
 // byte offset of 16-byte unit j of row r inside a swizzled [128][ROW_BYTES] tile (TMA SWIZZLE_128B / SWIZZLE_64B)
@@ -172,18 +184,21 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 // through swz_off so the same code reads the TMA-loaded residual and writes the TMA-stored result in place.
 template <int ACT, int RESMODE, int ROW_BYTES, int NV>
 __device__ __forceinline__ void epi_math_store(const uint32_t* a, const float* bias, uint8_t* tile, int row_l, int unit0) {
+  // Instruction budget matters here: a chunk's epilogue is bounded by issue slots once the TMEM read is overlapped, so the
+  // fp32 work is done two lanes at a time (add / mul .f32x2, sm_100) -- the same IEEE operations, half the instructions.
 #pragma unroll
   for (int j = 0; j < NV / 8; ++j) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias + j * 8);
     const float4 b1 = *reinterpret_cast<const float4*>(bias + j * 8 + 4);
-    float v[8];
-    v[0] = __uint_as_float(a[j * 8 + 0]) + b0.x; v[1] = __uint_as_float(a[j * 8 + 1]) + b0.y;
-    v[2] = __uint_as_float(a[j * 8 + 2]) + b0.z; v[3] = __uint_as_float(a[j * 8 + 3]) + b0.w;
-    v[4] = __uint_as_float(a[j * 8 + 4]) + b1.x; v[5] = __uint_as_float(a[j * 8 + 5]) + b1.y;
-    v[6] = __uint_as_float(a[j * 8 + 6]) + b1.z; v[7] = __uint_as_float(a[j * 8 + 7]) + b1.w;
+    float2 v[4];
+    v[0] = __fadd2_rn(make_float2(__uint_as_float(a[j * 8 + 0]), __uint_as_float(a[j * 8 + 1])), make_float2(b0.x, b0.y));
+    v[1] = __fadd2_rn(make_float2(__uint_as_float(a[j * 8 + 2]), __uint_as_float(a[j * 8 + 3])), make_float2(b0.z, b0.w));
+    v[2] = __fadd2_rn(make_float2(__uint_as_float(a[j * 8 + 4]), __uint_as_float(a[j * 8 + 5])), make_float2(b1.x, b1.y));
+    v[3] = __fadd2_rn(make_float2(__uint_as_float(a[j * 8 + 6]), __uint_as_float(a[j * 8 + 7])), make_float2(b1.z, b1.w));
     uint8_t* slot = tile + swz_off<ROW_BYTES>(row_l, unit0 + j);
     uint4 pk;
     __half2* h = reinterpret_cast<__half2*>(&pk);
+    const __half2 zero = __float2half2_rn(0.f);
     if constexpr (RESMODE != RES_NONE) {
       // residual layers: add in fp32 and round ONCE (the residual chains are 23 / 33 blocks deep; rounding the conv result
       // to fp16 before the add would round every block twice)
@@ -192,23 +207,29 @@ __device__ __forceinline__ void epi_math_store(const uint32_t* a, const float* b
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 rf = __half22float2(r[e]);
-        float x0 = v[2 * e], x1 = v[2 * e + 1];
-        if constexpr (RESMODE == RES_BEFORE_ACT) { x0 += rf.x; x1 += rf.y; }
-        if constexpr (ACT == ACT_LEAKY) { x0 = fmaxf(x0, 0.1f * x0); x1 = fmaxf(x1, 0.1f * x1); }
-        if constexpr (ACT == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-        if constexpr (ACT == ACT_SIGMOID) { x0 = 1.f / (1.f + __expf(-x0)); x1 = 1.f / (1.f + __expf(-x1)); }
-        if constexpr (RESMODE == RES_AFTER_ACT) { x0 += rf.x; x1 += rf.y; }
-        h[e] = __floats2half2_rn(x0, x1);
+        float2 x = v[e];
+        if constexpr (RESMODE == RES_BEFORE_ACT) x = __fadd2_rn(x, rf);
+        if constexpr (ACT == ACT_LEAKY) {
+          const float2 s = __fmul2_rn(x, make_float2(0.1f, 0.1f));
+          x.x = fmaxf(x.x, s.x);
+          x.y = fmaxf(x.y, s.y);
+        }
+        if constexpr (ACT == ACT_RELU && RESMODE == RES_AFTER_ACT) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+        if constexpr (ACT == ACT_SIGMOID) { x.x = 1.f / (1.f + __expf(-x.x)); x.y = 1.f / (1.f + __expf(-x.y)); }
+        if constexpr (RESMODE == RES_AFTER_ACT) x = __fadd2_rn(x, rf);
+        h[e] = __floats2half2_rn(x.x, x.y);
+        // ReLU after the rounding: rounding is monotonic and keeps the sign, so max(round(x), 0) == round(max(x, 0))
+        if constexpr (ACT == ACT_RELU && RESMODE == RES_BEFORE_ACT) h[e] = __hmax2(h[e], zero);
       }
     } else if constexpr (ACT == ACT_SIGMOID) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        h[e] = __floats2half2_rn(1.f / (1.f + __expf(-v[2 * e])), 1.f / (1.f + __expf(-v[2 * e + 1])));
+        h[e] = __floats2half2_rn(1.f / (1.f + __expf(-v[e].x)), 1.f / (1.f + __expf(-v[e].y)));
     } else {
-      const __half2 zero = __float2half2_rn(0.f), slope = __float2half2_rn(0.1f);
+      const __half2 slope = __float2half2_rn(0.1f);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        __half2 x = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        __half2 x = __floats2half2_rn(v[e].x, v[e].y);
         if constexpr (ACT == ACT_LEAKY) x = __hmax2(x, __hmul2(x, slope));  // slope < 1: max(x, 0.1 x)
         if constexpr (ACT == ACT_RELU) x = __hmax2(x, zero);
         h[e] = x;
@@ -240,7 +261,7 @@ __device__ __forceinline__ void epi_dispatch(int act, int res_mode, const uint32
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, int CG = 1, int NB = 4, int MT = 1, int SK = 0>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N, BLOCK_K, STAGES, CG, NB, MT, SK>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const ConvArgs p) {
@@ -468,11 +489,94 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
       }
     }
+  } else if (warp == Cfg::STORE_WARP) {
+    // ------------------------------------------------------------ store warp (TMA-stored layers).  The epilogue warps stage
+    // a chunk in ring buffer g % NBUF and ARRIVE on named barrier 2 + g % NBUF without waiting; this warp waits there,
+    // stores the chunk (cp.async.bulk.tensor, one thread: bulk groups are per thread) and, as soon as the previous store
+    // has read its buffer, hands that buffer on: with a residual by loading the residual tile of the chunk that will use
+    // it next (TMA, completes res_full_bar), without one by a plain arrive on the same mbarrier ("buffer free").  So the
+    // store issue, the commit and wait_group.read (~250-450 cycles per chunk when an epilogue thread did them between
+    // two barriers of all epilogue warps: harness trace) are off the epilogue's critical path.
+    if (p.tma_store) {
+      const bool use_res = p.res_mode != RES_NONE;
+      int pf_wi = 0, pf_sub = 0, pf_c = 0, pf_n0 = 0, pf_m0 = 0, pf_live = 0;  // residual prefetch cursor over the walk
+      uint32_t pf_g = 0;  // global index of the next chunk to prefetch
+      auto pf_decode = [&]() {
+        if constexpr (SK) {
+          while (pf_wi < n_walk && walk(pf_wi).mode == SK_STORE) ++pf_wi;  // a stored partial has no epilogue output, no residual
+        }
+        if (pf_wi < n_walk) {
+          const int pf_tile = walk(pf_wi).tile;
+          const int pm = fast_div(pf_tile, p.mul_nt);
+          pf_n0 = (pf_tile - pm * p.n_tiles) * BLOCK_N;
+          pf_m0 = (pm * CG + int(rank)) * Cfg::BLOCK_M;
+          pf_live = min(N_CHUNKS, (p.Cout - pf_n0 + CHUNK - 1) / CHUNK);
+        }
+      };
+      auto pf_issue = [&]() {  // load the residual of chunk pf_g (if there is one) and advance the cursor
+        if (pf_wi >= n_walk) return;
+        const uint32_t rb = pf_g % Cfg::NBUF;
+        if (lane == 0) {
+          mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
+          tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, pf_n0 + pf_c * CHUNK, pf_m0 + pf_sub * 128);
+        }
+        ++pf_g;
+        if (++pf_c == pf_live) {
+          pf_c = 0;
+          if (++pf_sub == MT) {
+            pf_sub = 0;
+            ++pf_wi;
+            pf_decode();
+          }
+        }
+      };
+      if (use_res) {
+        // the prefetch cursor runs NBUF - 1 chunks ahead of the chunk being stored, across tile boundaries
+        pf_decode();
+        for (int i = 0; i < Cfg::NBUF - 1; ++i) pf_issue();
+      } else if (lane == 0) {
+        for (int b = 0; b < Cfg::NBUF; ++b) mbar_arrive(&res_full_bar[b]);  // every buffer starts out free
+      }
+      uint32_t g = 0;
+      for (int wi = 0; wi < n_walk; ++wi) {
+        const SkSeg sg = walk(wi);
+        if constexpr (SK) {
+          if (sg.mode == SK_STORE) continue;
+        }
+        const int pm_tile = fast_div(sg.tile, p.mul_nt);
+        const int m0 = (pm_tile * CG + int(rank)) * Cfg::BLOCK_M;
+        const int n0 = (sg.tile - pm_tile * p.n_tiles) * BLOCK_N;
+        const int live = min(N_CHUNKS, (p.Cout - n0 + CHUNK - 1) / CHUNK);
+        for (int sub = 0; sub < MT; ++sub) {
+          for (int c = 0; c < live; ++c, ++g) {
+            const uint32_t bsel = g % Cfg::NBUF;
+            unsigned long long* const ss = (tr && g < 5 && lane == 0) ? tr + kTraceFine + 25 + 3 * g : nullptr;
+            bar_sync_named(2 + int(bsel), Cfg::EPI_THREADS + 32);  // chunk g is staged (its writers fenced the async proxy)
+            if (ss) ss[0] = clock64();
+            if (lane == 0) {
+              tma_store_2d(&tmOut, ring + bsel * Cfg::CHUNK_BYTES, n0 + c * CHUNK, m0 + sub * 128);
+              bulk_commit_group();
+              if (ss) ss[1] = clock64();
+              bulk_wait_group_read<1>();  // every store but the one just committed has read its buffer
+            }
+            __syncwarp();
+            if (use_res) {
+              pf_issue();  // into the buffer of chunk g - 1 (the first one: into the still unused last buffer)
+            } else if (g >= 1 && lane == 0) {
+              mbar_arrive(&res_full_bar[(g - 1) % Cfg::NBUF]);
+            }
+            if (ss) ss[2] = clock64();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait_group_read<0>();  // smem must stay valid until the last TMA store has read it
+    }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..9 = 256 threads)
-    constexpr int HALF = CHUNK / 2;          // channels of a chunk handled by one thread
+    // ------------------------------------------------------------ epilogue (warps 2 .. 2 + EPI_WARPS - 1)
+    constexpr int HALF = Cfg::EPI_COLS;      // channels of a chunk handled by one thread (16)
+    constexpr int ESPLIT = Cfg::EPI_SPLIT;   // warps sharing a lane quarter
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may read
-    const int hsel = (warp - 2) >> 2;        // which half of each chunk's columns
+    const int hsel = (warp - 2) >> 2;        // which share of each chunk's columns
     const int row_l = q4 * 32 + lane;        // row inside the tile
     const bool leader = threadIdx.x == 64;   // issues TMA stores / residual loads (bulk groups are per thread)
     const int et = threadIdx.x - 64;         // 0..255
@@ -482,43 +586,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float bias_next = (n_walk > 0 && et < BLOCK_N) ? __ldg(p.bias + (walk(0).tile % p.n_tiles) * BLOCK_N + et) : 0.f;
     const uint32_t tfull_wait0 = smem_u32(&tmem_full_bar[0]);
     const uint32_t tempty_arrive0 = CG == 2 ? leader_addr(smem_u32(&tmem_empty_bar[0])) : smem_u32(&tmem_empty_bar[0]);
-    // Residual tiles arrive by TMA in the ring buffers the results later leave from.  The leader runs a prefetch
-    // cursor NBUF - 1 chunks ahead of the chunk being computed, across tile boundaries: right after the store of chunk
-    // g is committed, `wait_group.read 1` guarantees the store of chunk g - 1 has read its buffer, which is the buffer
-    // of chunk g - 1 + NBUF, and that chunk's residual load is issued -- about three chunk times before it is needed.
-    int pf_wi = 0, pf_sub = 0, pf_c = 0, pf_n0 = 0, pf_m0 = 0, pf_live = 0;  // cursor over the walk (segments with an output)
-    uint32_t pf_g = 0;  // global index of the next chunk to prefetch
-    auto pf_decode = [&]() {
-      if constexpr (SK) {
-        while (pf_wi < n_walk && walk(pf_wi).mode == SK_STORE) ++pf_wi;  // a stored partial has no epilogue output, no residual
-      }
-      if (pf_wi < n_walk) {
-        const int pf_tile = walk(pf_wi).tile;
-        const int pm = fast_div(pf_tile, p.mul_nt);
-        pf_n0 = (pf_tile - pm * p.n_tiles) * BLOCK_N;
-        pf_m0 = (pm * CG + int(rank)) * Cfg::BLOCK_M;
-        pf_live = min(N_CHUNKS, (p.Cout - pf_n0 + CHUNK - 1) / CHUNK);
-      }
-    };
-    auto pf_issue = [&]() {  // leader only: load the residual of chunk pf_g (if there is one) and advance the cursor
-      if (pf_wi >= n_walk) return;
-      const uint32_t rb = pf_g % Cfg::NBUF;
-      mbar_expect_tx(&res_full_bar[rb], Cfg::CHUNK_BYTES);
-      tma_load_2d(&tmRes, &res_full_bar[rb], ring + rb * Cfg::CHUNK_BYTES, pf_n0 + pf_c * CHUNK, pf_m0 + pf_sub * 128);
-      ++pf_g;
-      if (++pf_c == pf_live) {
-        pf_c = 0;
-        if (++pf_sub == MT) {
-          pf_sub = 0;
-          ++pf_wi;
-          pf_decode();
-        }
-      }
-    };
-    if (p.tma_store && use_res && leader) {
-      pf_decode();
-      for (int i = 0; i < Cfg::NBUF - 1; ++i) pf_issue();
-    }
+    // Residual tiles arrive by TMA in the ring buffers the results later leave from (store warp above); res_full_bar[b]
+    // completes when buffer b holds the residual of its next chunk -- or, without a residual, when it is free again.
     for (int wi = 0; wi < n_walk; ++wi, ++it) {
       const SkSeg sg = walk(wi);
       const int tile = sg.tile;
@@ -545,7 +614,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __threadfence();
           const float4* wsrc = reinterpret_cast<const float4*>(p.sk_ws) + (size_t)src * (BLOCK_N / 32) * 8 * 128;
 #pragma unroll 1
-          for (int c = hsel; c < BLOCK_N / 32; c += 2) {
+          for (int c = hsel; c < BLOCK_N / 32; c += ESPLIT) {
             uint32_t a[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -585,7 +654,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int dst = cl_id * CG + int(rank);
           float4* wdst = reinterpret_cast<float4*>(p.sk_ws) + (size_t)dst * (BLOCK_N / 32) * 8 * 128;
 #pragma unroll 1
-          for (int c = hsel; c < BLOCK_N / 32; c += 2) {
+          for (int c = hsel; c < BLOCK_N / 32; c += ESPLIT) {
             uint32_t a[32];
             tmem_ld_32x32(tmem_acc0 + uint32_t(c * 32), a);
             tmem_ld_wait();
@@ -608,19 +677,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
 
       if (p.tma_store) {
+        // The chunks of a tile (MT sub-tiles x `live` chunks) are walked with the TMEM load issued ONE CHUNK AHEAD of its use:
+        // TMEM reads run at ~64 B/clk per SM (a 128 x 64 fp32 chunk: ~512 cycles) and the chunk's arithmetic needs about
+        // as many issue slots, so with load and arithmetic in lock step (all warps meet at the barrier of every chunk) a
+        // chunk took their SUM (~950 cycles, harness trace); overlapped it takes the larger of the two.
+        const int nchunk = MT * live;
+        uint32_t nx[32];
+        if constexpr (HALF == 32) tmem_ld_32x32(tmem_acc0 + uint32_t(hsel * HALF), nx);
+        else tmem_ld_32x16(tmem_acc0 + uint32_t(hsel * HALF), nx);
+        int sub = 0, c = 0;
 #pragma unroll 1
-        for (int sub = 0; sub < MT; ++sub) {
-        const uint32_t tmem_acc = tmem_acc0 + uint32_t(sub * BLOCK_N);
-        for (int c = 0; c < live; ++c, ++chunk_ctr) {
+        for (int ci = 0; ci < nchunk; ++ci, ++chunk_ctr) {
           const uint32_t bsel = chunk_ctr % Cfg::NBUF;
           uint32_t a[32];
-          if constexpr (HALF == 32) {
-            tmem_ld_32x32(tmem_acc + uint32_t(c * CHUNK + hsel * 32), a);
-          } else {
-            tmem_ld_32x16(tmem_acc + uint32_t(c * CHUNK + hsel * 16), a);
+          // harness trace: the leader's stamps inside the first 5 chunks of the CTA's first tile
+          unsigned long long* const fs = (tr && wi == 0 && ci < 5 && leader) ? tr + kTraceFine + 5 * ci : nullptr;
+          if (fs) fs[0] = clock64();
+          if constexpr (HALF == 32) tmem_ld_wait_dep32(nx);
+          else tmem_ld_wait_dep16(nx);
+          if (fs) fs[1] = clock64();
+#pragma unroll
+          for (int i = 0; i < HALF; ++i) a[i] = nx[i];
+          int c2 = c + 1, sub2 = sub;
+          if (c2 == live) {
+            c2 = 0;
+            ++sub2;
           }
-          tmem_ld_wait();
-          if (c == live - 1 && sub == MT - 1) {  // accumulators fully read: hand them back to the MMA warp
+          if (ci + 1 < nchunk) {
+            if constexpr (HALF == 32) tmem_ld_32x32(tmem_acc0 + uint32_t(sub2 * BLOCK_N + c2 * CHUNK + hsel * HALF), nx);
+            else tmem_ld_32x16(tmem_acc0 + uint32_t(sub2 * BLOCK_N + c2 * CHUNK + hsel * HALF), nx);
+          } else {  // accumulators fully read (the wait above covered the last load): hand them back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -629,24 +715,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           uint8_t* buf = ring + bsel * Cfg::CHUNK_BYTES;
-          if (use_res) {
-            mbar_wait(&res_full_bar[bsel], (chunk_ctr / Cfg::NBUF) & 1);
-          } else {
-            if (leader) bulk_wait_group_read<Cfg::NBUF - 1>();  // the store that used this buffer NBUF chunks ago has read it
-            bar_sync_named(1, Cfg::EPI_THREADS);
-          }
+          mbar_wait(&res_full_bar[bsel], (chunk_ctr / Cfg::NBUF) & 1);  // residual landed / buffer free (store warp)
+          if (fs) fs[2] = clock64();
           epi_dispatch<Cfg::OUT_SWZ, HALF>(p.act, p.res_mode, a, bias_s + c * CHUNK + hsel * HALF, buf, row_l, hsel * (HALF / 8));
+          if (fs) fs[3] = clock64();
           fence_proxy_async_smem();
-          bar_sync_named(1, Cfg::EPI_THREADS);
-          if (leader) {
-            tma_store_2d(&tmOut, buf, n0 + c * CHUNK, m0 + sub * 128);
-            bulk_commit_group();
-            if (use_res) {
-              bulk_wait_group_read<1>();  // every store but the one just committed has read its buffer
-              pf_issue();
-            }
-          }
-        }
+          bar_arrive_named(2 + int(bsel), Cfg::EPI_THREADS + 32);  // no waiting: the store warp takes it from here
+          if (fs) fs[4] = clock64();
+          c = c2;
+          sub = sub2;
         }
       } else if (p.staged_store) {
         if constexpr (MT != 1) __trap();  // 256-pixel tiles are planned for TMA-store layers only
@@ -662,11 +739,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < live; ++c, ++chunk_ctr) {
           const uint32_t bsel = chunk_ctr % Cfg::NBUF;
           uint32_t a[32];
-          if constexpr (HALF == 32) {
-            tmem_ld_32x32(tmem_acc + uint32_t(c * CHUNK + hsel * 32), a);
-          } else {
-            tmem_ld_32x16(tmem_acc + uint32_t(c * CHUNK + hsel * 16), a);
-          }
+          if constexpr (HALF == 32) tmem_ld_32x32(tmem_acc + uint32_t(c * CHUNK + hsel * HALF), a);
+          else tmem_ld_32x16(tmem_acc + uint32_t(c * CHUNK + hsel * HALF), a);
           tmem_ld_wait();
           if (c == live - 1) {  // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
@@ -743,12 +817,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
 #pragma unroll 1
-        for (int c = hsel; c < live32; c += 2) {
+        for (int c = hsel; c < live32; c += ESPLIT) {
           const int ch0 = n0 + c * 32;
           uint32_t a[32];
           tmem_ld_32x32(tmem_acc + uint32_t(c * 32), a);
           tmem_ld_wait();
-          if (c + 2 >= live32) {  // this warp's last chunk of the tile
+          if (c + ESPLIT >= live32) {  // this warp's last chunk of the tile
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -870,7 +944,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (tr && wi < kTraceTiles && leader) tr[5 + 4 * wi] = clock64();
     }
-    if (leader) bulk_wait_group_read<0>();  // smem must stay valid until the last TMA store has read it
   }
 
   tc_fence_before();

@@ -18,6 +18,7 @@ buffers (bp_net_create(share_buffers_with=...)) and a mixed batch is processed s
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -398,7 +399,7 @@ class PipelinedEngine:
             # stream already works on step j + 1 (resize, detector, ...): the tail is off the critical path of the lane.
             # Consecutive steps of a lane alternate between the engine's two small-tensor sets; the main part of step j + 2
             # waits for the tail of step j.
-            self.async_tail = bool(async_tail)
+            self.async_tail = bool(async_tail) and os.environ.get("BP_ASYNC_TAIL", "1") != "0"  # env: experiment switch
             self.tail_streams = [torch.cuda.Stream(priority=-1) for _ in engines] if self.async_tail else [None] * len(engines)
             self._ev_main = [[torch.cuda.Event() for _ in range(2)] for _ in engines]
             self._ev_tail = [[torch.cuda.Event() for _ in range(2)] for _ in engines]

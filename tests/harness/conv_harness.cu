@@ -270,6 +270,27 @@ static int run_case(const Case& cs) {
       }
       maxtiles = std::max(maxtiles, tiles);
     }
+    {  // stamps inside the first chunks of the first tile: an epilogue thread (thread 64) and the store warp
+      for (int k = 0; k < 5; ++k) {
+        double d[8] = {};
+        long cnt = 0;
+        for (int c = 0; c < pl.grid; ++c) {
+          const unsigned long long* t = tr.data() + (size_t)c * kTraceSlots + kTraceFine;
+          const unsigned long long *q = t + 5 * k, *w = t + 25 + 3 * k;
+          if (!q[0] || !q[4] || !w[0] || !w[2]) continue;
+          ++cnt;
+          for (int e = 0; e < 4; ++e) d[e] += double(q[e + 1] - q[e]);
+          if (k > 0 && (q - 5)[4]) d[4] += double(q[0] - (q - 5)[4]);
+          d[5] += double((long long)(w[0] - q[4]));  // arrive -> store warp released
+          d[6] += double(w[1] - w[0]);
+          d[7] += double(w[2] - w[1]);
+        }
+        if (cnt)
+          printf("    chunk %d of tile 0 (%ld CTAs): epilogue thread: loop top %.0f | TMEM wait %.0f | next load + buffer wait %.0f | math + st.shared %.0f | fence + arrive %.0f"
+                 " || store warp: released %.0f after that arrive | store + commit %.0f | wait_group.read + hand-on %.0f\n",
+                 k, cnt, d[4] / cnt, d[0] / cnt, d[1] / cnt, d[2] / cnt, d[3] / cnt, d[5] / cnt, d[6] / cnt, d[7] / cnt);
+      }
+    }
     if (nc && nt)
       printf("    trace: CTAs %ld, tiles/CTA max %ld | CTA active cycles mean %.0f max %.0f | start->first k-block %.0f | per tile: wait for first k-block %.0f, "
              "main loop %.0f (%.0f per k-block), epilogue %.0f | tile period %.0f | MMA warp blocked on epilogue %.0f\n",
