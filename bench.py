@@ -768,7 +768,7 @@ def ours_arm(args):
                 "how": "conv FLOPs of one step / time per step of both networks replayed as CUDA graphs the way the step runs them "
                        f"({len(pipe.lanes)} lanes in flight, CUDA events around {2 * reps if len(pipe.lanes) > 1 else reps} passes); *_one_lane: a single lane alone",
                 "aux_ms_per_op_events": t_aux * 1e3, "traffic": traffic,
-                "traffic_source": "profiles/conv_dram_traffic.json <- profiles/r02_counters_b64.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" if traffic else None}
+                "traffic_source": "profiles/conv_dram_traffic.json <- profiles/r03_counters_b64.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" if traffic else None}
         slow = sorted(prof, key=lambda p: -p["ms"])[:8]
         extra["top_ops"] = [{"op": f"{p['net']}[{p['i']}] {p['desc']}", "ms": round(p["ms"], 4),
                              "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["flops"] else None,

@@ -8,12 +8,16 @@
 // same time share A rows in L2 and all share the weights).
 //   warp 0    : TMA producer (A + B per k-block into a STAGES-deep mbarrier ring; warp-uniform loop, elect.sync issue)
 //   warp 1    : MMA issuer (warp-uniform loop, elect.sync issue) + TMEM owner
-//   warps 2-9 : epilogue.  tcgen05.ld -> bias + activation (+ residual) -> fp16 -> swizzled smem staging ->
-//               TMA store (cp.async.bulk.tensor), 64 output channels at a time; the residual arrives by TMA in the
-//               same ring buffers, prefetched NBUF - 1 chunks ahead across tile boundaries.  The epilogue of tile i
-//               overlaps the main loop of tile i+1 through the second TMEM accumulator.
-//   Stores that are not a dense [pixels, channels] box (fp32 heads, fused nearest-x2 upsample, fused PixelShuffle)
-//   go out as per-thread 16-byte stores instead.
+//   warps 2-9 : epilogue.  tcgen05.ld (issued one chunk ahead of its use) -> bias + activation (+ residual) -> fp16 ->
+//               swizzled smem staging, 64 output channels at a time, then an ARRIVE on the chunk's named barrier -- the
+//               epilogue warps never wait for a store.  The epilogue of tile i overlaps the main loop of tile i+1 through
+//               the second TMEM accumulator.
+//   warp 10   : store warp.  Waits on the chunk's named barrier, issues the TMA store (cp.async.bulk.tensor), and hands
+//               the ring buffer of the PREVIOUS chunk on as soon as its store has read it: by loading the residual tile of
+//               the chunk that will use it next (TMA, NBUF - 1 chunks ahead across tile boundaries), or, without a
+//               residual, by a plain arrive on the same mbarrier.
+//   Stores that are not a dense [pixels, channels] box go out as per-thread stores (fp32 heads) or, for the fused
+//   nearest-x2 upsample / PixelShuffle, staged through the same ring and written row-wise coalesced.
 // Variants (template parameters): CG = 2 runs CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256, each CTA stages
 // half of B); MT = 2 gives a CTA 256-pixel tiles (two M = 128 MMAs per K step against one B tile) for narrow layers.
 // Launched with programmatic stream serialisation: griddepcontrol.wait sits after the set-up.
@@ -155,11 +159,9 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + BAR_BYTES;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
   static constexpr int TMEM_COLS = 2 * MT * BLOCK_N;
-  // EPI_SPLIT warps share a TMEM lane quarter, each takes EPI_COLS = 16 columns of every chunk.  Four per quarter for the
-  // 64-channel chunks (16 epilogue warps, four per scheduler): the epilogue of a chunk is a ~130-instruction dependent chain
-  // per warp (TMEM load, bias, residual, activation, pack, swizzled store, barrier), and with two warps per scheduler it ran
-  // at ~1 070 cycles per chunk -- as long as the four k-blocks of a 1x1 256->1024 tile take (harness trace, round 2: those
-  // layers were bound by the epilogue, and every launch ends with one exposed epilogue).
+  // EPI_SPLIT warps share a TMEM lane quarter, each takes EPI_COLS columns of every chunk: two per quarter (8 epilogue warps,
+  // 32 columns each).  Four per quarter (-DBP_EPI_WARPS=16) shorten an isolated tile's epilogue by ~10 % but cost the
+  // whole step 3 %: a 608-thread CTA holds 58 K registers and the other lane's PnP CTAs (16 K) no longer fit beside it.
 #ifndef BP_EPI_WARPS
 #define BP_EPI_WARPS 8
 #endif
@@ -677,10 +679,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
 
       if (p.tma_store) {
-        // The chunks of a tile (MT sub-tiles x `live` chunks) are walked with the TMEM load issued ONE CHUNK AHEAD of its use:
-        // TMEM reads run at ~64 B/clk per SM (a 128 x 64 fp32 chunk: ~512 cycles) and the chunk's arithmetic needs about
-        // as many issue slots, so with load and arithmetic in lock step (all warps meet at the barrier of every chunk) a
-        // chunk took their SUM (~950 cycles, harness trace); overlapped it takes the larger of the two.
+        // The chunks of a tile (MT sub-tiles x `live` chunks) are walked with the TMEM load issued ONE CHUNK AHEAD of its use, so
+        // the wait at the top of a chunk finds its data there (harness trace: ~25 cycles).  A chunk costs ~1 000 cycles of a
+        // warp's time whatever is moved around in it -- short dependent chains (bias -> add -> pack -> st.shared -> fence ->
+        // arrive) on two warps per scheduler -- so a 128 x 256 tile drains in ~4 000 cycles: as long as 8 k-blocks of its
+        // main loop.  Layers with K <= 512 are therefore bounded by this epilogue, and every launch ends with one exposed.
         const int nchunk = MT * live;
         uint32_t nx[32];
         if constexpr (HALF == 32) tmem_ld_32x32(tmem_acc0 + uint32_t(hsel * HALF), nx);

@@ -439,6 +439,9 @@ class PipelinedEngine:
                 # first step of this lane at this batch size: capture the graphs of BOTH small-tensor sets now (the other
                 # set's main + tail run once on the same frames), so that no later step pays for a capture
                 self._primed[i].add(n)
+                # (both sets are written here: the tails of the lane's earlier steps -- other batch sizes -- must be done with them)
+                lane_stream.wait_event(self._ev_tail[i][0])
+                lane_stream.wait_event(self._ev_tail[i][1])
                 with torch.cuda.stream(lane_stream):
                     eng.run_device(n, graph=True, parts="main", parity=par ^ 1)
                     eng.run_device(n, graph=True, parts="tail", parity=par ^ 1)

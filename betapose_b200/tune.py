@@ -38,11 +38,49 @@ def time_op(net, batch: int, i: int, reps: int = 12) -> float:
     return float(np.median([a.elapsed_time(b) for a, b in ev][2:]))
 
 
-def tune_net(net, batch: int, margin: float = 0.03, reps: int = 12, log=None) -> dict:
+def time_op_sustained(net, batch: int, i: int, dur_s: float = 0.25, per_graph: int = 40) -> float:
+    """device time (ms) per launch of op i launched back to back for about `dur_s` seconds (a CUDA graph of `per_graph`
+    launches replayed).  On a power-capped GPU this is what a launch costs inside a long-running stream: the clock settles
+    where the layer's power draw meets the cap, so the figure ranks configurations by ENERGY per launch, not by cycles at
+    the boost clock -- a burst measurement (time_op) favours the configuration with the fewest cycles even when it moves
+    more bytes per flop and therefore runs at a lower sustained clock."""
+    if i > 0:
+        net.forward(batch, i - 1, i)
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        net.forward(batch, i, i + 1)
+    st.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        for _ in range(per_graph):
+            net.forward(batch, i, i + 1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    t1 = a.elapsed_time(b) / per_graph  # ms per launch, cold clocks
+    n = max(2, int(dur_s * 1e3 / max(t1, 1e-3) / per_graph))
+    for _ in range(max(1, n // 3)):  # let the clock settle
+        g.replay()
+    a.record()
+    for _ in range(n):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / (n * per_graph)
+
+
+def tune_net(net, batch: int, margin: float = 0.03, reps: int = 12, log=None, timer=None) -> dict:
     """-> {shape_key: {"cfg": [bn, cg, mt], "ms": best, "default": [bn, cg, mt], "default_ms": ...}} for the convolutions
     where a measured configuration beats the planner's by more than `margin`.  Leaves the winners applied to `net`."""
     net.forward(batch)
     torch.cuda.synchronize()
+    if timer is not None:  # e.g. time_op_sustained
+        time_op_ = lambda net_, batch_, i_, reps_: timer(net_, batch_, i_)  # noqa: E731
+    else:
+        time_op_ = time_op
     table: dict = {}
     seen: dict = {}
     for i in range(net.num_ops):
@@ -56,13 +94,13 @@ def tune_net(net, batch: int, margin: float = 0.03, reps: int = 12, log=None) ->
             continue
         net.set_op_config(i, batch, 0, 0, 0)
         d_cfg = net.op_config(i, batch)[:3]
-        d_ms = time_op(net, batch, i, reps)
+        d_ms = time_op_(net, batch, i, reps)
         best, best_ms = None, d_ms
         for cand in CANDIDATES:
             if tuple(cand) == tuple(d_cfg) or not net.set_op_config(i, batch, *cand):
                 continue
             try:
-                ms = time_op(net, batch, i, reps)
+                ms = time_op_(net, batch, i, reps)
             except Exception:
                 continue
             if ms < best_ms:
@@ -70,9 +108,9 @@ def tune_net(net, batch: int, margin: float = 0.03, reps: int = 12, log=None) ->
         if best is not None and best_ms < (1.0 - margin) * d_ms:
             # confirm against the default once more (the first sample of a layer sometimes carries a clock ramp)
             net.set_op_config(i, batch, 0, 0, 0)
-            d2 = time_op(net, batch, i, reps)
+            d2 = time_op_(net, batch, i, reps)
             net.set_op_config(i, batch, *best)
-            b2 = time_op(net, batch, i, reps)
+            b2 = time_op_(net, batch, i, reps)
             if b2 < (1.0 - margin) * d2:
                 table[key] = {"cfg": list(best), "ms": round(b2, 5), "default": list(d_cfg), "default_ms": round(d2, 5)}
                 seen[key] = best
