@@ -12,10 +12,10 @@
 //               swizzled smem staging, 64 output channels at a time, then an ARRIVE on the chunk's named barrier -- the
 //               epilogue warps never wait for a store.  The epilogue of tile i overlaps the main loop of tile i+1 through
 //               the second TMEM accumulator.
-//   warp 10   : store warp.  Waits on the chunk's named barrier, issues the TMA store (cp.async.bulk.tensor), and hands
-//               the ring buffer of the PREVIOUS chunk on as soon as its store has read it: by loading the residual tile of
-//               the chunk that will use it next (TMA, NBUF - 1 chunks ahead across tile boundaries), or, without a
-//               residual, by a plain arrive on the same mbarrier.
+//   warp 10   : store warp.  Waits on the chunk's named barrier, issues the TMA store (cp.async.bulk.tensor), waits until
+//               the store has read the ring buffer and hands the buffer on at once: by loading the residual tile of the
+//               chunk that will use it next (TMA, NBUF chunks ahead across tile boundaries), or, without a residual, by a
+//               plain arrive on the same mbarrier.
 //   Stores that are not a dense [pixels, channels] box go out as per-thread stores (fp32 heads) or, for the fused
 //   nearest-x2 upsample / PixelShuffle, staged through the same ring and written row-wise coalesced.
 // Variants (template parameters): CG = 2 runs CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256, each CTA stages
@@ -494,8 +494,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == Cfg::STORE_WARP) {
     // ------------------------------------------------------------ store warp (TMA-stored layers).  The epilogue warps stage
     // a chunk in ring buffer g % NBUF and ARRIVE on named barrier 2 + g % NBUF without waiting; this warp waits there,
-    // stores the chunk (cp.async.bulk.tensor, one thread: bulk groups are per thread) and, as soon as the previous store
-    // has read its buffer, hands that buffer on: with a residual by loading the residual tile of the chunk that will use
+    // stores the chunk (cp.async.bulk.tensor, one thread: bulk groups are per thread) and, as soon as that store
+    // has read its buffer, hands the buffer on: with a residual by loading the residual tile of the chunk that will use
     // it next (TMA, completes res_full_bar), without one by a plain arrive on the same mbarrier ("buffer free").  So the
     // store issue, the commit and wait_group.read (~250-450 cycles per chunk when an epilogue thread did them between
     // two barriers of all epilogue warps: harness trace) are off the epilogue's critical path.
@@ -533,9 +533,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
       if (use_res) {
-        // the prefetch cursor runs NBUF - 1 chunks ahead of the chunk being stored, across tile boundaries
+        // the prefetch cursor runs NBUF chunks ahead of the chunk being stored, across tile boundaries
         pf_decode();
-        for (int i = 0; i < Cfg::NBUF - 1; ++i) pf_issue();
+        for (int i = 0; i < Cfg::NBUF; ++i) pf_issue();
       } else if (lane == 0) {
         for (int b = 0; b < Cfg::NBUF; ++b) mbar_arrive(&res_full_bar[b]);  // every buffer starts out free
       }
@@ -559,19 +559,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_store_2d(&tmOut, ring + bsel * Cfg::CHUNK_BYTES, n0 + c * CHUNK, m0 + sub * 128);
               bulk_commit_group();
               if (ss) ss[1] = clock64();
-              bulk_wait_group_read<1>();  // every store but the one just committed has read its buffer
+              // This warp has nothing else to do: it waits until the store has read the buffer (a few hundred cycles) and
+              // hands the SAME buffer on at once -- the residual of chunk g + NBUF is then under way a whole chunk time
+              // earlier than if the hand-over waited for the next store's commit (a buffer is busy from the issue of its
+              // residual load to the end of its store's read, ~3 000 cycles: with 3-4 buffers every cycle of lead counts).
+              bulk_wait_group_read<0>();
             }
             __syncwarp();
             if (use_res) {
-              pf_issue();  // into the buffer of chunk g - 1 (the first one: into the still unused last buffer)
-            } else if (g >= 1 && lane == 0) {
-              mbar_arrive(&res_full_bar[(g - 1) % Cfg::NBUF]);
+              pf_issue();  // chunk g + NBUF into buffer g % NBUF
+            } else if (lane == 0) {
+              mbar_arrive(&res_full_bar[bsel]);
             }
             if (ss) ss[2] = clock64();
           }
         }
       }
-      if (lane == 0) bulk_wait_group_read<0>();  // smem must stay valid until the last TMA store has read it
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2 .. 2 + EPI_WARPS - 1)
