@@ -538,33 +538,37 @@ class PipelinedEngine:
                     self._step(i, streams[i], n, graph, after_step, self._rec_host[i][h], ev_done[i][h])
                 pending.append((i, h, n, idx0))
 
-            while True:
-                while not exhausted and len(pending) < L:
-                    try:
-                        nxt = next(it)           # host work (frame decoding, ...) overlaps the GPU
-                    except StopIteration:
-                        exhausted = True
-                        break
-                    launch(nxt, k, idx0)
-                    idx0 += int(torch.as_tensor(nxt).shape[0])
-                    k += 1
-                if not pending:
-                    break
-                i, h, n, first = pending.popleft()
-                # keep the pipe full while the oldest batch finishes: the next batch of this lane can be fetched and uploaded now
-                if not exhausted and len(pending) < L:
-                    try:
-                        nxt = next(it)
+            try:
+                while True:
+                    while not exhausted and len(pending) < L:
+                        try:
+                            nxt = next(it)           # host work (frame decoding, ...) overlaps the GPU
+                        except StopIteration:
+                            exhausted = True
+                            break
                         launch(nxt, k, idx0)
                         idx0 += int(torch.as_tensor(nxt).shape[0])
                         k += 1
-                    except StopIteration:
-                        exhausted = True
-                ev_done[i][h].synchronize()
-                out = stages.records_to_numpy(self._rec_host[i][h][:n]).copy()
-                out["image_index"] = first + np.arange(n)
-                yield out
-            if cur is not None:
+                    if not pending:
+                        break
+                    i, h, n, first = pending.popleft()
+                    # keep the pipe full while the oldest batch finishes: the next batch of this lane can be fetched and uploaded now
+                    if not exhausted and len(pending) < L:
+                        try:
+                            nxt = next(it)
+                            launch(nxt, k, idx0)
+                            idx0 += int(torch.as_tensor(nxt).shape[0])
+                            k += 1
+                        except StopIteration:
+                            exhausted = True
+                    ev_done[i][h].synchronize()
+                    out = stages.records_to_numpy(self._rec_host[i][h][:n]).copy()
+                    out["image_index"] = first + np.arange(n)
+                    yield out
+            finally:
+                # also when the consumer abandons the stream early (generator closed): whatever is still in flight on the lane
+                # and tail streams is ordered before the caller's next work on its own stream (e.g. a plain run() afterwards,
+                # which uses small-tensor set 0 on the caller's stream)
                 for s in streams + [t for t in self.tail_streams if t is not None]:
                     if s is not cur:
                         cur.wait_stream(s)

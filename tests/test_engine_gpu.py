@@ -699,3 +699,18 @@ def test_async_tail_many_steps_and_sync_tail_agree(yolo_stream, kpd_sd, kp_model
         for f in want[k].dtype.names:
             if f != "image_index":
                 assert np.array_equal(g[f], want[k][f]), (k, f)
+
+
+def test_run_stream_abandoned_early_then_plain_run(engine, frames8):
+    """A consumer that stops pulling records while batches are still in flight (lane and tail streams busy) and then makes a
+    plain per-batch call: the generator's clean-up orders the in-flight work before the caller's stream, so the plain call --
+    which shares the engine's buffers and small-tensor set 0 -- returns what it always returns."""
+    want = engine.run(frames8[2:6]).copy()
+    batches = [frames8[0:4], frames8[4:8], frames8[1:5], frames8[3:7], frames8[0:4]]
+    gen = engine.run_stream(iter(batches), graph=True)
+    first = next(gen)
+    assert len(first) == 4
+    gen.close()  # two more batches are in flight
+    got = engine.run(frames8[2:6])
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f]), f
